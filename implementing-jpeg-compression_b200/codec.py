@@ -1,0 +1,274 @@
+"""Host side of the B200 codec path: the reference's band/image API over libjpegb200.so.
+
+Drop-in surface (same names and meaning as the reference):
+
+* ``compress_band(a, config) -> bytes``            pipeline/__init__.py:71-76
+* ``decompress_band(data, config) -> ndarray``     pipeline/__init__.py:79-88
+* ``Jpeg(config).compress(image) -> bytes`` / ``Jpeg.decompress(bytes) -> image``
+                                                   pipeline/__init__.py:98-124
+
+plus the batched, device-resident calls the reference does not have
+(``compress_planes`` / ``decompress_planes``), which is what the benchmark and a
+production caller use.  PyTorch is only the buffer carrier (device memory, the
+current stream); every byte of codec work happens in the CUDA kernels.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib, file_format
+from .config import Configuration, QuantizationMethod  # noqa: F401  (re-exported)
+from .errors import (BadArrayShapeError, BadQuantizationError, BadRleCodeError, BadStreamError,
+                     EmptyArrayError, NativeLibraryError)
+
+
+def _raise_for_code(code, detail_word=None):
+    """Map a C-ABI code to the reference's exception types."""
+    if code == _lib.JB_OK:
+        return
+    if code == _lib.JB_ERR_BAD_QUANTIZATION:
+        raise BadQuantizationError()
+    if code == _lib.JB_ERR_EMPTY_ARRAY:
+        raise EmptyArrayError()
+    if code == _lib.JB_ERR_BAD_RLE_CODE:
+        msg = ""
+        if detail_word is not None and detail_word != 0xFFFFFFFFFFFFFFFF:
+            run = (detail_word >> 20) & 15
+            amp = (detail_word & 0xFFFFF) - (1 << 19)
+            size = abs(amp).bit_length() + 1
+            msg = "({}, {}, {})".format(run, size, amp)      # util.py:163
+        raise BadRleCodeError(msg)
+    if code == _lib.JB_ERR_BAD_STREAM:
+        raise BadStreamError(_lib.strerror(code))
+    if code == _lib.JB_ERR_UNSUPPORTED:
+        raise NotImplementedError("libjpegb200: " + _lib.strerror(code))
+    if code in (_lib.JB_ERR_BAD_PARAM, _lib.JB_ERR_OUT_CAPACITY, _lib.JB_ERR_WORKSPACE):
+        raise ValueError("libjpegb200: " + _lib.strerror(code))
+    raise NativeLibraryError("libjpegb200: %s (%d)" % (_lib.strerror(code), code))
+
+
+def _require_cuda(device=None):
+    if not torch.cuda.is_available():
+        raise NativeLibraryError("no CUDA device: the codec path runs only on the GPU (no CPU fallback)")
+    return torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def geometry(config):
+    """Derived sizes of one band as a dict (run_length_encoding.py:80-88)."""
+    p = config.c_params()
+    g = _lib.jb_geometry()
+    _raise_for_code(_lib.load().jb_geometry_of(ctypes.byref(p), ctypes.byref(g)))
+    return {k: getattr(g, k) for k, _ in g._fields_ if k != "reserved"}
+
+
+class CompressedPlanes:
+    """Result of ``compress_planes``: device buffer + device offsets; nothing has been
+    copied to the host yet."""
+
+    def __init__(self, data, offsets, status, n_planes):
+        self.data = data            # uint8 [capacity] on device; streams concatenated in plane order
+        self.offsets = offsets      # int64 [n_planes + 1] on device
+        self.status = status        # int64 [4] on device
+        self.n_planes = n_planes
+        self._host_offsets = None
+
+    def check(self):
+        """Synchronise with the producing stream and raise if the device reported an error."""
+        st = self.status.cpu()
+        code = int(st[0].item())
+        if code:
+            _raise_for_code(-code, int(st[1].item()) & 0xFFFFFFFFFFFFFFFF)
+        return self
+
+    def host_offsets(self):
+        if self._host_offsets is None:
+            self.check()
+            self._host_offsets = self.offsets.cpu().numpy().astype(np.int64)
+        return self._host_offsets
+
+    def total_bytes(self):
+        return int(self.host_offsets()[-1])
+
+    def to_bytes_list(self):
+        """One ``bytes`` per plane, in plane order (what compress_band returns)."""
+        off = self.host_offsets()
+        total = int(off[-1])
+        host = self.data[:total].cpu().numpy().tobytes() if total else b""
+        return [host[int(off[i]):int(off[i + 1])] for i in range(self.n_planes)]
+
+
+class _Workspace:
+    """Grow-only cache of device scratch buffers, one set per device (the library itself
+    allocates nothing)."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def get(self, key, nbytes, device):
+        k = (key, device.index)
+        t = self._bufs.get(k)
+        if t is None or t.numel() < nbytes:
+            t = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+            self._bufs[k] = t
+        return t
+
+
+_workspace = _Workspace()
+
+
+def compress_planes(planes, config, flags=0, out=None):
+    """Compress a batch of equally sized planes that already live on the GPU.
+
+    ``planes``: uint8 CUDA tensor [n, H, W] (or [H, W]); rows contiguous.  Returns a
+    ``CompressedPlanes`` whose buffers stay on the device; the call is asynchronous on the
+    current stream.  Replaces ``compress_band`` applied to each plane in turn."""
+    lib = _lib.load()
+    if planes.dim() == 2:
+        planes = planes.unsqueeze(0)
+    if planes.dim() != 3:
+        raise BadArrayShapeError(tuple(planes.shape))
+    if planes.dtype != torch.uint8 or not planes.is_cuda:
+        raise TypeError("compress_planes expects a uint8 CUDA tensor")
+    n, h, w = planes.shape
+    if h == 0 or w == 0 or n == 0:
+        raise EmptyArrayError()
+    if planes.stride(2) != 1:
+        planes = planes.contiguous()
+    if (h, w) != (config.height, config.width):
+        # the reference takes the geometry from the array; keep the two in agreement
+        raise ValueError("plane is %dx%d but config says %dx%d" % (h, w, config.height, config.width))
+    dev = planes.device
+    p = config.c_params(flags)
+    cap = lib.jb_max_stream_bytes(ctypes.byref(p), n)
+    if cap == 0:
+        g = _lib.jb_geometry()
+        _raise_for_code(lib.jb_geometry_of(ctypes.byref(p), ctypes.byref(g)))
+    ws_bytes = lib.jb_compress_workspace_bytes(ctypes.byref(p), n)
+    with torch.cuda.device(dev):
+        ws = _workspace.get("fwd", ws_bytes, dev)
+        if out is None:
+            out = torch.empty(cap, dtype=torch.uint8, device=dev)
+        offsets = torch.empty(n + 1, dtype=torch.int64, device=dev)
+        status = torch.empty(_lib.JB_STATUS_WORDS, dtype=torch.int64, device=dev)
+        rc = lib.jb_compress_planes(_ptr(planes), planes.stride(0) if n > 1 else h * planes.stride(1),
+                                    planes.stride(1), n, ctypes.byref(p), _ptr(out), out.numel(),
+                                    _ptr(offsets), _ptr(status), _ptr(ws), ws.numel(), _stream_ptr())
+    _raise_for_code(rc)
+    return CompressedPlanes(out, offsets, status, n)
+
+
+def decompress_planes(data, offsets, lengths, config, n_planes, in_bytes=None, flags=0, out=None):
+    """Decompress ``n_planes`` streams held in the device buffer ``data``.
+
+    ``offsets`` / ``lengths``: int64 CUDA tensors [n_planes].  ``in_bytes``: host-known upper
+    bound of the stream bytes in ``data`` (defaults to ``data.numel()``).  Returns
+    ``(planes uint8 [n, H, W] on device, status int64 [4] on device)``; asynchronous."""
+    lib = _lib.load()
+    dev = data.device
+    p = config.c_params(flags)
+    if in_bytes is None:
+        in_bytes = data.numel()
+    ws_bytes = lib.jb_decompress_workspace_bytes(ctypes.byref(p), n_planes, int(in_bytes))
+    if ws_bytes == 0:
+        g = _lib.jb_geometry()
+        _raise_for_code(lib.jb_geometry_of(ctypes.byref(p), ctypes.byref(g)))
+    h, w = int(config.height), int(config.width)
+    with torch.cuda.device(dev):
+        ws = _workspace.get("inv", ws_bytes, dev)
+        if out is None:
+            out = torch.empty((n_planes, h, w), dtype=torch.uint8, device=dev)
+        status = torch.empty(_lib.JB_STATUS_WORDS, dtype=torch.int64, device=dev)
+        rc = lib.jb_decompress_planes(_ptr(data), int(in_bytes), _ptr(offsets), _ptr(lengths), n_planes,
+                                      ctypes.byref(p), _ptr(out), out.stride(0), out.stride(1),
+                                      _ptr(status), _ptr(ws), ws.numel(), _stream_ptr())
+    _raise_for_code(rc)
+    return out, status
+
+
+def check_status(status):
+    st = status.cpu()
+    code = int(st[0].item())
+    if code:
+        _raise_for_code(-code, int(st[1].item()) & 0xFFFFFFFFFFFFFFFF)
+
+
+# ---- host-buffer entry points (the reference's signatures) --------------------------------------
+
+def _as_uint8_plane(a):
+    a = np.asarray(a)
+    if a.ndim != 2:
+        raise BadArrayShapeError()                       # util.py:27-28
+    if a.shape[0] == 0 or a.shape[1] == 0:
+        raise EmptyArrayError()                          # util.py:30-31
+    if a.dtype != np.uint8:
+        if np.iscomplexobj(a) or not np.all(a == np.round(a)) or a.min() < 0 or a.max() > 255:
+            raise ValueError("the CUDA codec path takes 8-bit samples (integers 0..255)")
+        a = a.astype(np.uint8)
+    return np.ascontiguousarray(a)
+
+
+def compress_band(a, config, flags=0):
+    """pipeline.compress_band (pipeline/__init__.py:71-76): 2-D integer array -> bytes."""
+    dev = _require_cuda()
+    a = _as_uint8_plane(a)
+    planes = torch.from_numpy(a).to(dev, non_blocking=False).unsqueeze(0)
+    res = compress_planes(planes, config, flags=flags)
+    return res.to_bytes_list()[0]
+
+
+def decompress_band(compression_result, config, flags=0):
+    """pipeline.decompress_band (pipeline/__init__.py:79-88): bytes -> (height, width) int array."""
+    planes = decompress_bands([compression_result], config, flags=flags)
+    return planes[0].astype(np.int64)
+
+
+def compress_bands(arrays, config, flags=0):
+    """compress_band for several equally sized planes in one launch; list of bytes."""
+    dev = _require_cuda()
+    stack = np.stack([_as_uint8_plane(a) for a in arrays])
+    planes = torch.from_numpy(stack).to(dev)
+    return compress_planes(planes, config, flags=flags).to_bytes_list()
+
+
+def decompress_bands(streams, config, flags=0):
+    """decompress_band for several streams in one launch; uint8 array [n, H, W] on the host."""
+    dev = _require_cuda()
+    streams = [bytes(s) for s in streams]
+    lens = np.array([len(s) for s in streams], dtype=np.int64)
+    offs = np.concatenate(([0], np.cumsum(lens)[:-1])).astype(np.int64)
+    blob = b"".join(streams)
+    data = torch.from_numpy(np.frombuffer(blob + b"\0" * 16, dtype=np.uint8).copy()).to(dev)
+    out, status = decompress_planes(data, torch.from_numpy(offs).to(dev), torch.from_numpy(lens).to(dev),
+                                    config, len(streams), in_bytes=len(blob), flags=flags)
+    check_status(status)
+    return out.cpu().numpy()
+
+
+class Jpeg:
+    """pipeline.Jpeg (pipeline/__init__.py:98-124) on the CUDA path: the three bands of an
+    image go through one batched launch each way; the container is the reference's."""
+
+    def __init__(self, config):
+        self.config = config
+
+    def compress(self, image):
+        bands = [np.asarray(b, dtype=np.uint8) for b in image.split()]   # y, cb, cr
+        y, cb, cr = compress_bands(bands, self.config)
+        return file_format.generate_data(self.config, file_format.CompressedData(y, cb, cr))
+
+    @staticmethod
+    def decompress(bytestream):
+        from PIL import Image
+        config, data = file_format.read_data(bytestream)
+        planes = decompress_bands([data.y, data.cb, data.cr], config)
+        # np.dstack(...).astype(np.uint8) -> Image.fromarray(mode='YCbCr'), :120-124
+        return Image.merge("YCbCr", [Image.fromarray(np.ascontiguousarray(planes[i]), "L") for i in range(3)])

@@ -1,0 +1,271 @@
+// jb_api.cu -- the extern "C" surface declared in include/jpegb200.h.
+#include <string.h>
+
+#include "jb_common.cuh"
+#include "jb_forward.cuh"
+#include "jb_inverse.cuh"
+
+#define JB_CUDA_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return jb_cuda_fail(_e); } while (0)
+
+static int jb_cuda_fail(cudaError_t e) {
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorNoKernelImageForDevice)
+        return JB_ERR_NO_DEVICE;
+    return JB_ERR_CUDA;
+}
+
+extern "C" int jb_version(void) { return JB_VERSION; }
+
+extern "C" const char* jb_strerror(int code) {
+    switch (code) {
+    case JB_OK: return "ok";
+    case JB_ERR_BAD_PARAM: return "bad parameter";
+    case JB_ERR_BAD_QUANTIZATION: return "bad quantization (BadQuantizationError)";
+    case JB_ERR_EMPTY_ARRAY: return "empty array (EmptyArrayError)";
+    case JB_ERR_UNSUPPORTED: return "dct_size or block_size beyond the supported range";
+    case JB_ERR_WORKSPACE: return "workspace too small";
+    case JB_ERR_OUT_CAPACITY: return "output buffer too small";
+    case JB_ERR_CUDA: return "CUDA runtime error";
+    case JB_ERR_BAD_RLE_CODE: return "amplitude does not fit a 15-bit size field (BadRleCodeError)";
+    case JB_ERR_BAD_STREAM: return "malformed stream";
+    case JB_ERR_NO_DEVICE: return "no usable CUDA device";
+    default: return "unknown error";
+    }
+}
+
+extern "C" int jb_geometry_of(const jb_params* p, jb_geometry* geo) {
+    JbGeom g;
+    int rc = jb_make_geom(p, &g);
+    if (rc != JB_OK) return rc;
+    if (!geo) return JB_ERR_BAD_PARAM;
+    geo->h1 = g.H1; geo->w1 = g.W1; geo->h2 = g.H2; geo->w2 = g.W2;
+    geo->vb = g.vb; geo->hb = g.hb;
+    geo->blocks_per_plane = g.nblocks;
+    geo->max_block_bytes = g.maxblk;
+    geo->chunks_per_plane = g.cpp;
+    geo->reserved = 0;
+    return JB_OK;
+}
+
+extern "C" size_t jb_max_stream_bytes(const jb_params* p, int n_planes) {
+    JbGeom g;
+    if (jb_make_geom(p, &g) != JB_OK || n_planes <= 0) return 0;
+    return (size_t)n_planes * (size_t)g.nblocks * (size_t)g.maxblk;
+}
+
+// ---- compress ----------------------------------------------------------------------------------
+struct JbFwdWs { size_t desc, ticket, total; };
+static JbFwdWs jb_fwd_ws(int d, size_t n_chunks) {
+    JbFwdWs w;
+    size_t o = jb_align_up(jb_table_layout(d).total, 256);
+    w.desc = o;   o += jb_align_up(n_chunks * 8, 256);
+    w.ticket = o; o += 256;
+    w.total = o;
+    return w;
+}
+
+extern "C" size_t jb_compress_workspace_bytes(const jb_params* p, int n_planes) {
+    JbGeom g;
+    if (jb_make_geom(p, &g) != JB_OK || n_planes <= 0) return 0;
+    return jb_fwd_ws(g.d, (size_t)n_planes * g.cpp).total;
+}
+
+extern "C" size_t jb_stage_pack_workspace_bytes(int n_planes, int blocks_per_plane, int dct_size) {
+    if (n_planes <= 0 || blocks_per_plane <= 0 || dct_size < 1 || dct_size > JB_MAX_DCT_SIZE) return 0;
+    size_t cpp = ((size_t)blocks_per_plane + JB_CHUNK - 1) / JB_CHUNK;
+    return jb_fwd_ws(dct_size, (size_t)n_planes * cpp).total;
+}
+
+static int jb_reset_status(uint64_t* d_status, cudaStream_t s) {
+    JB_CUDA_TRY(cudaMemsetAsync(d_status, 0, JB_STATUS_WORDS * sizeof(uint64_t), s));
+    JB_CUDA_TRY(cudaMemsetAsync(d_status + 1, 0xFF, sizeof(uint64_t), s));
+    return JB_OK;
+}
+
+static int jb_forward_common(int mode, const uint8_t* d_planes, size_t plane_stride, size_t row_pitch,
+                             int n_planes, const JbGeom& g, uint8_t* d_out, size_t out_cap,
+                             uint64_t* d_plane_off, uint64_t* d_status, int16_t* d_coeffs_out,
+                             const int32_t* d_coeffs_in, void* d_ws, size_t ws_bytes, cudaStream_t s) {
+    const size_t n_chunks = (size_t)n_planes * g.cpp;
+    if (n_chunks > 0x7FFFFFFFull) return JB_ERR_UNSUPPORTED;
+    JbFwdWs w = jb_fwd_ws(g.d, n_chunks);
+    if (!d_ws || ws_bytes < w.total) return JB_ERR_WORKSPACE;
+    if (((uintptr_t)d_ws & 255) != 0) return JB_ERR_BAD_PARAM;
+    char* ws = (char*)d_ws;
+    int rc = jb_reset_status(d_status, s);
+    if (rc != JB_OK) return rc;
+    JB_CUDA_TRY(cudaMemsetAsync(ws + w.desc, 0, w.total - w.desc, s));
+
+    JbFwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.g = g;
+    a.t = jb_tables_at(d_ws, g.d);
+    a.planes = d_planes; a.plane_stride = plane_stride; a.row_pitch = row_pitch;
+    a.n_planes = n_planes; a.n_chunks = (unsigned)n_chunks;
+    a.out = d_out; a.out_cap = out_cap;
+    a.plane_off = (unsigned long long*)d_plane_off;
+    a.status = (unsigned long long*)d_status;
+    a.desc = (unsigned long long*)(ws + w.desc);
+    a.ticket = (unsigned*)(ws + w.ticket);
+    a.coeffs_out = d_coeffs_out; a.coeffs_in = d_coeffs_in;
+    if (mode != 2) JB_CUDA_TRY(jb_launch_build_tables(g, a.t, s));
+    if (mode != 2 && !(g.flags & JB_FLAG_FORCE_GENERIC) && jb_fwd_fast_eligible(g))
+        JB_CUDA_TRY(jb_launch_fwd_fast(a, mode, s));
+    else
+        JB_CUDA_TRY(jb_launch_fwd_generic(a, mode, s));
+    return JB_OK;
+}
+
+extern "C" int jb_compress_planes(const uint8_t* d_planes, size_t plane_stride, size_t row_pitch, int n_planes,
+                                  const jb_params* p, uint8_t* d_out, size_t out_cap, uint64_t* d_plane_off,
+                                  uint64_t* d_status, void* d_ws, size_t ws_bytes, void* stream) {
+    JbGeom g;
+    int rc = jb_make_geom(p, &g);
+    if (rc != JB_OK) return rc;
+    if (!d_planes || !d_out || !d_plane_off || !d_status || n_planes <= 0) return JB_ERR_BAD_PARAM;
+    if (row_pitch < (size_t)g.W || plane_stride < row_pitch * (size_t)(g.H - 1) + (size_t)g.W) return JB_ERR_BAD_PARAM;
+    return jb_forward_common(0, d_planes, plane_stride, row_pitch, n_planes, g, d_out, out_cap, d_plane_off,
+                             d_status, nullptr, nullptr, d_ws, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int jb_stage_forward_coeffs(const uint8_t* d_planes, size_t plane_stride, size_t row_pitch, int n_planes,
+                                       const jb_params* p, int16_t* d_coeffs, uint64_t* d_status,
+                                       void* d_ws, size_t ws_bytes, void* stream) {
+    JbGeom g;
+    int rc = jb_make_geom(p, &g);
+    if (rc != JB_OK) return rc;
+    if (!d_planes || !d_coeffs || !d_status || n_planes <= 0) return JB_ERR_BAD_PARAM;
+    if (row_pitch < (size_t)g.W || plane_stride < row_pitch * (size_t)(g.H - 1) + (size_t)g.W) return JB_ERR_BAD_PARAM;
+    return jb_forward_common(1, d_planes, plane_stride, row_pitch, n_planes, g, nullptr, 0, nullptr, d_status,
+                             d_coeffs, nullptr, d_ws, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int jb_stage_pack(const int32_t* d_coeffs, int n_planes, int blocks_per_plane, int dct_size,
+                             uint8_t* d_out, size_t out_cap, uint64_t* d_plane_off, uint64_t* d_status,
+                             void* d_ws, size_t ws_bytes, void* stream) {
+    if (!d_coeffs || !d_out || !d_plane_off || !d_status || n_planes <= 0 || blocks_per_plane <= 0)
+        return JB_ERR_BAD_PARAM;
+    if (dct_size < 1) return JB_ERR_BAD_PARAM;
+    if (dct_size > JB_MAX_DCT_SIZE) return JB_ERR_UNSUPPORTED;
+    JbGeom g;
+    memset(&g, 0, sizeof(g));
+    g.d = dct_size; g.n = dct_size * dct_size; g.nblocks = blocks_per_plane;
+    g.maxblk = jb_max_block_bytes(g.n);
+    g.cpp = (blocks_per_plane + JB_CHUNK - 1) / JB_CHUNK;
+    g.bs = 1;
+    return jb_forward_common(2, nullptr, 0, 0, n_planes, g, d_out, out_cap, d_plane_off, d_status, nullptr,
+                             d_coeffs, d_ws, ws_bytes, (cudaStream_t)stream);
+}
+
+// ---- decompress --------------------------------------------------------------------------------
+extern "C" size_t jb_decompress_workspace_bytes(const jb_params* p, int n_planes, size_t in_bytes) {
+    JbGeom g;
+    if (jb_make_geom(p, &g) != JB_OK || n_planes <= 0) return 0;
+    return jb_dec_layout(g.d, n_planes, g.nblocks, in_bytes, jb_table_layout(g.d).total).total;
+}
+
+extern "C" size_t jb_stage_unpack_workspace_bytes(int n_planes, int blocks_per_plane, int dct_size, size_t in_bytes) {
+    if (n_planes <= 0 || blocks_per_plane <= 0 || dct_size < 1 || dct_size > JB_MAX_DCT_SIZE) return 0;
+    return jb_dec_layout(dct_size, n_planes, blocks_per_plane, in_bytes, jb_table_layout(dct_size).total).total;
+}
+
+static int jb_inverse_common(int mode, const uint8_t* d_in, size_t in_bytes, const uint64_t* d_plane_off,
+                             const uint64_t* d_plane_len, int n_planes, const JbGeom& g,
+                             uint8_t* d_planes_out, size_t plane_stride, size_t row_pitch,
+                             int16_t* d_coeffs_out, const int16_t* d_coeffs_in, uint64_t* d_status,
+                             void* d_ws, size_t ws_bytes, cudaStream_t s) {
+    const size_t n_chunks = (size_t)n_planes * g.cpp;
+    if (n_chunks > 0x7FFFFFFFull) return JB_ERR_UNSUPPORTED;
+    const size_t table_bytes = jb_table_layout(g.d).total;
+    if (!d_ws || ((uintptr_t)d_ws & 255) != 0) return JB_ERR_WORKSPACE;
+    char* ws = (char*)d_ws;
+    int rc = jb_reset_status(d_status, s);
+    if (rc != JB_OK) return rc;
+
+    JbInvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.g = g;
+    a.t = jb_tables_at(d_ws, g.d);
+    a.n_planes = n_planes; a.n_chunks = (unsigned)n_chunks;
+    a.planes_out = d_planes_out; a.plane_stride = plane_stride; a.row_pitch = row_pitch;
+    a.coeffs_out = d_coeffs_out; a.coeffs_in = d_coeffs_in;
+    a.status = (unsigned long long*)d_status;
+
+    if (mode != 2) {
+        JbDecLayout L = jb_dec_layout(g.d, n_planes, g.nblocks, in_bytes, table_bytes);
+        if (ws_bytes < L.total) return JB_ERR_WORKSPACE;
+        JbFrameArgs f;
+        memset(&f, 0, sizeof(f));
+        f.in = d_in;
+        f.plane_off = (const unsigned long long*)d_plane_off;
+        f.plane_len = (const unsigned long long*)d_plane_len;
+        f.n_planes = n_planes; f.n = g.n; f.nblocks = g.nblocks; f.maxblk = g.maxblk;
+        f.max_tiles = L.max_tiles; f.win_n = L.win_n;
+        f.tile_first = (unsigned*)(ws + L.tile_first);
+        f.block_start = (unsigned*)(ws + L.block_start);
+        f.tile_uniq = (unsigned*)(ws + L.tile_uniq);
+        f.tile_entry = (unsigned*)(ws + L.tile_entry);
+        f.tile_base = (unsigned*)(ws + L.tile_base);
+        f.tile_hops = (unsigned*)(ws + L.tile_hops);
+        f.tile_ncand = (unsigned*)(ws + L.tile_ncand);
+        f.win = (unsigned*)(ws + L.win);
+        f.cand_pos = (uint16_t*)(ws + L.cand_pos);
+        f.cand_next = (uint16_t*)(ws + L.cand_next);
+        f.status = (unsigned long long*)d_status;
+        // a stream that fails framing leaves block_start unwritten: make it deterministic
+        JB_CUDA_TRY(cudaMemsetAsync(f.block_start, 0xFF, (size_t)n_planes * g.nblocks * 4, s));
+        JB_CUDA_TRY(jb_launch_framing(f, s));
+        a.in = d_in;
+        a.plane_off = f.plane_off; a.plane_len = f.plane_len;
+        a.block_start = f.block_start;
+    } else if (ws_bytes < table_bytes) {
+        return JB_ERR_WORKSPACE;
+    }
+    if (mode != 1) JB_CUDA_TRY(jb_launch_build_tables(g, a.t, s));
+    if (mode != 1 && !(g.flags & JB_FLAG_FORCE_GENERIC) && jb_inv_fast_eligible(g))
+        JB_CUDA_TRY(jb_launch_inv_fast(a, mode, s));
+    else
+        JB_CUDA_TRY(jb_launch_inv_generic(a, mode, s));
+    return JB_OK;
+}
+
+extern "C" int jb_decompress_planes(const uint8_t* d_in, size_t in_bytes, const uint64_t* d_plane_off,
+                                    const uint64_t* d_plane_len, int n_planes, const jb_params* p,
+                                    uint8_t* d_planes_out, size_t plane_stride, size_t row_pitch,
+                                    uint64_t* d_status, void* d_ws, size_t ws_bytes, void* stream) {
+    JbGeom g;
+    int rc = jb_make_geom(p, &g);
+    if (rc != JB_OK) return rc;
+    if (!d_in || !d_plane_off || !d_plane_len || !d_planes_out || !d_status || n_planes <= 0) return JB_ERR_BAD_PARAM;
+    if (row_pitch < (size_t)g.W || plane_stride < row_pitch * (size_t)(g.H - 1) + (size_t)g.W) return JB_ERR_BAD_PARAM;
+    return jb_inverse_common(0, d_in, in_bytes, d_plane_off, d_plane_len, n_planes, g, d_planes_out, plane_stride,
+                             row_pitch, nullptr, nullptr, d_status, d_ws, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int jb_stage_unpack(const uint8_t* d_in, size_t in_bytes, const uint64_t* d_plane_off,
+                               const uint64_t* d_plane_len, int n_planes, int blocks_per_plane, int dct_size,
+                               int16_t* d_coeffs, uint64_t* d_status, void* d_ws, size_t ws_bytes, void* stream) {
+    if (!d_in || !d_plane_off || !d_plane_len || !d_coeffs || !d_status || n_planes <= 0 || blocks_per_plane <= 0)
+        return JB_ERR_BAD_PARAM;
+    if (dct_size < 1) return JB_ERR_BAD_PARAM;
+    if (dct_size > JB_MAX_DCT_SIZE) return JB_ERR_UNSUPPORTED;
+    JbGeom g;
+    memset(&g, 0, sizeof(g));
+    g.d = dct_size; g.n = dct_size * dct_size; g.nblocks = blocks_per_plane;
+    g.maxblk = jb_max_block_bytes(g.n);
+    g.cpp = (blocks_per_plane + JB_CHUNK - 1) / JB_CHUNK;
+    g.bs = 1;
+    return jb_inverse_common(1, d_in, in_bytes, d_plane_off, d_plane_len, n_planes, g, nullptr, 0, 0, d_coeffs,
+                             nullptr, d_status, d_ws, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int jb_stage_inverse_coeffs(const int16_t* d_coeffs, int n_planes, const jb_params* p,
+                                       uint8_t* d_planes_out, size_t plane_stride, size_t row_pitch,
+                                       uint64_t* d_status, void* d_ws, size_t ws_bytes, void* stream) {
+    JbGeom g;
+    int rc = jb_make_geom(p, &g);
+    if (rc != JB_OK) return rc;
+    if (!d_coeffs || !d_planes_out || !d_status || n_planes <= 0) return JB_ERR_BAD_PARAM;
+    if (row_pitch < (size_t)g.W || plane_stride < row_pitch * (size_t)(g.H - 1) + (size_t)g.W) return JB_ERR_BAD_PARAM;
+    return jb_inverse_common(2, nullptr, 0, nullptr, nullptr, n_planes, g, d_planes_out, plane_stride, row_pitch,
+                             nullptr, d_coeffs, d_status, d_ws, ws_bytes, (cudaStream_t)stream);
+}

@@ -1,0 +1,273 @@
+// jb_forward.cu -- compress direction.
+//
+//   jb_fwd_generic_kernel : any (block_size, dct_size <= 32, DCT | DFT, quantiser); one CTA per
+//                           chunk of 32 blocks.  Reference stages 0-8 fused:
+//                           padding.py:8-12, subsampling.py:9-11, dct_padding.py:8-9,
+//                           normalization.py:7-8, basis_change.py:11-26 (transforms.py:36-58),
+//                           quantization.py:8-18 (quantizers.py), zigzag_order.py:85-99,
+//                           run_length_encoding.py:47-62, rle_byte_stream.py:48-58.
+//   jb_fwd_fast kernels   : see jb_forward_fast.cuh (dct_size 8, block_size 4).
+//
+// Output order is the reference's: blocks in raster order inside a plane
+// (run_length_encoding.py:56-60), planes concatenated; the byte offset of every chunk
+// comes from a decoupled look-back scan over chunk lengths, so the kernel writes each
+// block's bytes once, at its final position.
+#include "jb_common.cuh"
+#include "jb_forward.cuh"
+
+// ----------------------------------------------------------------------------------------------
+// generic kernel
+// ----------------------------------------------------------------------------------------------
+struct JbBigAmp { int blk, pos, amp; };
+#define JB_BIGAMP_CAP 16
+
+struct JbFwdSmemLayout {
+    int slot_threads, nsub;
+    int coefW;      // 32-bit words per coefficient row (int16 pairs), odd
+    int stageW;     // 32-bit words per staging row, odd
+    size_t off_A, off_B, off_X, off_T, off_T2, off_coef, off_stage, total;
+};
+
+__host__ __device__ inline JbFwdSmemLayout jb_fwd_smem_layout(int d, bool dft) {
+    JbFwdSmemLayout L;
+    int n = d * d;
+    int st = (n + 31) / 32 * 32;
+    if (st > JB_GENERIC_THREADS) st = JB_GENERIC_THREADS;
+    L.slot_threads = st;
+    L.nsub = JB_GENERIC_THREADS / st;
+    L.coefW = ((n + 1) / 2) | 1;
+    L.stageW = ((jb_max_block_bytes(n) + 3) / 4 + 1) | 1;
+    size_t o = 0;
+    L.off_A = o;     o += (size_t)n * 4;
+    L.off_B = o;     o += dft ? (size_t)n * 4 : 0;
+    L.off_X = o;     o += (size_t)L.nsub * n * 4;
+    L.off_T = o;     o += (size_t)L.nsub * n * 4;
+    L.off_T2 = o;    o += dft ? (size_t)L.nsub * n * 4 : 0;
+    L.off_coef = o;  o += (size_t)JB_CHUNK * L.coefW * 4;
+    L.off_stage = o; o += (size_t)JB_CHUNK * L.stageW * 4;
+    L.total = o;
+    return L;
+}
+
+size_t jb_fwd_generic_smem_bytes(int d, bool dft) { return jb_fwd_smem_layout(d, dft).total; }
+
+// float64 re-evaluation of one coefficient the way the reference computes it
+// (transforms.py:46-58 rows then columns; quantizers.py:27-28,47-49).
+__device__ double jb_refine_coefficient(const int* X, int u, int v, const JbGeom& g, const JbTables& t) {
+    const int d = g.d;
+    const double bs2 = (double)(g.bs * g.bs);
+    double y = 0.0;
+    if (g.transform == JB_TRANSFORM_DCT) {
+        for (int i = 0; i < d; ++i) {
+            double m = 0.0;
+            for (int j = 0; j < d; ++j) m += t.fA64[v * d + j] * ((double)X[i * d + j] / bs2);
+            y += t.fA64[u * d + i] * m;
+        }
+    } else {
+        for (int i = 0; i < d; ++i) {
+            double mc = 0.0, ms = 0.0;
+            for (int j = 0; j < d; ++j) {
+                double x = (double)X[i * d + j] / bs2;
+                mc += t.fA64[v * d + j] * x;
+                ms += t.fB64[v * d + j] * x;
+            }
+            y += t.fA64[u * d + i] * mc - t.fB64[u * d + i] * ms;
+        }
+    }
+    double r = t.qrecip[u * d + v];
+    if (g.qmode == JB_Q_QTABLE) return y * r;
+    if (g.qmode == JB_Q_DIVIDE) return y / r;
+    return y;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(JB_GENERIC_THREADS)
+jb_fwd_generic_kernel(const JbFwdArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const JbGeom& g = a.g;
+    const int d = g.d, n = g.n;
+    const bool dft = g.transform == JB_TRANSFORM_DFT;
+    const JbFwdSmemLayout L = jb_fwd_smem_layout(d, dft);
+    float* sA = (float*)(smem + L.off_A);
+    float* sB = (float*)(smem + L.off_B);
+    int* sX = (int*)(smem + L.off_X);
+    float* sT = (float*)(smem + L.off_T);
+    float* sT2 = (float*)(smem + L.off_T2);
+    uint32_t* sCoef = (uint32_t*)(smem + L.off_coef);
+    uint32_t* sStage = (uint32_t*)(smem + L.off_stage);
+
+    __shared__ unsigned s_chunk;
+    __shared__ unsigned s_blen[JB_CHUNK], s_boff[JB_CHUNK];
+    __shared__ unsigned long long s_base;
+    __shared__ unsigned s_total;
+    __shared__ JbBigAmp s_big[JB_BIGAMP_CAP];
+    __shared__ int s_nbig;
+
+    const int tid = threadIdx.x;
+    if (tid == 0) { s_chunk = atomicAdd(a.ticket, 1u); s_nbig = 0; }
+    if (MODE != 2) {
+        for (int i = tid; i < n; i += JB_GENERIC_THREADS) {
+            sA[i] = a.t.fA[i];
+            if (dft) sB[i] = a.t.fB[i];
+        }
+    }
+    __syncthreads();
+    const unsigned chunk = s_chunk;
+    if (chunk >= a.n_chunks) return;
+    const int plane = chunk / g.cpp;
+    const int blk0 = (chunk % g.cpp) * JB_CHUNK;
+    const int nvalid = jb_min(JB_CHUNK, g.nblocks - blk0);
+
+    if (MODE != 2) {
+        const uint8_t* src = a.planes + (size_t)plane * a.plane_stride;
+        const int slot = tid / L.slot_threads, within = tid % L.slot_threads;
+        for (int base = 0; base < nvalid; base += L.nsub) {
+            const int gi = base + slot;
+            const bool live = slot < L.nsub && gi < nvalid;
+            int* X = sX + slot * n;
+            float* T = sT + slot * n;
+            float* T2 = sT2 + slot * n;
+            const int blk = blk0 + gi;
+            const int by = blk / g.hb, bx = blk % g.hb;
+            // A1-A3: box sums with two-level edge replication
+            if (live) {
+                for (int idx = within; idx < n; idx += L.slot_threads) {
+                    int i = idx / d, j = idx % d;
+                    int si = jb_min(by * d + i, g.H1 - 1), sj = jb_min(bx * d + j, g.W1 - 1);
+                    int s = 0;
+                    for (int di = 0; di < g.bs; ++di) {
+                        const uint8_t* row = src + (size_t)jb_min(si * g.bs + di, g.H - 1) * a.row_pitch;
+                        for (int dj = 0; dj < g.bs; ++dj) s += row[jb_min(sj * g.bs + dj, g.W - 1)];
+                    }
+                    X[idx] = s;
+                }
+            }
+            __syncthreads();
+            // A5 first pass: T[i][v] = sum_j X[i][j] A[v][j]
+            if (live) {
+                for (int idx = within; idx < n; idx += L.slot_threads) {
+                    int i = idx / d, v = idx % d;
+                    float acc = 0.f, acc2 = 0.f;
+                    for (int j = 0; j < d; ++j) {
+                        float x = (float)X[i * d + j];
+                        acc = fmaf(x, sA[v * d + j], acc);
+                        if (dft) acc2 = fmaf(x, sB[v * d + j], acc2);
+                    }
+                    T[idx] = acc;
+                    if (dft) T2[idx] = acc2;
+                }
+            }
+            __syncthreads();
+            // A5 second pass + A7 quantise + A8 zigzag
+            if (live) {
+                for (int idx = within; idx < n; idx += L.slot_threads) {
+                    int u = idx / d, v = idx % d;
+                    float acc = 0.f;
+                    for (int i = 0; i < d; ++i) {
+                        acc = fmaf(sA[u * d + i], T[i * d + v], acc);
+                        if (dft) acc = fmaf(-sB[u * d + i], T2[i * d + v], acc);
+                    }
+                    float val = acc * a.t.qmult[idx];
+                    float r = rintf(val);
+                    float tol = a.t.qtol[idx];
+                    if (!(g.flags & JB_FLAG_NO_REFINE) &&
+                        fabsf(fabsf(val - r) - 0.5f) < tol + 2.4e-7f * fabsf(val)) {
+                        r = (float)rint(jb_refine_coefficient(X, u, v, g, a.t));
+                    }
+                    int q = (int)r;
+                    int zp = a.t.zz[idx];
+                    if (MODE == 1) {
+                        int qs = q > 32767 ? 32767 : (q < -32767 ? -32767 : q);
+                        a.coeffs_out[((size_t)plane * g.nblocks + blk) * n + zp] = (int16_t)qs;
+                    } else {
+                        if (q > JB_MAX_AMP || q < -JB_MAX_AMP) {
+                            int k = atomicAdd(&s_nbig, 1);
+                            if (k < JB_BIGAMP_CAP) { s_big[k].blk = gi; s_big[k].pos = zp; s_big[k].amp = q; }
+                            q = q > 0 ? 32767 : -32767;
+                        }
+                        ((int16_t*)(sCoef + gi * L.coefW))[zp] = (int16_t)q;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (MODE == 1) return;
+    }
+
+    // A9 + A10: one thread per block
+    if (tid < JB_CHUNK) {
+        unsigned len = 0;
+        if (tid < nvalid) {
+            int bad_pos, bad_run;
+            const unsigned long long gblk = (unsigned long long)plane * g.nblocks + blk0 + tid;
+            if (MODE == 2) {
+                const int32_t* c = a.coeffs_in + gblk * n;
+                len = jb_pack_block<int32_t>(c, n, sStage + tid * L.stageW, &bad_pos, &bad_run);
+                if (bad_pos >= 0) jb_report_bad_code(a.status, gblk, bad_pos, bad_run, c[bad_pos]);
+            } else {
+                const int16_t* c = (const int16_t*)(sCoef + tid * L.coefW);
+                len = jb_pack_block<int16_t>(c, n, sStage + tid * L.stageW, &bad_pos, &bad_run);
+                if (bad_pos >= 0) {
+                    long long amp = c[bad_pos];
+                    int nb = jb_min(s_nbig, JB_BIGAMP_CAP);
+                    for (int k = 0; k < nb; ++k)
+                        if (s_big[k].blk == tid && s_big[k].pos == bad_pos) amp = s_big[k].amp;
+                    jb_report_bad_code(a.status, gblk, bad_pos, bad_run, amp);
+                }
+            }
+        }
+        // warp scan of block lengths, then the chunk's place in the output
+        unsigned incl = len;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (tid >= o) incl += y;
+        }
+        const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+        s_blen[tid] = len;
+        s_boff[tid] = incl - len;
+        unsigned long long base = jb_lookback_exclusive(a.desc, chunk, total, tid, a.status);
+        if (tid == 0) {
+            s_base = base;
+            s_total = total;
+            if (chunk % g.cpp == 0) a.plane_off[plane] = base;
+            if (chunk == a.n_chunks - 1) a.plane_off[a.n_planes] = base + total;
+        }
+    }
+    __syncthreads();
+    const unsigned long long base = s_base;
+    if (base + s_total > a.out_cap) {
+        if (tid == 0) jb_set_error(a.status, JB_ERR_OUT_CAPACITY);
+        return;
+    }
+    for (int gi = 0; gi < nvalid; ++gi) {
+        const uint8_t* sb = (const uint8_t*)(sStage + gi * L.stageW);
+        uint8_t* dst = a.out + base + s_boff[gi];
+        for (unsigned j = tid; j < s_blen[gi]; j += JB_GENERIC_THREADS) dst[j] = sb[j];
+    }
+}
+
+cudaError_t jb_launch_fwd_generic(const JbFwdArgs& a, int mode, cudaStream_t s) {
+    const bool dft = a.g.transform == JB_TRANSFORM_DFT;
+    size_t smem = jb_fwd_generic_smem_bytes(a.g.d, dft);
+    cudaError_t e;
+    if (a.n_chunks == 0) return cudaSuccess;
+    switch (mode) {
+    case 0:
+        e = cudaFuncSetAttribute(jb_fwd_generic_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        jb_fwd_generic_kernel<0><<<a.n_chunks, JB_GENERIC_THREADS, smem, s>>>(a);
+        break;
+    case 1:
+        e = cudaFuncSetAttribute(jb_fwd_generic_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        jb_fwd_generic_kernel<1><<<a.n_chunks, JB_GENERIC_THREADS, smem, s>>>(a);
+        break;
+    default:
+        e = cudaFuncSetAttribute(jb_fwd_generic_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        jb_fwd_generic_kernel<2><<<a.n_chunks, JB_GENERIC_THREADS, smem, s>>>(a);
+        break;
+    }
+    return cudaGetLastError();
+}

@@ -1,0 +1,29 @@
+// jb_forward.cuh -- launch arguments of the compress-direction kernels.
+#pragma once
+#include "jb_common.cuh"
+
+#define JB_GENERIC_THREADS 256
+
+struct JbFwdArgs {
+    JbGeom g;
+    JbTables t;
+    const uint8_t* planes;            // MODE 0/1 input
+    size_t plane_stride, row_pitch;
+    int n_planes;
+    unsigned n_chunks;                // n_planes * g.cpp
+    uint8_t* out;                     // MODE 0/2 output: concatenated streams
+    unsigned long long out_cap;
+    unsigned long long* plane_off;    // n_planes + 1
+    unsigned long long* status;       // JB_STATUS_WORDS
+    unsigned long long* desc;         // n_chunks look-back descriptors (zeroed)
+    unsigned* ticket;                 // chunk ticket counter (zeroed)
+    int16_t* coeffs_out;              // MODE 1
+    const int32_t* coeffs_in;         // MODE 2
+};
+
+size_t jb_fwd_generic_smem_bytes(int d, bool dft);
+cudaError_t jb_launch_fwd_generic(const JbFwdArgs& a, int mode, cudaStream_t s);
+
+// specialised path: dct_size 8, block_size 4 (jb_forward_fast.cu)
+bool jb_fwd_fast_eligible(const JbGeom& g);
+cudaError_t jb_launch_fwd_fast(const JbFwdArgs& a, int mode, cudaStream_t s);

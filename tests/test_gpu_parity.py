@@ -1,0 +1,234 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI, against the oracle and the
+committed outputs of the unmodified reference.  All need a GPU."""
+import numpy as np
+import pytest
+
+import golden_io
+from golden_inputs import make_input, synth_plane
+from oracle import ref_port as rp
+from parity import check_pixels, check_quantised
+
+pytestmark = pytest.mark.gpu
+
+FLAG_SETS = [pytest.param(0, id="default"), pytest.param(1, id="generic")]   # JB_FLAG_FORCE_GENERIC = 1
+
+
+@pytest.fixture(scope="module")
+def jb():
+    import jpeg_b200
+    return jpeg_b200
+
+
+def _cfgs(jb, case_or_tuple):
+    if isinstance(case_or_tuple, dict):
+        c = case_or_tuple
+        h, w, bs, d, tr, qn, qp = c["h"], c["w"], c["bs"], c["d"], c["transform"], c["qname"], c.get("qparam")
+    else:
+        h, w, bs, d, tr, qn, qp = case_or_tuple
+    kw = {"keep": qp} if qn == "discard" else {"divisor": qp} if qn == "divide" else {}
+    cfg = jb.Configuration(width=w, height=h, block_size=bs, dct_size=d, transform=tr,
+                           quantization=jb.QuantizationMethod(qn, **kw))
+    return cfg, rp.OracleConfig(w, h, bs, d, tr, qn, qp)
+
+
+def _check_forward(jb, planes, cfg, ocfg, flags, what):
+    """Quantised-integer gate + bit-exact packing gate for a list of planes."""
+    n = cfg.dct_size ** 2
+    streams = jb.compress_bands(planes, cfg, flags=flags)
+    coeffs = jb.stages.forward_coefficients(np.stack(planes).astype(np.uint8), cfg, flags=flags)
+    total_ties = 0
+    for i, a in enumerate(planes):
+        zz = rp.quantised_zigzag(a, ocfg)
+        ties = check_quantised(coeffs[i], zz, rp.prerounding_zigzag(a, ocfg), what="%s plane %d" % (what, i))
+        total_ties += ties
+        # packing is bit exact given the coefficients the GPU itself produced
+        assert streams[i] == rp.pack_blocks(coeffs[i].reshape(-1, n)), what
+        if ties == 0:
+            assert streams[i] == rp.compress_band(a, ocfg), what
+    return streams, total_ties
+
+
+@pytest.mark.parametrize("flags", FLAG_SETS)
+@pytest.mark.parametrize("case", golden_io.cases(), ids=golden_io.case_ids())
+def test_golden_reference_cases(jb, case, flags):
+    a = make_input(case)
+    cfg, ocfg = _cfgs(jb, case)
+    if case.get("error"):
+        with pytest.raises(jb.BadRleCodeError) as ei:
+            jb.compress_band(a, cfg, flags=flags)
+        assert str(ei.value) == case["error_msg"]
+        return
+    streams, ties = _check_forward(jb, [a], cfg, ocfg, flags, case["name"])
+    if ties == 0:
+        assert streams[0] == golden_io.stream(case)
+    # decode the REFERENCE's stream
+    rec = jb.decompress_band(golden_io.stream(case), cfg, flags=flags)
+    assert rec.dtype == np.int64 and rec.shape == (case["h"], case["w"])
+    check_pixels(rec, golden_io.restored(case), a, what=case["name"])
+
+
+GRID = [
+    (96, 160, 4, 8, "DCT", "qtable", None), (97, 161, 4, 8, "DCT", "qtable", None),
+    (33, 31, 4, 8, "DFT", "qtable", None), (128, 128, 4, 8, "DFT", "none", None),
+    (64, 96, 4, 8, "DCT", "none", None), (64, 96, 4, 8, "DCT", "divide", 3),
+    (64, 96, 4, 8, "DCT", "discard", 4), (75, 50, 2, 8, "DCT", "qtable", None),
+    (40, 56, 1, 8, "DCT", "qtable", None), (240, 250, 5, 24, "DCT", "divide", 1000),
+    (240, 250, 5, 24, "DCT", "divide", 40), (90, 70, 3, 5, "DFT", "divide", 7),
+    (64, 64, 2, 16, "DCT", "divide", 20), (50, 60, 1, 32, "DCT", "divide", 50),
+    (30, 30, 7, 3, "DCT", "none", None), (20, 20, 1, 1, "DCT", "none", None),
+    (64, 64, 16, 2, "DFT", "none", None),
+]
+
+
+@pytest.mark.parametrize("flags", FLAG_SETS)
+@pytest.mark.parametrize("h,w,bs,d,tr,qn,qp", GRID)
+def test_differential_grid(jb, h, w, bs, d, tr, qn, qp, flags):
+    cfg, ocfg = _cfgs(jb, (h, w, bs, d, tr, qn, qp))
+    rng = np.random.default_rng(h * 7 + w)
+    planes = [synth_plane(h, w, 3, phase=0.5), rng.integers(0, 256, (h, w)).astype(np.int64),
+              np.full((h, w), 200, dtype=np.int64)]
+    what = "grid %s" % ((h, w, bs, d, tr, qn, qp),)
+    streams, _ = _check_forward(jb, planes, cfg, ocfg, flags, what)
+    rec = jb.decompress_bands(streams, cfg, flags=flags)
+    for i, a in enumerate(planes):
+        check_pixels(rec[i], rp.decompress_band(streams[i], ocfg), a, what=what)
+
+
+def test_rle_stage_vectors_from_the_reference_tests(jb):
+    # tests/RLE_tests.py:16-26,36-46,77-86,99-122 through the CUDA packer / unpacker
+    a = np.zeros((1, 64), dtype=np.int64)
+    a[0, :15] = [-15, 0, 0, 0, 3, 2, 0, 0, 0, 0, 120, 0, 0, 0, 0]
+    s = jb.stages.pack_coefficients(a, 8)[0]
+    assert s == rp.pack_tuples([(0, 5, -15), (3, 3, 3), (0, 3, 2), (4, 8, 120), (0, 0)])
+    a = np.zeros((1, 64), dtype=np.int64)
+    a[0, 1], a[0, 34] = 2, 5
+    s = jb.stages.pack_coefficients(a, 8)[0]
+    assert s == rp.pack_tuples([(1, 3, 2), (15, 0, 0), (15, 0, 0), (2, 4, 5), (0, 0)])
+    blocks = np.zeros((3, 9), dtype=np.int64)
+    blocks[0] = [21, 3, 0, 0, 0, 0, 2, 0, 0]
+    blocks[1] = [0, 0, 0, 15, 0, 0, 0, 0, 9]
+    s = jb.stages.pack_coefficients(blocks, 3)[0]
+    assert s == rp.pack_tuples([(0, 6, 21), (0, 3, 3), (4, 3, 2), (0, 0), (3, 5, 15), (4, 5, 9), (0, 0), (0, 0)])
+    assert jb.stages.unpack_streams([s], 3, 3)[0].tolist() == blocks.tolist()
+    a = np.zeros((1, 64), dtype=np.int64)
+    a[0, 4] = 2
+    bits = "".join(format(x, "08b") for x in jb.stages.pack_coefficients(a, 8)[0])
+    assert bits == "0100" + "0011" + "110" + "0" * 13
+    for x in ([(15, 0, 0), (15, 0, 0), (0, 2, 1), (0, 0)],
+              [(1, 2, -1), (0, 3, -2), (8, 3, -3), (8, 5, -15), (0, 0)],
+              [(14, 4, 7), (0, 0), (0, 0), (15, 0, 0), (0, 2, 1), (0, 0)]):
+        want = rp.tuples_to_blocks(x, 64)
+        got = jb.stages.unpack_streams([rp.pack_tuples(x)], want.shape[0], 8)[0]
+        assert got.tolist() == want.tolist()
+    with pytest.raises(jb.BadRleCodeError):
+        bad = np.zeros((2, 64), dtype=np.int64)
+        bad[1, 3] = 20000
+        jb.stages.pack_coefficients(bad, 8)
+
+
+@pytest.mark.parametrize("n,density,bits", [(64, 0.25, 7), (64, 1.0, 14), (64, 0.0, 1), (576, 0.05, 10),
+                                            (1024, 0.02, 12), (1, 0.6, 9), (25, 0.3, 5)])
+def test_pack_unpack_random_coefficients(jb, n, density, bits):
+    rng = np.random.default_rng(n + bits)
+    d = int(round(n ** 0.5))
+    zz = np.zeros((3, 700, n), dtype=np.int64)
+    mask = rng.random(zz.shape) < density
+    vals = rng.integers(1, 1 << bits, zz.shape) * (rng.integers(0, 2, zz.shape) * 2 - 1)
+    zz[mask] = vals[mask]
+    streams = jb.stages.pack_coefficients(zz, d)
+    for i in range(3):
+        assert streams[i] == rp.pack_blocks(zz[i])
+    back = jb.stages.unpack_streams(streams, 700, d)
+    assert np.array_equal(back, zz)
+
+
+def test_zero_heavy_streams_every_byte_a_candidate(jb):
+    # an all-black plane packs to one 0x00 per block: every byte is a block start
+    cfg, ocfg = _cfgs(jb, (600, 800, 1, 8, "DCT", "qtable", None))
+    a = np.zeros((600, 800), dtype=np.int64)
+    s = jb.compress_band(a, cfg)
+    assert s == b"\0" * (75 * 100)
+    assert np.array_equal(jb.decompress_band(s, cfg), a)
+
+
+def test_malformed_streams_are_rejected(jb):
+    cfg, ocfg = _cfgs(jb, (64, 64, 4, 8, "DCT", "qtable", None))
+    a = synth_plane(64, 64, 1)
+    good = jb.compress_band(a, cfg)
+    with pytest.raises(jb.BadStreamError):
+        jb.decompress_band(good[:-1], cfg)              # truncated
+    with pytest.raises(jb.BadStreamError):
+        jb.decompress_band(good + b"\0", cfg)           # one block too many
+    with pytest.raises(jb.BadStreamError):
+        jb.decompress_band(b"\x50" + good[1:], cfg)     # (5, 0, 0) is not a code
+    with pytest.raises(jb.BadQuantizationError):
+        jb.Configuration(width=8, height=8, dct_size=4, quantization=jb.QuantizationMethod("qtable"))
+    with pytest.raises(jb.EmptyArrayError):
+        jb.compress_band(np.zeros((0, 5)), cfg)
+    with pytest.raises(jb.BadArrayShapeError):
+        jb.compress_band(np.zeros(5), cfg)
+
+
+@pytest.mark.parametrize("flags", FLAG_SETS)
+@pytest.mark.parametrize("h,w,tr,qn", [(1080, 1920, "DCT", "qtable"), (2160, 3840, "DCT", "qtable"),
+                                       (1024, 2048, "DFT", "qtable")])
+def test_full_size_frames(jb, h, w, tr, qn, flags):
+    """BASELINE.json configs 2 / 4 / 5 geometry (one frame each): all gates, plus the
+    round trip through the container and the image facade."""
+    cfg, ocfg = _cfgs(jb, (h, w, 4, 8, tr, qn, None))
+    planes = [synth_plane(h, w, 1000 + b, phase=0.7 * b) for b in range(3)]
+    streams, ties = _check_forward(jb, planes, cfg, ocfg, flags, "%dx%d %s" % (h, w, tr))
+    rec = jb.decompress_bands(streams, cfg, flags=flags)
+    for i in range(3):
+        check_pixels(rec[i], rp.decompress_band(streams[i], ocfg), planes[i], what="full frame")
+    blob = jb.file_format.generate_data(cfg, jb.CompressedData(*streams))
+    cfg2, data = jb.file_format.read_data(blob)
+    assert (cfg2.width, cfg2.height, cfg2.block_size, cfg2.dct_size, cfg2.transform) == (w, h, 4, 8, tr)
+    assert [data.y, data.cb, data.cr] == streams
+
+
+def test_large_block_config3(jb):
+    """BASELINE.json config 3: 3840x2160, --block_size 5 --dct_size 24 --quantization divide --qdivisor 1000."""
+    h, w = 2160, 3840
+    cfg, ocfg = _cfgs(jb, (h, w, 5, 24, "DCT", "divide", 1000))
+    planes = [synth_plane(h, w, 77)]
+    streams, _ = _check_forward(jb, planes, cfg, ocfg, 0, "config3")
+    rec = jb.decompress_bands(streams, cfg)
+    check_pixels(rec[0], rp.decompress_band(streams[0], ocfg), planes[0], what="config3")
+
+
+def test_image_facade_round_trip(jb):
+    from PIL import Image
+    rng = np.random.default_rng(9)
+    rgb = np.clip(np.stack([synth_plane(120, 200, 5 + i) for i in range(3)], -1) + rng.integers(-3, 4, (120, 200, 3)),
+                  0, 255).astype(np.uint8)
+    im = Image.fromarray(rgb, "RGB").convert("YCbCr")
+    cfg = jb.Configuration(width=im.width, height=im.height, block_size=4, dct_size=8, transform="DCT",
+                           quantization=jb.QuantizationMethod("qtable"))
+    blob = jb.Jpeg(cfg).compress(im)
+    out = jb.Jpeg.decompress(blob)
+    assert out.mode == "YCbCr" and out.size == im.size
+    ocfg = rp.OracleConfig(im.width, im.height, 4, 8, "DCT", "qtable")
+    bands = [np.asarray(b).astype(np.int64) for b in im.split()]
+    cfg2, data = jb.file_format.read_data(blob)
+    for got, band, stream in zip(out.split(), bands, (data.y, data.cb, data.cr)):
+        check_pixels(np.asarray(got), rp.decompress_band(stream, ocfg), band, what="facade")
+
+
+def test_batch_equals_per_plane_and_sharding_concatenates(jb):
+    """Multi-GPU contract on one GPU: a batch equals plane-by-plane calls, and block-row
+    bands compressed separately concatenate to the whole-image stream."""
+    h, w = 272, 320
+    cfg, _ = _cfgs(jb, (h, w, 4, 8, "DCT", "qtable", None))
+    planes = [synth_plane(h, w, 40 + i) for i in range(6)]
+    batch = jb.compress_bands(planes, cfg)
+    assert batch == [jb.compress_band(p, cfg) for p in planes]
+    whole = jb.compress_band(planes[0], cfg)
+    parts = []
+    for r0, r1 in jb.sharding.block_row_bands(h, 4, 8, 4):
+        if r1 > r0:
+            sub, _ = _cfgs(jb, (r1 - r0, w, 4, 8, "DCT", "qtable", None))
+            parts.append([jb.compress_band(planes[0][r0:r1], sub)])
+        else:
+            parts.append([])
+    assert jb.sharding.concat_band_streams(parts)[0] == whole
