@@ -1,4 +1,467 @@
-// placeholder until the specialised kernels land
+// jb_forward_fast.cu -- compress direction, specialised for dct_size 8 / block_size 4
+// (the CLI default, BASELINE.json configs 1, 2, 4, 5), DCT or real-part DFT, any quantiser.
+//
+// Work unit: one warp owns a chunk of 32 consecutive blocks (raster order) of one plane.
+//   * 8 iterations, each over a 32-row x 128-byte source tile = 4 horizontally adjacent
+//     blocks.  Tiles are staged in shared memory by TMA (cp.async.bulk.tensor, one elected
+//     lane, mbarrier completion) through a per-warp ring, so the next tiles are in flight
+//     while the current one is transformed.  Tiles that touch the replicated edge
+//     (padding.py:8-12, dct_padding.py:8-9) or a misaligned plane are filled by the warp
+//     with clamped loads instead (TMA would zero-fill, the reference replicates).
+//   * lane (i, b) = (row 0..7, block 0..3): 8 x LDS.128 -> 4x4 box sums by dp4a -> 8-point
+//     transform along the row in registers -> transpose through shared memory -> 8-point
+//     transform down the column -> quantise (fp32; coefficients that land within the
+//     fp32 error bound of a rounding tie are re-evaluated in fp64 the way the reference
+//     computes them) -> int16 store at the zigzag position.
+//   * then lane t run-length-encodes and bit-packs block t of the chunk (util.py:146-160,
+//     203-221), the warp scans the 32 byte lengths, gets its output offset by decoupled
+//     look-back over all earlier chunks, and copies the packed bytes out.
+// No block-level synchronisation: warps are independent after the table preload.
+#include <cuda.h>
+#include <string.h>
+
+#include "jb_common.cuh"
+#include "jb_fast_common.cuh"
 #include "jb_forward.cuh"
-bool jb_fwd_fast_eligible(const JbGeom&) { return false; }
-cudaError_t jb_launch_fwd_fast(const JbFwdArgs&, int, cudaStream_t) { return cudaErrorNotSupported; }
+
+#define FF_WARPS 8
+#define FF_RING 3
+#define FF_STAGE_W 49       // words per packed-bytes row: ceil(185 / 4) = 47 -> odd stride
+#define FF_BIG_CAP 8
+
+struct __align__(128) FfWarpSmem {
+    uint8_t tile[FF_RING][FF_TILE_BYTES];
+    float scr[4 * FF_BLK_W];            // row-pass results, [block][row][col]
+    float stash[4 * FF_BLK_W];          // box sums of the 4 blocks (fp64 re-evaluation input)
+    uint32_t coef[JB_CHUNK * FF_COEF_W];
+    uint32_t stage[JB_CHUNK * FF_STAGE_W];
+    unsigned long long bar[FF_RING];
+    int big_blk[FF_BIG_CAP], big_pos[FF_BIG_CAP], big_amp[FF_BIG_CAP];
+    int nbig;
+};
+
+struct FfCtaSmem {
+    double A64[64];
+    double B64[64];
+};
+
+// fp64 re-evaluation of coefficient (u, v) from the 8x8 box sums of one block, following the
+// reference's order (rows then columns, transforms.py:46-58; quantizers.py:27-28,47-49).
+template <bool DFT>
+__device__ __noinline__ double ff_refine8(const float* X, int u, int v, const FfCtaSmem& cs, int qmode, double recip) {
+    double y = 0.0;
+    for (int i = 0; i < 8; ++i) {
+        double mc = 0.0, ms = 0.0;
+        for (int j = 0; j < 8; ++j) {
+            double x = (double)X[i * 8 + j] / 16.0;
+            mc += cs.A64[v * 8 + j] * x;
+            if (DFT) ms += cs.B64[v * 8 + j] * x;
+        }
+        y += cs.A64[u * 8 + i] * mc;
+        if (DFT) y -= cs.B64[u * 8 + i] * ms;
+    }
+    if (qmode == JB_Q_QTABLE) return y * recip;
+    if (qmode == JB_Q_DIVIDE) return y / recip;
+    return y;
+}
+
+// ---- tile classification and staging ----------------------------------------------------------
+// kind 0: whole 32x128 tile inside the image, 16-byte aligned rows -> TMA (or LDG.128 when TMA is off)
+// kind 2: touches an edge / wraps a block row / partial group     -> clamped byte loads
+__device__ __forceinline__ int ff_tile_kind(const JbGeom& g, int blk0, int nvalid, int it, bool aligned) {
+    const int n0 = blk0 + 4 * it;
+    if (!aligned || 4 * it + 4 > nvalid) return 2;
+    const int by = n0 / g.hb, bx = n0 - by * g.hb;
+    if (bx + 4 > g.hb || (bx + 4) * 32 > g.W || (by + 1) * 32 > g.H) return 2;
+    return 0;
+}
+
+// two-level edge replication of SURVEY.md section 8(a) rows A1-A3, written into the tile layout
+__device__ __forceinline__ void ff_fill_clamped(uint8_t* tile, const uint8_t* plane, size_t pitch, const JbGeom& g,
+                                                int n0, int nlive, int lane) {
+    uint32_t* t32 = (uint32_t*)tile;
+    for (int idx = lane; idx < 1024; idx += 32) {
+        const int row = idx >> 5, wcol = idx & 31, b = wcol >> 3;
+        uint32_t word = 0;
+        if (b < nlive) {
+            const int blk = n0 + b;
+            const int by = blk / g.hb, bx = blk - by * g.hb;
+            const int si = jb_min(by * 8 + (row >> 2), g.H1 - 1), sj = jb_min(bx * 8 + (wcol & 7), g.W1 - 1);
+            const uint8_t* r = plane + (size_t)jb_min(si * 4 + (row & 3), g.H - 1) * pitch;
+            const int x0 = sj * 4, xm = g.W - 1;
+            word = (uint32_t)r[jb_min(x0, xm)] | ((uint32_t)r[jb_min(x0 + 1, xm)] << 8) |
+                   ((uint32_t)r[jb_min(x0 + 2, xm)] << 16) | ((uint32_t)r[jb_min(x0 + 3, xm)] << 24);
+        }
+        t32[idx] = word;
+    }
+}
+
+__device__ __forceinline__ void ff_fill_direct(uint8_t* tile, const uint8_t* plane, size_t pitch, const JbGeom& g,
+                                               int n0, int lane) {
+    const int by = n0 / g.hb, bx = n0 - by * g.hb;
+    const uint8_t* src = plane + (size_t)by * 32 * pitch + (size_t)bx * 32;
+    uint4* t16 = (uint4*)tile;
+    uint4 v[8];
+    #pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int idx = k * 32 + lane;
+        v[k] = __ldg((const uint4*)(src + (size_t)(idx >> 3) * pitch) + (idx & 7));
+    }
+    #pragma unroll
+    for (int k = 0; k < 8; ++k) t16[k * 32 + lane] = v[k];
+}
+
+struct FfKernelArgs {
+    JbFwdArgs a;
+    int use_tma;        // tensor map valid
+    int aligned;        // plane base / pitch / stride are multiples of 16 bytes
+};
+
+// ---- the kernel -------------------------------------------------------------------------------
+template <bool DFT, int MODE>
+__global__ void __launch_bounds__(FF_WARPS * 32, 1)
+jb_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfKernelArgs ka) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const JbFwdArgs& a = ka.a;
+    const JbGeom& g = a.g;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    FfCtaSmem& cs = *(FfCtaSmem*)smem_raw;
+    FfWarpSmem& ws = *(FfWarpSmem*)(smem_raw + 1024 + (size_t)warp * sizeof(FfWarpSmem));
+
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) { cs.A64[i] = a.t.fA64[i]; cs.B64[i] = a.t.fB64[i]; }
+    if (lane == 0) {
+        for (int s = 0; s < FF_RING; ++s) ff_mbar_init(&ws.bar[s], 1);
+        ws.nbig = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // lane roles: (i, b) for loads and the row pass, (c, b) for the column pass
+    const int li = lane >> 2, lb = lane & 3;
+    const int v = DFT ? (li < 5 ? li : 12 - li) : li;          // frequency column this lane quantises
+    float qm[8], qt[8];
+    int zz[8];
+    #pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        qm[u] = a.t.qmult[u * 8 + v];
+        qt[u] = a.t.qtol[u * 8 + v];
+        zz[u] = a.t.zz[u * 8 + v];
+    }
+    const bool refine_on = !(g.flags & JB_FLAG_NO_REFINE);
+
+    // ---- chunk / tile cursors (all warp-uniform) ----
+    auto claim = [&]() -> unsigned {
+        unsigned c = 0;
+        if (lane == 0) c = atomicAdd(a.ticket, 1u);
+        return __shfl_sync(0xffffffffu, c, 0);
+    };
+    auto chunk_nvalid = [&](unsigned chunk) -> int {
+        const int blk0 = (int)(chunk % (unsigned)g.cpp) * JB_CHUNK;
+        return jb_min(JB_CHUNK, g.nblocks - blk0);
+    };
+    auto issue_tile = [&](unsigned chunk, int it, int slot) {
+        const int plane = (int)(chunk / (unsigned)g.cpp);
+        const int blk0 = (int)(chunk % (unsigned)g.cpp) * JB_CHUNK;
+        const int nvalid = jb_min(JB_CHUNK, g.nblocks - blk0);
+        if (ka.use_tma && ff_tile_kind(g, blk0, nvalid, it, ka.aligned != 0) == 0) {
+            if (lane == 0) {
+                const int n0 = blk0 + 4 * it;
+                const int by = n0 / g.hb, bx = n0 - by * g.hb;
+                ff_fence_proxy_async();
+                ff_mbar_expect_tx(&ws.bar[slot], FF_TILE_BYTES);
+                ff_tma_load_3d(ws.tile[slot], &tmap, bx * 32, by * 32, plane, &ws.bar[slot]);
+            }
+        }
+    };
+
+    unsigned cur = claim();
+    if (cur >= a.n_chunks) return;
+    unsigned iss_chunk = cur;
+    int iss_it = 0, iss_nit = (chunk_nvalid(cur) + 3) >> 2;
+    unsigned seq_issue = 0, seq_consume = 0;
+    unsigned phasebits = 0;
+    bool no_more = false;
+
+    for (;;) {
+        const int plane = (int)(cur / (unsigned)g.cpp);
+        const int blk0 = (int)(cur % (unsigned)g.cpp) * JB_CHUNK;
+        const int nvalid = jb_min(JB_CHUNK, g.nblocks - blk0);
+        const int nit = (nvalid + 3) >> 2;
+        const uint8_t* plane_ptr = a.planes + (size_t)plane * a.plane_stride;
+
+        for (int it = 0; it < nit; ++it) {
+            // keep the ring full: at most FF_RING tiles issued and not yet consumed, at most one chunk ahead
+            while (seq_issue - seq_consume < FF_RING) {
+                if (iss_it == iss_nit) {
+                    if (iss_chunk != cur || no_more) break;
+                    unsigned nx = claim();
+                    if (nx >= a.n_chunks) { no_more = true; break; }
+                    iss_chunk = nx; iss_it = 0; iss_nit = (chunk_nvalid(nx) + 3) >> 2;
+                }
+                issue_tile(iss_chunk, iss_it, (int)(seq_issue % FF_RING));
+                ++seq_issue; ++iss_it;
+            }
+
+            const int slot = (int)(seq_consume % FF_RING);
+            uint8_t* tile = ws.tile[slot];
+            const int kind = ff_tile_kind(g, blk0, nvalid, it, ka.aligned != 0);
+            if (kind == 0 && ka.use_tma) {
+                const uint32_t par = (phasebits >> slot) & 1u;
+                int spins = 0;
+                while (!ff_mbar_try_wait(&ws.bar[slot], par)) {
+                    if (++spins > (1 << 24)) { if (lane == 0) jb_set_error(a.status, JB_ERR_CUDA); break; }
+                }
+                phasebits ^= 1u << slot;
+            } else if (kind == 0) {
+                ff_fill_direct(tile, plane_ptr, a.row_pitch, g, blk0 + 4 * it, lane);
+                __syncwarp();
+            } else {
+                ff_fill_clamped(tile, plane_ptr, a.row_pitch, g, blk0 + 4 * it, jb_min(4, nvalid - 4 * it), lane);
+                __syncwarp();
+            }
+
+            // ---- box sums: rows 4i..4i+3, bytes 32b..32b+31 of the tile ----
+            float x[8];
+            {
+                const uint4* t16 = (const uint4*)tile;
+                const int h0 = li & 1;                      // alternate the 16-byte half: conflict-free LDS.128
+                uint32_t sa[4] = {0x4B000000u, 0x4B000000u, 0x4B000000u, 0x4B000000u};
+                uint32_t sb[4] = {0x4B000000u, 0x4B000000u, 0x4B000000u, 0x4B000000u};
+                #pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int row = 4 * li + k;
+                    const uint4 qa = t16[row * 8 + 2 * lb + h0];
+                    const uint4 qb = t16[row * 8 + 2 * lb + (h0 ^ 1)];
+                    sa[0] = __dp4a(qa.x, 0x01010101u, sa[0]); sa[1] = __dp4a(qa.y, 0x01010101u, sa[1]);
+                    sa[2] = __dp4a(qa.z, 0x01010101u, sa[2]); sa[3] = __dp4a(qa.w, 0x01010101u, sa[3]);
+                    sb[0] = __dp4a(qb.x, 0x01010101u, sb[0]); sb[1] = __dp4a(qb.y, 0x01010101u, sb[1]);
+                    sb[2] = __dp4a(qb.z, 0x01010101u, sb[2]); sb[3] = __dp4a(qb.w, 0x01010101u, sb[3]);
+                }
+                // 0x4B000000 + s is the bit pattern of 2^23 + s: exact int -> float without I2F
+                #pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float fa = __uint_as_float(sa[j]) - 8388608.0f, fb = __uint_as_float(sb[j]) - 8388608.0f;
+                    x[j] = h0 ? fb : fa;
+                    x[4 + j] = h0 ? fa : fb;
+                }
+            }
+            // ---- stash the sums, row pass, transpose ----
+            float r[8];
+            if (DFT) ff_rdft8(x, r); else ff_dct8(x, r);
+            {
+                float4* st = (float4*)(ws.stash + lb * FF_BLK_W + li * 8);
+                float4* sc = (float4*)(ws.scr + lb * FF_BLK_W + li * 8);
+                const int h0 = li & 1;
+                const float4 x0 = make_float4(x[0], x[1], x[2], x[3]), x1 = make_float4(x[4], x[5], x[6], x[7]);
+                const float4 r0 = make_float4(r[0], r[1], r[2], r[3]), r1 = make_float4(r[4], r[5], r[6], r[7]);
+                st[h0] = h0 ? x1 : x0; st[h0 ^ 1] = h0 ? x0 : x1;
+                sc[h0] = h0 ? r1 : r0; sc[h0 ^ 1] = h0 ? r0 : r1;
+            }
+            __syncwarp();
+            float col[8], y[8];
+            #pragma unroll
+            for (int k = 0; k < 8; ++k) col[k] = ws.scr[lb * FF_BLK_W + k * 8 + li];
+            if (DFT) {
+                ff_dft_column_stage(col, li, y);
+            } else {
+                ff_dct8(col, y);
+            }
+
+            // ---- quantise, tie check, zigzag store ----
+            const int gblk = 4 * it + lb;                   // block inside the chunk
+            int qi[8];
+            unsigned nearmask = 0;
+            #pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float val = y[u] * qm[u];
+                const float t = val + 12582912.0f;          // 1.5 * 2^23: rounds half-even to an integer
+                const float rr = t - 12582912.0f;
+                qi[u] = __float_as_int(t) - 0x4B400000;
+                if (fabsf(fabsf(val - rr) - 0.5f) < qt[u] + 2.4e-7f * fabsf(val)) nearmask |= 1u << u;
+            }
+            if (refine_on && __any_sync(0xffffffffu, nearmask != 0)) {
+                if (nearmask) {
+                    const float* X = ws.stash + lb * FF_BLK_W;
+                    #pragma unroll 1
+                    for (int u = 0; u < 8; ++u)
+                        if (nearmask >> u & 1u)
+                            qi[u] = (int)rint(ff_refine8<DFT>(X, u, v, cs, g.qmode, a.t.qrecip[u * 8 + v]));
+                }
+                __syncwarp();
+            }
+            if (gblk < nvalid) {
+                if (MODE == 1) {
+                    int16_t* dst = a.coeffs_out + ((size_t)plane * g.nblocks + blk0 + gblk) * 64;
+                    #pragma unroll
+                    for (int u = 0; u < 8; ++u) dst[zz[u]] = (int16_t)max(-32767, min(32767, qi[u]));
+                } else {
+                    int16_t* row = (int16_t*)(ws.coef + gblk * FF_COEF_W);
+                    #pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        int q = qi[u];
+                        if (q > JB_MAX_AMP || q < -JB_MAX_AMP) {
+                            int k = atomicAdd(&ws.nbig, 1);
+                            if (k < FF_BIG_CAP) { ws.big_blk[k] = gblk; ws.big_pos[k] = zz[u]; ws.big_amp[k] = q; }
+                            q = q > 0 ? 32767 : -32767;
+                        }
+                        row[zz[u]] = (int16_t)q;
+                    }
+                }
+            }
+            __syncwarp();          // tile, scr and stash are free again
+            ++seq_consume;
+        }
+
+        if (MODE == 0) {
+            // ---- A9 + A10: lane t packs block t ----
+            unsigned len = 0;
+            if (lane < nvalid) {
+                const uint32_t* rowp = ws.coef + lane * FF_COEF_W;
+                uint32_t lo = 0, hi = 0;
+                #pragma unroll
+                for (int q4 = 0; q4 < 8; ++q4) {
+                    const uint4 w = *(const uint4*)(rowp + 4 * q4);
+                    uint32_t m = ((w.x & 0xFFFFu) ? 1u : 0u) | ((w.x >> 16) ? 2u : 0u)
+                               | ((w.y & 0xFFFFu) ? 4u : 0u) | ((w.y >> 16) ? 8u : 0u)
+                               | ((w.z & 0xFFFFu) ? 16u : 0u) | ((w.z >> 16) ? 32u : 0u)
+                               | ((w.w & 0xFFFFu) ? 64u : 0u) | ((w.w >> 16) ? 128u : 0u);
+                    if (q4 < 4) lo |= m << (8 * q4); else hi |= m << (8 * (q4 - 4));
+                }
+                const int16_t* c16 = (const int16_t*)rowp;
+                JbBitWriter bw;
+                bw.init(ws.stage + lane * FF_STAGE_W);
+                int prev = -1, bad_pos = -1, bad_run = 0;
+                #pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t m = half ? hi : lo;
+                    while (m) {
+                        const int p = half * 32 + __ffs((int)m) - 1;
+                        m &= m - 1;
+                        const int amp = c16[p];
+                        const int run = p - prev - 1;
+                        prev = p;
+                        if (!jb_put_coefficient(bw, run, amp) && bad_pos < 0) { bad_pos = p; bad_run = run % JB_MAX_RUN; }
+                    }
+                }
+                bw.put(0u, 8);
+                len = bw.finish();
+                if (bad_pos >= 0) {
+                    long long amp = c16[bad_pos];
+                    const int nb = jb_min(ws.nbig, FF_BIG_CAP);
+                    for (int k = 0; k < nb; ++k)
+                        if (ws.big_blk[k] == lane && ws.big_pos[k] == bad_pos) amp = ws.big_amp[k];
+                    jb_report_bad_code(a.status, (unsigned long long)plane * g.nblocks + blk0 + lane, bad_pos, bad_run, amp);
+                }
+            }
+            __syncwarp();
+            unsigned incl = len;
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+            const unsigned excl = incl - len;
+            const unsigned long long base = jb_lookback_exclusive(a.desc, cur, total, lane, a.status);
+            if (lane == 0) {
+                if (cur % (unsigned)g.cpp == 0) a.plane_off[plane] = base;
+                if (cur == a.n_chunks - 1) a.plane_off[a.n_planes] = base + total;
+            }
+            if (base + total > a.out_cap) {
+                if (lane == 0) jb_set_error(a.status, JB_ERR_OUT_CAPACITY);
+            } else {
+                for (int bk = 0; bk < nvalid; ++bk) {
+                    const unsigned l = __shfl_sync(0xffffffffu, len, bk);
+                    const unsigned o = __shfl_sync(0xffffffffu, excl, bk);
+                    const uint8_t* sb = (const uint8_t*)(ws.stage + bk * FF_STAGE_W);
+                    uint8_t* dst = a.out + base + o;
+                    for (unsigned j = lane; j < l; j += 32) dst[j] = sb[j];
+                }
+            }
+            if (lane == 0) ws.nbig = 0;
+            __syncwarp();
+        }
+
+        // next chunk: either the one the issue cursor already moved into, or a fresh claim
+        if (iss_chunk != cur) {
+            cur = iss_chunk;
+        } else {
+            if (no_more) break;
+            unsigned nx = claim();
+            if (nx >= a.n_chunks) break;
+            cur = nx; iss_chunk = nx; iss_it = 0; iss_nit = (chunk_nvalid(nx) + 3) >> 2;
+        }
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+bool jb_fwd_fast_eligible(const JbGeom& g) { return g.d == 8 && g.bs == 4; }
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled jb_get_encode_tiled() {
+    static PFN_encodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+// 3-D uint8 tensor (x = byte in row, y = row, z = plane), box 128 x 32 x 1
+bool jb_make_plane_tensor_map(CUtensorMap* map, const void* base, int W, int H, int n_planes, size_t row_pitch,
+                              size_t plane_stride) {
+    PFN_encodeTiled enc = jb_get_encode_tiled();
+    if (!enc) return false;
+    if (((uintptr_t)base & 15) || (row_pitch & 15) || (plane_stride & 15) || W < 128 || H < 32) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_planes};
+    cuuint64_t strides[2] = {(cuuint64_t)row_pitch, (cuuint64_t)(n_planes > 1 ? plane_stride : row_pitch * (size_t)H)};
+    if (strides[1] & 15) return false;
+    cuuint32_t box[3] = {128, 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)base, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+template <bool DFT, int MODE>
+static cudaError_t jb_fwd_fast_launch_t(const CUtensorMap& map, const FfKernelArgs& ka, cudaStream_t s) {
+    const size_t smem = 1024 + (size_t)FF_WARPS * sizeof(FfWarpSmem);
+    cudaError_t e = cudaFuncSetAttribute(jb_fwd_fast_kernel<DFT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jb_fwd_fast_kernel<DFT, MODE>, FF_WARPS * 32, smem);
+    if (per_sm < 1) per_sm = 1;
+    unsigned want = (ka.a.n_chunks + FF_WARPS - 1) / FF_WARPS;
+    unsigned grid = want < (unsigned)(sms * per_sm) ? want : (unsigned)(sms * per_sm);
+    if (grid == 0) return cudaSuccess;
+    jb_fwd_fast_kernel<DFT, MODE><<<grid, FF_WARPS * 32, smem, s>>>(map, ka);
+    return cudaGetLastError();
+}
+
+cudaError_t jb_launch_fwd_fast(const JbFwdArgs& a, int mode, cudaStream_t s) {
+    FfKernelArgs ka;
+    ka.a = a;
+    const JbGeom& g = a.g;
+    ka.aligned = (((uintptr_t)a.planes & 15) == 0 && (a.row_pitch & 15) == 0 &&
+                  (a.n_planes == 1 || (a.plane_stride & 15) == 0)) ? 1 : 0;
+    CUtensorMap map;
+    memset(&map, 0, sizeof(map));
+    ka.use_tma = 0;
+    if (!(g.flags & JB_FLAG_NO_TMA) && ka.aligned)
+        ka.use_tma = jb_make_plane_tensor_map(&map, a.planes, g.W, g.H, a.n_planes, a.row_pitch, a.plane_stride) ? 1 : 0;
+    const bool dft = g.transform == JB_TRANSFORM_DFT;
+    if (mode == 0) return dft ? jb_fwd_fast_launch_t<true, 0>(map, ka, s) : jb_fwd_fast_launch_t<false, 0>(map, ka, s);
+    return dft ? jb_fwd_fast_launch_t<true, 1>(map, ka, s) : jb_fwd_fast_launch_t<false, 1>(map, ka, s);
+}

@@ -275,9 +275,12 @@ __global__ void __launch_bounds__(JB_FRAME_THREADS) jb_frame_resolve_kernel(JbFr
         unsigned t = b + tid, hops = 0;
         if (t < nt) {
             unsigned e = f.tile_entry[t0 + t];
-            unsigned w = (e != JB_U32_NONE && e < f.win_n) ? f.win[(size_t)(t0 + t) * f.win_n + e] : JB_U32_NONE;
+            // the last tile may hold nothing but the tail of a block that started earlier
+            const bool tail_only = (t + 1 == nt) && e != JB_U32_NONE && (unsigned long long)t * JB_TILE_BYTES + e == len;
+            unsigned w = (!tail_only && e != JB_U32_NONE && e < f.win_n) ? f.win[(size_t)(t0 + t) * f.win_n + e] : JB_U32_NONE;
             unsigned ex = w & 0xFFFFu;
-            if (w == JB_U32_NONE || ex == JB_EX_INVALID) bad = 1;
+            if (tail_only) hops = 0;
+            else if (w == JB_U32_NONE || ex == JB_EX_INVALID) bad = 1;
             else {
                 hops = w >> 16;
                 if (t + 1 < nt) {

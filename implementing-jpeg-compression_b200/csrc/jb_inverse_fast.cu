@@ -1,4 +1,269 @@
-// placeholder until the specialised kernels land
+// jb_inverse_fast.cu -- decompress direction, specialised for dct_size 8 / block_size 4.
+//
+// One warp owns a chunk of 32 consecutive blocks of one plane (block offsets come from
+// jb_framing.cu):
+//   * the chunk's bytes (contiguous in the stream) are copied to shared memory, then lane t
+//     decodes block t (rle_byte_stream.py:74-88, run_length_encoding.py:31-41) straight into
+//     natural (un-zigzagged, zigzag_order.py:101-119) order as int16;
+//   * 8 iterations over 4 blocks: lane (u, b) dequantises row u (quantizers.py restore, with
+//     the 1/|c_k|^2 scale of transforms.py:14-26 folded in), 8-point inverse transform along
+//     the row, transpose through shared memory, 8-point inverse transform down the column,
+//     np.round + clamp (basis_change.py:43, normalization.py:10-14), 4x4 replication
+//     (util.inflate) into a 32-row x 128-byte tile in shared memory;
+//   * the tile goes out by TMA store (cp.async.bulk.tensor shared -> global), which also
+//     performs the crops of dct_padding.py:11-21 / padding.py:14-16 by clipping at the tensor
+//     bounds; tiles that wrap a block row or belong to a partial group use bounded stores.
+#include <cuda.h>
+#include <string.h>
+
+#include "jb_common.cuh"
+#include "jb_fast_common.cuh"
 #include "jb_inverse.cuh"
-bool jb_inv_fast_eligible(const JbGeom&) { return false; }
-cudaError_t jb_launch_inv_fast(const JbInvArgs&, int, cudaStream_t) { return cudaErrorNotSupported; }
+
+#define FI_WARPS 8
+#define FI_RING 2
+#define FI_STREAM_WORDS 1488            // 32 blocks * 185 bytes worst case + alignment slack
+
+struct __align__(128) FiWarpSmem {
+    uint8_t tile[FI_RING][FF_TILE_BYTES];
+    float scr[4 * FF_BLK_W];
+    uint32_t coef[JB_CHUNK * FF_COEF_W];
+    uint32_t sbytes[FI_STREAM_WORDS];
+};
+
+struct FiKernelArgs {
+    JbInvArgs a;
+    int use_tma;
+    int aligned;
+};
+
+// Decode one block from big-endian words staged in shared memory (bit `bitpos` of the staged
+// range) into natural order.  Returns 0 or 1 (malformed).
+__device__ __forceinline__ int fi_decode_block(const uint32_t* words, uint32_t bitpos, uint32_t bitlimit,
+                                               int16_t* row, const uint8_t* izz) {
+    uint32_t widx = bitpos >> 5;
+    int nb = 32 - (int)(bitpos & 31u);
+    uint64_t buf = jb_bswap32(words[widx < FI_STREAM_WORDS ? widx : FI_STREAM_WORDS - 1]);
+    ++widx;
+    uint32_t used = bitpos;
+    int count = 0;
+    for (;;) {
+        if (nb < 8) { buf = (buf << 32) | jb_bswap32(words[widx < FI_STREAM_WORDS ? widx : FI_STREAM_WORDS - 1]); ++widx; nb += 32; }
+        const uint32_t head = (uint32_t)(buf >> (nb - 8)) & 0xFFu;
+        nb -= 8; used += 8;
+        if (used > bitlimit) return 1;
+        const uint32_t run = head >> 4, size = head & 15u;
+        if (size == 0u) {
+            if (run == 0u) return 0;                     // EOB
+            if (run != (uint32_t)JB_MAX_RUN) return 1;
+            count += JB_MAX_RUN;
+            if (count > 64) return 1;
+            continue;
+        }
+        if (size == 1u) return 1;
+        count += (int)run;
+        if (count >= 64) return 1;
+        if (nb < (int)size) { buf = (buf << 32) | jb_bswap32(words[widx < FI_STREAM_WORDS ? widx : FI_STREAM_WORDS - 1]); ++widx; nb += 32; }
+        const uint32_t raw = (uint32_t)(buf >> (nb - (int)size)) & ((1u << size) - 1u);
+        nb -= (int)size; used += size;
+        if (used > bitlimit) return 1;
+        const int mag = (int)(raw & ((1u << (size - 1)) - 1u));
+        row[izz[count]] = (int16_t)((raw >> (size - 1)) ? mag : -mag);
+        ++count;
+    }
+}
+
+__device__ __forceinline__ int fi_tile_kind(const JbGeom& g, int blk0, int nvalid, int it, bool aligned) {
+    const int n0 = blk0 + 4 * it;
+    if (!aligned || 4 * it + 4 > nvalid) return 2;
+    const int by = n0 / g.hb, bx = n0 - by * g.hb;
+    if (bx + 4 > g.hb) return 2;
+    // fully inside -> 0 (TMA or STG.128); crossing the right / bottom edge -> 1 (TMA clips, else bounded)
+    return ((bx + 4) * 32 <= g.W && (by + 1) * 32 <= g.H) ? 0 : 1;
+}
+
+template <bool DFT, int MODE>
+__global__ void __launch_bounds__(FI_WARPS * 32, 1)
+jb_inv_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FiKernelArgs ka) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const JbInvArgs& a = ka.a;
+    const JbGeom& g = a.g;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t* s_izz = (uint8_t*)smem_raw;                               // zigzag position -> natural index
+    FiWarpSmem& ws = *(FiWarpSmem*)(smem_raw + 128 + (size_t)warp * sizeof(FiWarpSmem));
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) s_izz[i] = (uint8_t)a.t.izz[i];
+    __syncthreads();
+
+    const int li = lane >> 2, lb = lane & 3;
+    const int ncol = DFT ? (li < 5 ? li : 12 - li) : li;               // sample column after the column stage
+    // dequantiser of row u = li with the inverse-transform scale folded in (powers of two: exact)
+    float dq[8];
+    #pragma unroll
+    for (int v = 0; v < 8; ++v) {
+        const float sc = DFT ? (1.0f / 64.0f) : ((li == 0 ? 0.125f : 0.25f) * (v == 0 ? 0.125f : 0.25f));
+        dq[v] = a.t.dqmult[li * 8 + v] * sc;
+    }
+
+    const unsigned total_warps = gridDim.x * FI_WARPS;
+    unsigned store_seq = 0;
+    for (unsigned chunk = blockIdx.x * FI_WARPS + warp; chunk < a.n_chunks; chunk += total_warps) {
+        const int plane = (int)(chunk / (unsigned)g.cpp);
+        const int blk0 = (int)(chunk % (unsigned)g.cpp) * JB_CHUNK;
+        const int nvalid = jb_min(JB_CHUNK, g.nblocks - blk0);
+        const int nit = (nvalid + 3) >> 2;
+
+        // ---- coefficients of the chunk in natural order ----
+        {
+            uint4* z = (uint4*)ws.coef;
+            for (int i = lane; i < JB_CHUNK * FF_COEF_W / 4; i += 32) z[i] = make_uint4(0, 0, 0, 0);
+        }
+        __syncwarp();
+        if (MODE == 2) {
+            const int16_t* src = a.coeffs_in + ((size_t)plane * g.nblocks + blk0) * 64;
+            for (int idx = lane; idx < nvalid * 64; idx += 32)
+                ((int16_t*)(ws.coef + (idx >> 6) * FF_COEF_W))[s_izz[idx & 63]] = src[idx];
+        } else {
+            const unsigned long long len = a.plane_len[plane];
+            const uint8_t* stream = a.in + a.plane_off[plane];
+            const unsigned* bs = a.block_start + (size_t)plane * g.nblocks + blk0;
+            const unsigned my_start = lane < nvalid ? bs[lane] : 0u;
+            const unsigned c_start = __shfl_sync(0xffffffffu, my_start, 0);
+            unsigned c_end = (blk0 + nvalid < g.nblocks) ? bs[nvalid] : (unsigned)len;
+            c_end = __shfl_sync(0xffffffffu, c_end, 0);
+            const unsigned long long addr0 = (unsigned long long)(uintptr_t)(stream + c_start);
+            const unsigned mis = (unsigned)(addr0 & 3ull);
+            bool ok = c_start <= c_end && c_end <= len && (c_end - c_start) + mis <= (FI_STREAM_WORDS - 1) * 4u;
+            if (ok) {
+                const uint32_t* wsrc = (const uint32_t*)(uintptr_t)(addr0 - mis);
+                const unsigned nwords = ((c_end - c_start) + mis + 3u) >> 2;
+                for (unsigned i = lane; i < nwords; i += 32) ws.sbytes[i] = __ldg(wsrc + i);
+            }
+            __syncwarp();
+            int bad = ok ? 0 : 1;
+            if (ok && lane < nvalid) {
+                if (my_start < c_start || my_start >= c_end) bad = 1;
+                else bad = fi_decode_block(ws.sbytes, (my_start - c_start + mis) * 8u, (c_end - c_start + mis) * 8u,
+                                           (int16_t*)(ws.coef + lane * FF_COEF_W), s_izz);
+            }
+            if (__any_sync(0xffffffffu, bad) && lane == 0) jb_set_error(a.status, JB_ERR_BAD_STREAM);
+        }
+        __syncwarp();
+
+        // ---- 4 blocks per iteration ----
+        for (int it = 0; it < nit; ++it) {
+            const int slot = (int)(store_seq % FI_RING);
+            uint8_t* tile = ws.tile[slot];
+            const int kind = fi_tile_kind(g, blk0, nvalid, it, ka.aligned != 0);
+            // the TMA store issued FI_RING tiles ago must have finished reading this slot
+            if (lane == 0) ff_bulk_wait_read<FI_RING - 1>();
+            __syncwarp();
+
+            float z[8], r[8];
+            {
+                const uint4 w = *(const uint4*)(ws.coef + (4 * it + lb) * FF_COEF_W + li * 4);
+                z[0] = (float)(short)(w.x & 0xFFFFu) * dq[0]; z[1] = (float)(short)(w.x >> 16) * dq[1];
+                z[2] = (float)(short)(w.y & 0xFFFFu) * dq[2]; z[3] = (float)(short)(w.y >> 16) * dq[3];
+                z[4] = (float)(short)(w.z & 0xFFFFu) * dq[4]; z[5] = (float)(short)(w.z >> 16) * dq[5];
+                z[6] = (float)(short)(w.w & 0xFFFFu) * dq[6]; z[7] = (float)(short)(w.w >> 16) * dq[7];
+            }
+            if (DFT) ff_rdft8(z, r); else ff_idct8(z, r);
+            {
+                float4* sc = (float4*)(ws.scr + lb * FF_BLK_W + li * 8);
+                const int h0 = li & 1;
+                const float4 r0 = make_float4(r[0], r[1], r[2], r[3]), r1 = make_float4(r[4], r[5], r[6], r[7]);
+                sc[h0] = h0 ? r1 : r0; sc[h0 ^ 1] = h0 ? r0 : r1;
+            }
+            __syncwarp();
+            float col[8], x[8];
+            #pragma unroll
+            for (int k = 0; k < 8; ++k) col[k] = ws.scr[lb * FF_BLK_W + k * 8 + li];
+            if (DFT) ff_dft_column_stage(col, li, x); else ff_idct8(col, x);
+
+            // round half-even, clamp to 0..255, replicate 4x4: word column 8b + ncol, rows 4m..4m+3
+            uint32_t* t32 = (uint32_t*)tile;
+            #pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                int p = __float_as_int(x[m] + 12582912.0f) - 0x4B400000;
+                p = max(0, min(255, p));
+                const uint32_t wv = (uint32_t)p * 0x01010101u;
+                #pragma unroll
+                for (int k = 0; k < 4; ++k) t32[(4 * m + k) * 32 + 8 * lb + ncol] = wv;
+            }
+            __syncwarp();
+
+            const int n0 = blk0 + 4 * it;
+            uint8_t* plane_ptr = a.planes_out + (size_t)plane * a.plane_stride;
+            if (kind <= 1 && ka.use_tma) {
+                if (lane == 0) {
+                    const int by = n0 / g.hb, bx = n0 - by * g.hb;
+                    ff_fence_proxy_async();
+                    ff_tma_store_3d(&tmap, bx * 32, by * 32, plane, tile);
+                    ff_bulk_commit();
+                }
+            } else if (kind == 0) {
+                const int by = n0 / g.hb, bx = n0 - by * g.hb;
+                uint8_t* dst = plane_ptr + (size_t)by * 32 * a.row_pitch + (size_t)bx * 32;
+                const uint4* t16 = (const uint4*)tile;
+                #pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int idx = k * 32 + lane;
+                    *((uint4*)(dst + (size_t)(idx >> 3) * a.row_pitch) + (idx & 7)) = t16[idx];
+                }
+            } else {
+                const int nlive = jb_min(4, nvalid - 4 * it);
+                for (int idx = lane; idx < 1024; idx += 32) {
+                    const int row = idx >> 5, wcol = idx & 31, b = wcol >> 3;
+                    if (b >= nlive) continue;
+                    const int blk = n0 + b;
+                    const int by = blk / g.hb, bx = blk - by * g.hb;
+                    const int yy = by * 32 + row, xx = bx * 32 + (wcol & 7) * 4;
+                    if (yy >= g.H || xx >= g.W) continue;
+                    const uint32_t wv = t32[idx];
+                    uint8_t* d = plane_ptr + (size_t)yy * a.row_pitch + xx;
+                    const int nbytes = jb_min(4, g.W - xx);
+                    for (int q = 0; q < nbytes; ++q) d[q] = (uint8_t)(wv >> (8 * q));
+                }
+            }
+            ++store_seq;
+            __syncwarp();
+        }
+    }
+    if (lane == 0) ff_bulk_wait_read<0>();
+    __syncwarp();
+}
+
+bool jb_inv_fast_eligible(const JbGeom& g) { return g.d == 8 && g.bs == 4; }
+
+template <bool DFT, int MODE>
+static cudaError_t jb_inv_fast_launch_t(const CUtensorMap& map, const FiKernelArgs& ka, cudaStream_t s) {
+    const size_t smem = 128 + (size_t)FI_WARPS * sizeof(FiWarpSmem);
+    cudaError_t e = cudaFuncSetAttribute(jb_inv_fast_kernel<DFT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jb_inv_fast_kernel<DFT, MODE>, FI_WARPS * 32, smem);
+    if (per_sm < 1) per_sm = 1;
+    unsigned want = (ka.a.n_chunks + FI_WARPS - 1) / FI_WARPS;
+    unsigned grid = want < (unsigned)(sms * per_sm) ? want : (unsigned)(sms * per_sm);
+    if (grid == 0) return cudaSuccess;
+    jb_inv_fast_kernel<DFT, MODE><<<grid, FI_WARPS * 32, smem, s>>>(map, ka);
+    return cudaGetLastError();
+}
+
+cudaError_t jb_launch_inv_fast(const JbInvArgs& a, int mode, cudaStream_t s) {
+    FiKernelArgs ka;
+    ka.a = a;
+    const JbGeom& g = a.g;
+    ka.aligned = (((uintptr_t)a.planes_out & 15) == 0 && (a.row_pitch & 15) == 0 &&
+                  (a.n_planes == 1 || (a.plane_stride & 15) == 0)) ? 1 : 0;
+    CUtensorMap map;
+    memset(&map, 0, sizeof(map));
+    ka.use_tma = 0;
+    if (!(g.flags & JB_FLAG_NO_TMA) && ka.aligned)
+        ka.use_tma = jb_make_plane_tensor_map(&map, a.planes_out, g.W, g.H, a.n_planes, a.row_pitch, a.plane_stride) ? 1 : 0;
+    const bool dft = g.transform == JB_TRANSFORM_DFT;
+    if (mode == 0) return dft ? jb_inv_fast_launch_t<true, 0>(map, ka, s) : jb_inv_fast_launch_t<false, 0>(map, ka, s);
+    return dft ? jb_inv_fast_launch_t<true, 2>(map, ka, s) : jb_inv_fast_launch_t<false, 2>(map, ka, s);
+}

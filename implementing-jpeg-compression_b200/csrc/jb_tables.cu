@@ -68,10 +68,11 @@ __global__ void jb_build_tables_kernel(JbGeom g, JbTables t) {
             if (g.transform == JB_TRANSFORM_DCT) {
                 a = cos(PI / d * (m + 0.5) * k);
             } else {
-                // exact reduction of the angle: (k*m mod d) keeps cos/sin arguments small
+                // (k*m mod d) keeps the angle small; cospi/sinpi make the trivial twiddles
+                // (0, +-1) exact, as they are inside an FFT (np.fft.fft2, basis_change.py:23)
                 int r = (k * m) % d;
-                a = cos(2.0 * PI * r / d);
-                b = sin(2.0 * PI * r / d);
+                a = cospi(2.0 * r / d);
+                b = sinpi(2.0 * r / d);
             }
             sa += fabs(a) + fabs(b);
             s2 += a * a;
@@ -94,8 +95,8 @@ __global__ void jb_build_tables_kernel(JbGeom g, JbTables t) {
             ia = (ct / nm) * (1.0 / nm);
         } else {
             int r = (k * m) % d;
-            a = cos(2.0 * PI * r / d);
-            b = sin(2.0 * PI * r / d);
+            a = cospi(2.0 * r / d);
+            b = sinpi(2.0 * r / d);
             ia = a / d;                                       // Re ifft2 = (Cc Q Cc - S Q S) / N^2
             ib = b / d;
         }

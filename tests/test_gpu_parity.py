@@ -10,7 +10,8 @@ from parity import check_pixels, check_quantised
 
 pytestmark = pytest.mark.gpu
 
-FLAG_SETS = [pytest.param(0, id="default"), pytest.param(1, id="generic")]   # JB_FLAG_FORCE_GENERIC = 1
+# JB_FLAG_FORCE_GENERIC = 1, JB_FLAG_NO_TMA = 2 (specialised kernels with plain loads / stores)
+FLAG_SETS = [pytest.param(0, id="default"), pytest.param(1, id="generic"), pytest.param(2, id="no_tma")]
 
 
 @pytest.fixture(scope="module")
