@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""Benchmark of the per-block codec hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[3], the one the metric is quoted on at 1/2/4/8 GPUs): a batch
+of 1024 synthetic 1920x1080 three-band images, --block_size 4 --dct_size 8 --transform DCT,
+table quantisation, sharded by image across the ranks (strong scaling, no collective on the
+data path).  One step = compress the rank's images, then decompress the streams just
+produced.  `value` = source megapixels of the whole batch / step time (device-timed, inputs
+resident in HBM); `e2e` = the same through BatchCodec.compress_host / decompress_host with
+pinned host buffers, host<->device copies inside the timed region.
+
+--impl reference times the CPU restatement of the reference (oracle/ref_port.py: the reference
+is pure Python and does not exist on the GPU box) on all host cores, on a bounded sample.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+N_IMAGES, H, W = 1024, 1080, 1920
+BS, D, TRANSFORM, QNAME = 4, 8, "DCT", "qtable"
+METRIC = "compress+decompress megapixels/s"
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU side (oracle port) -- used for cpu_baseline and --impl reference only
+# ----------------------------------------------------------------------------------------------
+def _cpu_roundtrip_image(planes):
+    """One image (3 planes, numpy uint8) through the oracle; returns (streams, decoded)."""
+    from oracle import ref_port as rp
+    cfg = rp.OracleConfig(planes.shape[2], planes.shape[1], BS, D, TRANSFORM, QNAME)
+    streams = [rp.compress_band(p.astype("int64"), cfg) for p in planes]
+    decoded = [rp.decompress_band(s, cfg) for s in streams]
+    return streams, decoded
+
+
+_CPU_IMAGES = None          # a few distinct synthetic images, built before the pool forks
+
+
+def _cpu_images():
+    global _CPU_IMAGES
+    if _CPU_IMAGES is None:
+        import numpy as np
+        from golden_inputs import synth_plane
+        _CPU_IMAGES = [np.stack([synth_plane(H, W, 1000 * i + b, phase=0.7 * b) for b in range(3)]).astype(np.uint8)
+                       for i in range(4)]
+    return _CPU_IMAGES
+
+
+def _cpu_worker(i):
+    _cpu_roundtrip_image(_CPU_IMAGES[i % len(_CPU_IMAGES)])
+    return 0
+
+
+def cpu_sample_throughput(n_images, procs):
+    """Round-trip n_images synthetic images (compress + decompress, three planes each) over
+    `procs` processes; returns (MP/s of the sample, seconds)."""
+    import multiprocessing as mp
+    _cpu_images()
+    ctx = mp.get_context("fork")
+    with ctx.Pool(procs) as pool:
+        pool.map(_cpu_worker, range(procs), chunksize=1)              # page in numpy in every worker
+        t0 = time.perf_counter()
+        pool.map(_cpu_worker, range(n_images), chunksize=1)
+        dt = time.perf_counter() - t0
+    return n_images * H * W / 1e6 / dt, dt
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = max(2 * cores, 8)
+    vals = []
+    for step in range(args.warmup + args.steps):
+        v, dt = cpu_sample_throughput(sample, cores)
+        if step >= args.warmup:
+            vals.append((v, dt))
+        if sum(d for _, d in vals) > 150:
+            break
+    v = sum(x for x, _ in vals) / len(vals)
+    ms = 1e3 * sum(d for _, d in vals) / len(vals)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "MP/s", "n_gpus": args.gpus,
+        "steps": len(vals), "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": v, "unit": "MP/s", "cores": cores, "kind": "port",
+                         "sample": "%d synthetic 1920x1080 images per step, one image per task, "
+                                   "multiprocessing.Pool(%d), oracle/ref_port.py (float64 numpy restatement; "
+                                   "the reference itself is pure Python and is not shipped to the GPU box)"
+                                   % (sample, cores)},
+        "e2e": {"value": v, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus):
+    return {"workload": "batch of %d synthetic %dx%d 3-band images, block_size %d, dct_size %d, %s, %s "
+                        "quantisation; one step = compress then decompress" % (N_IMAGES, W, H, BS, D, TRANSFORM, QNAME),
+            "images": N_IMAGES, "width": W, "height": H, "block_size": BS, "dct_size": D,
+            "transform": TRANSFORM, "quantization": QNAME,
+            "sharding": "by image, %d per rank, no collective" % (N_IMAGES // max(n_gpus, 1)),
+            "l2": "inputs larger than L2 (%.0f MB per rank vs 126 MB), no flush needed"
+                  % (N_IMAGES // max(n_gpus, 1) * 3 * H * W / 1e6)}
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU side
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons of this rank's GPU during the timed region."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, uuid):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", uuid, "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.tmp.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); smax.append(float(parts[1])); power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.tmp.name)
+        if sm:
+            # "under load": samples drawing at least half of the peak power seen
+            pmax = max(power)
+            loaded = sorted(s for s, p in zip(sm, power) if p >= 0.5 * pmax) or sorted(sm)
+            out.update(sm_mhz=loaded[len(loaded) // 2], sm_max_mhz=max(smax), reasons=sorted(reasons),
+                       samples=len(sm), power_w_max=pmax)
+        return out
+
+
+def synth_planes_device(n_images, device, first_image):
+    """[n_images * 3, H, W] uint8 on the device: clip(127 + 100 sin(x/37 + ph) cos(y/53 + ph) + N(0, 8^2))
+    (SURVEY.md section 8d), seeded per image so that any rank layout gives the same batch."""
+    import torch
+    out = torch.empty((n_images * 3, H, W), dtype=torch.uint8, device=device)
+    ys = torch.arange(H, device=device, dtype=torch.float32).view(H, 1)
+    xs = torch.arange(W, device=device, dtype=torch.float32).view(1, W)
+    gen = torch.Generator(device=device)
+    for i in range(n_images):
+        gen.manual_seed(1000 * (first_image + i) + 7)
+        for b in range(3):
+            ph = 0.7 * b + 0.01 * ((first_image + i) % 97)
+            v = 127.0 + 100.0 * torch.sin(xs / 37.0 + ph) * torch.cos(ys / 53.0 + ph)
+            v = v + 8.0 * torch.randn((H, W), device=device, generator=gen)
+            out[3 * i + b] = v.round().clamp_(0, 255).to(torch.uint8)
+    return out
+
+
+def run_ours(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import jpeg_b200 as jb
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the codec path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    i0, i1 = jb.sharding.image_slice(N_IMAGES, rank, world)
+    n_img = i1 - i0
+    n_planes = 3 * n_img
+    cfg = jb.Configuration(width=W, height=H, block_size=BS, dct_size=D, transform=TRANSFORM,
+                           quantization=jb.QuantizationMethod(QNAME))
+    bc = jb.BatchCodec(cfg, n_planes, device=device)
+    bc.d_planes.copy_(synth_planes_device(n_img, device, i0))
+    torch.cuda.synchronize()
+    mp_rank = n_img * H * W / 1e6
+    mp_total = N_IMAGES * H * W / 1e6
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- untimed: first pass for the stream size, and the parity sample ----
+    comp = bc.compress_device()
+    total_bytes = comp.total_bytes()
+    out, status = bc.decompress_device(comp, total_bytes)
+    jb.check_status(status)
+
+    sampler = None
+    if rank == 0:
+        uuid = str(torch.cuda.get_device_properties(device).uuid)
+        sampler = ClockSampler(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+        if sampler.proc is None:
+            sampler = None
+
+    # ---- device-resident timing ----
+    K, Wm = args.steps, args.warmup
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    for step in range(Wm):
+        comp = bc.compress_device()
+        bc.decompress_device(comp, total_bytes)
+    barrier()
+    for step in range(K):
+        ev[step][0].record()
+        comp = bc.compress_device()
+        ev[step][1].record()
+        bc.decompress_device(comp, total_bytes)
+        ev[step][2].record()
+    barrier()
+    t_c = sum(e[0].elapsed_time(e[1]) for e in ev) / K           # ms per step, compress part
+    t_d = sum(e[1].elapsed_time(e[2]) for e in ev) / K
+    t_all = ev[0][0].elapsed_time(ev[-1][2]) / K
+    t_c, t_d, t_all = max_over_ranks(t_c), max_over_ranks(t_d), max_over_ranks(t_all)
+    jb.check_status(comp.status)
+
+    # ---- end to end through host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        h_planes = torch.empty((n_planes, H, W), dtype=torch.uint8, pin_memory=True)
+        h_planes.copy_(bc.d_planes)
+        torch.cuda.synchronize()
+        for step in range(min(Wm, 2)):
+            hs, offs = bc.compress_host(h_planes)
+            bc.decompress_host(hs, offs)
+        barrier()
+        t0 = time.perf_counter()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for step in range(K):
+            hs, offs = bc.compress_host(h_planes)
+            dec = bc.decompress_host(hs, offs)
+        e1.record()
+        barrier()
+        t_e2e = max_over_ranks(e0.elapsed_time(e1) / K)
+        wall_e2e = max_over_ranks((time.perf_counter() - t0) / K * 1e3)
+        e2e = {"value": mp_total / (t_e2e * 1e-3), "unit": "MP/s",
+               "h2d_bytes_per_step": n_planes * H * W + total_bytes + 8 * (n_planes + 1),
+               "d2h_bytes_per_step": total_bytes + 8 * (n_planes + 1) + 64 + n_planes * H * W,
+               "ms_per_step": t_e2e, "wall_ms_per_step": wall_e2e,
+               "api": "BatchCodec.compress_host + decompress_host (pinned host buffers), per rank",
+               "matches_device_path": bool(torch.equal(dec[:3], bc.d_decoded[:3].cpu()))}
+
+    clocks = sampler.stop() if sampler is not None else {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+
+    # ---- gather totals ----
+    stream_total = total_bytes
+    if world > 1:
+        t = torch.tensor([total_bytes], dtype=torch.float64, device=device)
+        dist.all_reduce(t)
+        stream_total = int(t.item())
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        # per-rank algorithmic bytes of one launch of the fused kernels
+        a_c = n_planes * H * W + total_bytes
+        a_d = total_bytes + n_planes * H * W
+        ach_c = a_c / (t_c * 1e-3) / 1e9
+        ach_d = a_d / (t_d * 1e-3) / 1e9
+        cpu = None if args.no_cpu else cpu_baseline_with_parity(bc, comp, n_img)
+        line = {
+            "metric": METRIC, "value": mp_total / (t_all * 1e-3), "unit": "MP/s", "n_gpus": world,
+            "steps": K, "warmup": Wm, "ms_per_step": t_all, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+            "compress_mps": mp_total / (t_c * 1e-3), "decompress_mps": mp_total / (t_d * 1e-3),
+            "ms_compress": t_c, "ms_decompress": t_d, "stream_bytes": stream_total,
+            "bytes_per_pixel": stream_total / (N_IMAGES * H * W),
+            "roofline": {"bound": "hbm", "kernel": "jb_fwd_fast_kernel (fused compress; timed with the table "
+                         "builder and two memsets of the same call)", "achieved": ach_c, "peak": peak,
+                         "unit": "GB/s", "frac": ach_c / peak, "frac_of_nominal_8000": ach_c / 8000.0,
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": a_c},
+            "roofline_decompress": {"bound": "hbm", "kernel": "framing kernels + jb_inv_fast_kernel",
+                                    "achieved": ach_d, "peak": peak, "unit": "GB/s", "frac": ach_d / peak,
+                                    "frac_of_nominal_8000": ach_d / 8000.0, "traffic": None,
+                                    "algorithmic_bytes_per_launch": a_d},
+            "cpu_baseline": cpu,
+            "e2e": e2e,
+            "gpu_launches": K * 8,       # per step: tables + fused compress; tables + 4 framing + fused decompress
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline_with_parity(bc, comp, n_img):
+    """Rank 0, N-independent: the oracle on the first images of this rank's batch, all host
+    cores; the oracle's outputs double as the parity check of the GPU results."""
+    import numpy as np
+    import torch
+    from oracle import ref_port as rp
+    from parity import check_pixels, check_quantised
+    import jpeg_b200 as jb
+
+    cores = os.cpu_count() or 1
+    sample = max(2 * cores, 8)
+    mps, dt = cpu_sample_throughput(sample, cores)
+    # parity of the GPU batch against the oracle on image 0 (three planes)
+    planes = bc.d_planes[:3].cpu().numpy()
+    offs = comp.host_offsets()
+    blob = comp.data[:int(offs[3])].cpu().numpy().tobytes()
+    streams = [blob[int(offs[i]):int(offs[i + 1])] for i in range(3)]
+    ocfg = rp.OracleConfig(W, H, BS, D, TRANSFORM, QNAME)
+    gpu_coeffs = jb.stages.forward_coefficients(planes, bc.config)
+    exact, ties, maxerr = 0, 0, 0
+    for i in range(3):
+        zz = rp.quantised_zigzag(planes[i].astype(np.int64), ocfg)
+        ties += check_quantised(gpu_coeffs[i], zz, rp.prerounding_zigzag(planes[i].astype(np.int64), ocfg),
+                                what="bench plane %d" % i, strict_fraction=True)
+        assert streams[i] == rp.pack_blocks(gpu_coeffs[i].reshape(-1, D * D))
+        exact += int(streams[i] == rp.compress_band(planes[i].astype(np.int64), ocfg))
+        ref_dec = rp.decompress_band(streams[i], ocfg)
+        got = bc.d_decoded[i].cpu().numpy()
+        check_pixels(got, ref_dec, planes[i], what="bench plane %d" % i)
+        maxerr = max(maxerr, int(np.abs(got.astype(np.int64) - ref_dec).max()))
+    return {"value": mps, "unit": "MP/s", "cores": cores, "kind": "port",
+            "sample": "%d synthetic 1920x1080 images, one per task, multiprocessing.Pool(%d), %.1f s; "
+                      "oracle/ref_port.py (float64 numpy restatement of the reference)" % (sample, cores, dt),
+            "parity_image0": {"streams_byte_exact": "%d/3" % exact, "tie_mismatches": ties,
+                              "max_pixel_error": maxerr}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--images", type=int, default=N_IMAGES, help="batch size (profiling runs use a smaller one)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
+    args = ap.parse_args()
+    global N_IMAGES
+    N_IMAGES = args.images
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if args.warmup < 3:
+        args.warmup = 3                       # timing rule: at least three warm-up steps
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -12,11 +12,11 @@ from .errors import (BadArrayShapeError, BadQuantizationError, BadRleCodeError, 
 from .config import Configuration, QuantizationMethod  # noqa: F401
 from . import file_format  # noqa: F401
 from .file_format import CompressedData  # noqa: F401
-from .codec import (Jpeg, CompressedPlanes, compress_band, decompress_band, compress_bands,  # noqa: F401
+from .codec import (Jpeg, CompressedPlanes, BatchCodec, compress_band, decompress_band, compress_bands,  # noqa: F401
                     decompress_bands, compress_planes, decompress_planes, check_status, geometry)
 from . import stages, sharding  # noqa: F401
 
-__all__ = ["Configuration", "QuantizationMethod", "Jpeg", "CompressedData", "CompressedPlanes",
+__all__ = ["Configuration", "QuantizationMethod", "Jpeg", "CompressedData", "CompressedPlanes", "BatchCodec",
            "compress_band", "decompress_band", "compress_bands", "decompress_bands", "compress_planes",
            "decompress_planes", "check_status", "geometry", "file_format", "stages", "sharding",
            "BadArrayShapeError", "BadQuantizationError", "BadRleCodeError", "BadStreamError",

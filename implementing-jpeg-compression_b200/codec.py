@@ -272,3 +272,66 @@ class Jpeg:
         planes = decompress_bands([data.y, data.cb, data.cr], config)
         # np.dstack(...).astype(np.uint8) -> Image.fromarray(mode='YCbCr'), :120-124
         return Image.merge("YCbCr", [Image.fromarray(np.ascontiguousarray(planes[i]), "L") for i in range(3)])
+
+
+class BatchCodec:
+    """Repeated batched (de)compression of ``n_planes`` equally sized planes with buffers that
+    are allocated once: device staging for the planes and the streams, pinned host buffers for
+    the host-facing calls.  This is the call a service that compresses frame batches makes."""
+
+    def __init__(self, config, n_planes, device=None, flags=0, pinned=True):
+        lib = _lib.load()
+        self.config, self.n_planes, self.flags = config, int(n_planes), flags
+        self.device = _require_cuda(device)
+        p = config.c_params(flags)
+        g = _lib.jb_geometry()
+        _raise_for_code(lib.jb_geometry_of(ctypes.byref(p), ctypes.byref(g)))
+        self.h, self.w = int(config.height), int(config.width)
+        self.cap = lib.jb_max_stream_bytes(ctypes.byref(p), self.n_planes)
+        with torch.cuda.device(self.device):
+            self.d_planes = torch.empty((self.n_planes, self.h, self.w), dtype=torch.uint8, device=self.device)
+            self.d_streams = torch.empty(self.cap, dtype=torch.uint8, device=self.device)
+            self.d_decoded = torch.empty((self.n_planes, self.h, self.w), dtype=torch.uint8, device=self.device)
+        self.pinned = pinned
+        self.h_streams = None
+        self.h_decoded = None
+
+    # -- device-resident --------------------------------------------------------------------
+    def compress_device(self, planes=None):
+        return compress_planes(self.d_planes if planes is None else planes, self.config, flags=self.flags,
+                               out=self.d_streams)
+
+    def decompress_device(self, comp, total_bytes):
+        lengths = comp.offsets[1:] - comp.offsets[:-1]
+        return decompress_planes(comp.data, comp.offsets[:-1], lengths, self.config, self.n_planes,
+                                 in_bytes=int(total_bytes), flags=self.flags, out=self.d_decoded)
+
+    # -- host buffers in, host buffers out ------------------------------------------------------
+    def compress_host(self, h_planes):
+        """h_planes: uint8 host tensor [n, H, W] (pinned for full copy speed).  Returns
+        (host uint8 tensor holding the concatenated streams, int64 numpy offsets [n + 1])."""
+        self.d_planes.copy_(h_planes, non_blocking=True)
+        comp = self.compress_device()
+        offsets = comp.host_offsets()                      # syncs, raises on a device-side error
+        total = int(offsets[-1])
+        if self.h_streams is None or self.h_streams.numel() < total:
+            self.h_streams = torch.empty(max(total, 1), dtype=torch.uint8, pin_memory=self.pinned)
+        out = self.h_streams[:total]
+        out.copy_(comp.data[:total], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out, offsets
+
+    def decompress_host(self, h_streams, offsets):
+        """Inverse of compress_host; returns a uint8 host tensor [n, H, W]."""
+        total = int(offsets[-1])
+        self.d_streams[:total].copy_(h_streams[:total], non_blocking=True)
+        d_off = torch.from_numpy(np.ascontiguousarray(offsets, dtype=np.int64)).to(self.device, non_blocking=True)
+        lengths = d_off[1:] - d_off[:-1]
+        out, status = decompress_planes(self.d_streams, d_off[:-1], lengths, self.config, self.n_planes,
+                                        in_bytes=total, flags=self.flags, out=self.d_decoded)
+        if self.h_decoded is None:
+            self.h_decoded = torch.empty((self.n_planes, self.h, self.w), dtype=torch.uint8, pin_memory=self.pinned)
+        self.h_decoded.copy_(out, non_blocking=True)
+        check_status(status)                               # syncs
+        torch.cuda.current_stream().synchronize()
+        return self.h_decoded
