@@ -371,6 +371,7 @@ def cpu_baseline_with_parity(bc, comp, n_img):
 
 
 def main():
+    global N_IMAGES
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -380,7 +381,6 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
     args = ap.parse_args()
-    global N_IMAGES
     N_IMAGES = args.images
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
