@@ -53,12 +53,16 @@ extern "C" size_t jb_max_stream_bytes(const jb_params* p, int n_planes) {
 }
 
 // ---- compress ----------------------------------------------------------------------------------
-struct JbFwdWs { size_t desc, ticket, total; };
+struct JbFwdWs { size_t ticket, chunk_len, chunk_off, seg_total, tmp, total; unsigned chunk_cap; };
 static JbFwdWs jb_fwd_ws(int d, size_t n_chunks) {
     JbFwdWs w;
     size_t o = jb_align_up(jb_table_layout(d).total, 256);
-    w.desc = o;   o += jb_align_up(n_chunks * 8, 256);
-    w.ticket = o; o += 256;
+    w.chunk_cap = (unsigned)jb_align_up((size_t)JB_CHUNK * jb_max_block_bytes(d * d) + 16, 16);
+    w.ticket = o;    o += 256;
+    w.chunk_len = o; o += jb_align_up(n_chunks * 4, 256);
+    w.chunk_off = o; o += jb_align_up(n_chunks * 4, 256);
+    w.seg_total = o; o += jb_align_up(((n_chunks + JB_SCAN_SEG - 1) / JB_SCAN_SEG) * 8, 256);
+    w.tmp = o;       o += jb_align_up(n_chunks * (size_t)w.chunk_cap, 256);
     w.total = o;
     return w;
 }
@@ -93,7 +97,7 @@ static int jb_forward_common(int mode, const uint8_t* d_planes, size_t plane_str
     char* ws = (char*)d_ws;
     int rc = jb_reset_status(d_status, s);
     if (rc != JB_OK) return rc;
-    JB_CUDA_TRY(cudaMemsetAsync(ws + w.desc, 0, w.total - w.desc, s));
+    JB_CUDA_TRY(cudaMemsetAsync(ws + w.ticket, 0, 256, s));
 
     JbFwdArgs a;
     memset(&a, 0, sizeof(a));
@@ -104,8 +108,12 @@ static int jb_forward_common(int mode, const uint8_t* d_planes, size_t plane_str
     a.out = d_out; a.out_cap = out_cap;
     a.plane_off = (unsigned long long*)d_plane_off;
     a.status = (unsigned long long*)d_status;
-    a.desc = (unsigned long long*)(ws + w.desc);
     a.ticket = (unsigned*)(ws + w.ticket);
+    a.chunk_len = (unsigned*)(ws + w.chunk_len);
+    a.chunk_off = (unsigned*)(ws + w.chunk_off);
+    a.seg_total = (unsigned long long*)(ws + w.seg_total);
+    a.tmp = (uint8_t*)(ws + w.tmp);
+    a.chunk_cap = w.chunk_cap;
     a.coeffs_out = d_coeffs_out; a.coeffs_in = d_coeffs_in;
     if (mode != 2) JB_CUDA_TRY(jb_launch_build_tables(g, a.t, s));
     if (mode != 2 && !(g.flags & JB_FLAG_FORCE_GENERIC) && jb_fwd_fast_eligible(g))

@@ -101,73 +101,42 @@ __device__ __forceinline__ void jb_report_bad_code(unsigned long long* status, u
     jb_set_error(status, JB_ERR_BAD_RLE_CODE);
 }
 
-// ---- decoupled look-back over chunk byte lengths ----------------------------------------
-// desc[c] = flag << 62 | value; flag 0 = not ready, 1 = aggregate (this chunk's bytes),
-// 2 = inclusive prefix (bytes of chunks 0..c).
-#define JB_DESC_AGG (1ull << 62)
-#define JB_DESC_PFX (2ull << 62)
-#define JB_DESC_VAL (~(3ull << 62))
-
-__device__ __forceinline__ unsigned long long jb_ld_relaxed(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void jb_st_relaxed(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
-}
-
-// Called by a full warp; `mine` = this chunk's byte count (uniform).  Returns the
-// exclusive prefix (bytes of all earlier chunks).  Chunks must be claimed in
-// increasing order (atomic ticket) so that every predecessor is already running.
-// A bounded spin turns a lost descriptor into an error instead of a hang.
-__device__ __forceinline__ unsigned long long jb_lookback_exclusive(unsigned long long* desc, unsigned chunk,
-                                                                    unsigned long long mine, int lane,
-                                                                    unsigned long long* status) {
-    if (chunk == 0) {
-        if (lane == 0) jb_st_relaxed(desc, JB_DESC_PFX | mine);
-        return 0ull;
-    }
-    if (lane == 0) jb_st_relaxed(desc + chunk, JB_DESC_AGG | mine);
-    unsigned long long excl = 0ull;
-    long long look = (long long)chunk - 1;     // highest predecessor not yet accounted for
-    int spins = 0;
-    while (true) {
-        long long idx = look - lane;
-        unsigned long long v = (idx >= 0) ? jb_ld_relaxed(desc + idx) : JB_DESC_PFX;   // virtual prefix 0 before chunk 0
-        unsigned flag = (unsigned)(v >> 62);
-        unsigned not_ready = __ballot_sync(0xffffffffu, flag == 0u);
-        unsigned has_pfx = __ballot_sync(0xffffffffu, flag == 2u);
-        // usable window: lanes below the first not-ready lane; stop at the first prefix
-        int first_nr = not_ready ? __ffs(not_ready) - 1 : 32;
-        int first_pf = has_pfx ? __ffs(has_pfx) - 1 : 32;
-        int take = first_pf < first_nr ? first_pf + 1 : first_nr;   // number of lanes to add
-        unsigned long long contrib = (lane < take) ? (v & JB_DESC_VAL) : 0ull;
-        #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-        excl += contrib;
-        if (first_pf < first_nr) break;          // reached an inclusive prefix
-        look -= take;
-        if (take == 0) {
-            if (++spins > (1 << 22)) {           // ~seconds: give up loudly, never hang the GPU
-                if (lane == 0) jb_set_error(status, JB_ERR_CUDA);
-                break;
-            }
-            __nanosleep(64);
-        } else {
-            spins = 0;
-        }
-    }
-    if (lane == 0) jb_st_relaxed(desc + chunk, JB_DESC_PFX | (excl + mine));
-    return excl;
-}
-
 // ---- small helpers -------------------------------------------------------------------------
 __device__ __forceinline__ int jb_min(int a, int b) { return a < b ? a : b; }
 
 // round-half-even to integer for |x| < 2^22 without a conversion instruction
 __device__ __forceinline__ float jb_rint_magic(float x) {
     return (x + 12582912.0f) - 12582912.0f;
+}
+
+__device__ __forceinline__ unsigned jb_warp_excl_scan(unsigned v, int lane, unsigned* total) {
+    unsigned incl = v;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    *total = __shfl_sync(0xffffffffu, incl, 31);
+    return incl - v;
+}
+
+// exclusive scan across a block of up to 1024 threads; every thread must call
+__device__ __forceinline__ unsigned jb_block_excl_scan(unsigned v, unsigned* s_warp /*[33]*/, unsigned* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    unsigned wtot;
+    unsigned ex = jb_warp_excl_scan(v, lane, &wtot);
+    __syncthreads();                       // protect s_warp from the previous use
+    if (lane == 0) s_warp[warp] = wtot;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned w = lane < nw ? s_warp[lane] : 0u, t;
+        unsigned wex = jb_warp_excl_scan(w, lane, &t);
+        s_warp[lane] = wex;
+        if (lane == 0) s_warp[32] = t;
+    }
+    __syncthreads();
+    *total = s_warp[32];
+    return ex + s_warp[warp];
 }
 
 // Host-side API internals shared between translation units.

@@ -9,9 +9,10 @@
 //   jb_fwd_fast kernels   : see jb_forward_fast.cuh (dct_size 8, block_size 4).
 //
 // Output order is the reference's: blocks in raster order inside a plane
-// (run_length_encoding.py:56-60), planes concatenated; the byte offset of every chunk
-// comes from a decoupled look-back scan over chunk lengths, so the kernel writes each
-// block's bytes once, at its final position.
+// (run_length_encoding.py:56-60), planes concatenated.  The transform kernels leave every
+// chunk's packed bytes in a per-chunk slot; a device-wide exclusive scan of the chunk lengths
+// and a gather pass put them in place (the streams are ~2 % of the pixel bytes, so the extra
+// pass costs ~4 % more traffic and needs no inter-block waiting).
 #include "jb_common.cuh"
 #include "jb_forward.cuh"
 
@@ -98,8 +99,6 @@ jb_fwd_generic_kernel(const JbFwdArgs a) {
 
     __shared__ unsigned s_chunk;
     __shared__ unsigned s_blen[JB_CHUNK], s_boff[JB_CHUNK];
-    __shared__ unsigned long long s_base;
-    __shared__ unsigned s_total;
     __shared__ JbBigAmp s_big[JB_BIGAMP_CAP];
     __shared__ int s_nbig;
 
@@ -226,25 +225,91 @@ jb_fwd_generic_kernel(const JbFwdArgs a) {
         const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
         s_blen[tid] = len;
         s_boff[tid] = incl - len;
-        unsigned long long base = jb_lookback_exclusive(a.desc, chunk, total, tid, a.status);
-        if (tid == 0) {
-            s_base = base;
-            s_total = total;
-            if (chunk % g.cpp == 0) a.plane_off[plane] = base;
-            if (chunk == a.n_chunks - 1) a.plane_off[a.n_planes] = base + total;
-        }
+        if (tid == 0) a.chunk_len[chunk] = total;
     }
     __syncthreads();
-    const unsigned long long base = s_base;
-    if (base + s_total > a.out_cap) {
-        if (tid == 0) jb_set_error(a.status, JB_ERR_OUT_CAPACITY);
-        return;
-    }
+    // compacted copy of the chunk into its slot of the temporary buffer; the scan + gather
+    // kernels below move it to its final place in the stream
+    uint8_t* slot = a.tmp + (size_t)chunk * a.chunk_cap;
     for (int gi = 0; gi < nvalid; ++gi) {
         const uint8_t* sb = (const uint8_t*)(sStage + gi * L.stageW);
-        uint8_t* dst = a.out + base + s_boff[gi];
+        uint8_t* dst = slot + s_boff[gi];
         for (unsigned j = tid; j < s_blen[gi]; j += JB_GENERIC_THREADS) dst[j] = sb[j];
     }
+}
+
+// ----------------------------------------------------------------------------------------------
+// device-wide exclusive scan of the chunk lengths, then gather
+//   S1: one CTA per segment of JB_SCAN_SEG chunks: offsets inside the segment + segment total
+//   S2: one CTA: exclusive scan of the segment totals (in place) + grand total
+//   S3: one warp per chunk: copy tmp slot -> out[base], record the start of every plane
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(JB_SCAN_SEG) jb_scan_local_kernel(JbFwdArgs a) {
+    __shared__ unsigned s_warp[33];
+    const unsigned c = blockIdx.x * JB_SCAN_SEG + threadIdx.x;
+    const unsigned len = c < a.n_chunks ? a.chunk_len[c] : 0u;
+    unsigned total;
+    const unsigned ex = jb_block_excl_scan(len, s_warp, &total);
+    if (c < a.n_chunks) a.chunk_off[c] = ex;
+    if (threadIdx.x == 0) a.seg_total[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) jb_scan_segments_kernel(JbFwdArgs a, unsigned n_seg) {
+    __shared__ unsigned s_warp[33];
+    __shared__ unsigned long long s_carry;
+    if (threadIdx.x == 0) s_carry = 0ull;
+    __syncthreads();
+    for (unsigned base = 0; base < n_seg; base += 1024) {
+        const unsigned i = base + threadIdx.x;
+        // segment totals fit 32 bits (JB_SCAN_SEG chunks of < 2^20 bytes each would not, so split hi/lo)
+        const unsigned long long v = i < n_seg ? a.seg_total[i] : 0ull;
+        unsigned tlo, thi;
+        const unsigned lo = jb_block_excl_scan((unsigned)(v & 0xFFFFFu), s_warp, &tlo);
+        const unsigned hi = jb_block_excl_scan((unsigned)(v >> 20), s_warp, &thi);
+        const unsigned long long carry = s_carry;
+        if (i < n_seg) a.seg_total[i] = carry + (((unsigned long long)hi) << 20) + lo;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + (((unsigned long long)thi) << 20) + tlo;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        a.plane_off[a.n_planes] = s_carry;
+        if (s_carry > a.out_cap) jb_set_error(a.status, JB_ERR_OUT_CAPACITY);
+    }
+}
+
+__global__ void __launch_bounds__(256) jb_gather_chunks_kernel(JbFwdArgs a) {
+    const int lane = threadIdx.x & 31;
+    const unsigned c = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (c >= a.n_chunks) return;
+    const unsigned len = a.chunk_len[c];
+    const unsigned long long base = a.seg_total[c / JB_SCAN_SEG] + a.chunk_off[c];
+    if (lane == 0 && c % (unsigned)a.g.cpp == 0) a.plane_off[c / (unsigned)a.g.cpp] = base;
+    if (base + len > a.out_cap) return;                       // flagged by the segment scan
+    const uint8_t* src = a.tmp + (size_t)c * a.chunk_cap;
+    uint8_t* dst = a.out + base;
+    // head bytes up to a 4-byte boundary of dst, then word stores fed by unaligned byte gathers
+    const unsigned head = jb_min((int)len, (int)((4u - (unsigned)((uintptr_t)dst & 3u)) & 3u));
+    if (lane < (int)head) dst[lane] = src[lane];
+    const unsigned nwords = (len - head) >> 2;
+    const uint32_t* s32 = (const uint32_t*)src;               // slot is 16-byte aligned
+    uint32_t* d32 = (uint32_t*)(dst + head);
+    const unsigned sh = (head & 3u) * 8u;
+    for (unsigned i = lane; i < nwords; i += 32) {
+        const unsigned w0 = s32[(head >> 2) + i], w1 = s32[(head >> 2) + i + 1];
+        d32[i] = sh ? __funnelshift_r(w0, w1, sh) : w0;
+    }
+    const unsigned tail0 = head + nwords * 4u;
+    if (tail0 + lane < len) dst[tail0 + lane] = src[tail0 + lane];
+}
+
+cudaError_t jb_launch_scan_gather(const JbFwdArgs& a, cudaStream_t s) {
+    if (a.n_chunks == 0) return cudaSuccess;
+    const unsigned n_seg = (a.n_chunks + JB_SCAN_SEG - 1) / JB_SCAN_SEG;
+    jb_scan_local_kernel<<<n_seg, JB_SCAN_SEG, 0, s>>>(a);
+    jb_scan_segments_kernel<<<1, 1024, 0, s>>>(a, n_seg);
+    jb_gather_chunks_kernel<<<(a.n_chunks + 7) / 8, 256, 0, s>>>(a);
+    return cudaGetLastError();
 }
 
 cudaError_t jb_launch_fwd_generic(const JbFwdArgs& a, int mode, cudaStream_t s) {
@@ -257,7 +322,8 @@ cudaError_t jb_launch_fwd_generic(const JbFwdArgs& a, int mode, cudaStream_t s) 
         e = cudaFuncSetAttribute(jb_fwd_generic_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         jb_fwd_generic_kernel<0><<<a.n_chunks, JB_GENERIC_THREADS, smem, s>>>(a);
-        break;
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        return jb_launch_scan_gather(a, s);
     case 1:
         e = cudaFuncSetAttribute(jb_fwd_generic_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -267,7 +333,8 @@ cudaError_t jb_launch_fwd_generic(const JbFwdArgs& a, int mode, cudaStream_t s) 
         e = cudaFuncSetAttribute(jb_fwd_generic_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         jb_fwd_generic_kernel<2><<<a.n_chunks, JB_GENERIC_THREADS, smem, s>>>(a);
-        break;
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        return jb_launch_scan_gather(a, s);
     }
     return cudaGetLastError();
 }

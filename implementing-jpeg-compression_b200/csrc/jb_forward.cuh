@@ -15,13 +15,21 @@ struct JbFwdArgs {
     unsigned long long out_cap;
     unsigned long long* plane_off;    // n_planes + 1
     unsigned long long* status;       // JB_STATUS_WORDS
-    unsigned long long* desc;         // n_chunks look-back descriptors (zeroed)
+    uint8_t* tmp;                     // n_chunks * chunk_cap: each chunk's packed bytes, compacted
+    unsigned chunk_cap;               // bytes reserved per chunk in tmp (multiple of 16)
+    unsigned* chunk_len;              // n_chunks: packed bytes of each chunk
+    unsigned* chunk_off;              // n_chunks: offset of the chunk inside its scan segment
+    unsigned long long* seg_total;    // per scan segment (JB_SCAN_SEG chunks): bytes, then exclusive base
     unsigned* ticket;                 // chunk ticket counter (zeroed)
     int16_t* coeffs_out;              // MODE 1
     const int32_t* coeffs_in;         // MODE 2
 };
 
+#define JB_SCAN_SEG 1024            // chunks per scan segment (one CTA of the local scan)
+
 size_t jb_fwd_generic_smem_bytes(int d, bool dft);
+// device-wide exclusive scan of chunk lengths + gather of the chunks into the output stream
+cudaError_t jb_launch_scan_gather(const JbFwdArgs& a, cudaStream_t s);
 cudaError_t jb_launch_fwd_generic(const JbFwdArgs& a, int mode, cudaStream_t s);
 
 // specialised path: dct_size 8, block_size 4 (jb_forward_fast.cu)

@@ -14,8 +14,9 @@
 //     fp32 error bound of a rounding tie are re-evaluated in fp64 the way the reference
 //     computes them) -> int16 store at the zigzag position.
 //   * then lane t run-length-encodes and bit-packs block t of the chunk (util.py:146-160,
-//     203-221), the warp scans the 32 byte lengths, gets its output offset by decoupled
-//     look-back over all earlier chunks, and copies the packed bytes out.
+//     203-221), the warp scans the 32 byte lengths and writes the packed bytes, compacted,
+//     to the chunk's slot of a temporary buffer; a device-wide exclusive scan of the chunk
+//     lengths and a gather (jb_forward.cu) then place every chunk in the output stream.
 // No block-level synchronisation: warps are independent after the table preload.
 #include <cuda.h>
 #include <string.h>
@@ -362,19 +363,15 @@ jb_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfKernelArgs 
             }
             const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
             const unsigned excl = incl - len;
-            const unsigned long long base = jb_lookback_exclusive(a.desc, cur, total, lane, a.status);
-            if (lane == 0) {
-                if (cur % (unsigned)g.cpp == 0) a.plane_off[plane] = base;
-                if (cur == a.n_chunks - 1) a.plane_off[a.n_planes] = base + total;
-            }
-            if (base + total > a.out_cap) {
-                if (lane == 0) jb_set_error(a.status, JB_ERR_OUT_CAPACITY);
-            } else {
+            // compacted copy into the chunk's slot; jb_launch_scan_gather moves it to its final place
+            if (lane == 0) a.chunk_len[cur] = total;
+            {
+                uint8_t* slot = a.tmp + (size_t)cur * a.chunk_cap;
                 for (int bk = 0; bk < nvalid; ++bk) {
                     const unsigned l = __shfl_sync(0xffffffffu, len, bk);
                     const unsigned o = __shfl_sync(0xffffffffu, excl, bk);
                     const uint8_t* sb = (const uint8_t*)(ws.stage + bk * FF_STAGE_W);
-                    uint8_t* dst = a.out + base + o;
+                    uint8_t* dst = slot + o;
                     for (unsigned j = lane; j < l; j += 32) dst[j] = sb[j];
                 }
             }
@@ -462,6 +459,10 @@ cudaError_t jb_launch_fwd_fast(const JbFwdArgs& a, int mode, cudaStream_t s) {
     if (!(g.flags & JB_FLAG_NO_TMA) && ka.aligned)
         ka.use_tma = jb_make_plane_tensor_map(&map, a.planes, g.W, g.H, a.n_planes, a.row_pitch, a.plane_stride) ? 1 : 0;
     const bool dft = g.transform == JB_TRANSFORM_DFT;
-    if (mode == 0) return dft ? jb_fwd_fast_launch_t<true, 0>(map, ka, s) : jb_fwd_fast_launch_t<false, 0>(map, ka, s);
+    if (mode == 0) {
+        cudaError_t e = dft ? jb_fwd_fast_launch_t<true, 0>(map, ka, s) : jb_fwd_fast_launch_t<false, 0>(map, ka, s);
+        if (e != cudaSuccess) return e;
+        return jb_launch_scan_gather(a, s);
+    }
     return dft ? jb_fwd_fast_launch_t<true, 1>(map, ka, s) : jb_fwd_fast_launch_t<false, 1>(map, ka, s);
 }

@@ -24,36 +24,6 @@
 #define JB_TERM 0xFFFFu
 #define JB_EX_INVALID 0xFFFFu
 
-__device__ __forceinline__ unsigned jb_warp_excl_scan(unsigned v, int lane, unsigned* total) {
-    unsigned incl = v;
-    #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += y;
-    }
-    *total = __shfl_sync(0xffffffffu, incl, 31);
-    return incl - v;
-}
-
-// exclusive scan across a block of up to 1024 threads; every thread must call
-__device__ unsigned jb_block_excl_scan(unsigned v, unsigned* s_warp /*[33]*/, unsigned* total) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-    unsigned wtot;
-    unsigned ex = jb_warp_excl_scan(v, lane, &wtot);
-    __syncthreads();                       // protect s_warp from the previous use
-    if (lane == 0) s_warp[warp] = wtot;
-    __syncthreads();
-    if (warp == 0) {
-        unsigned w = lane < nw ? s_warp[lane] : 0u, t;
-        unsigned wex = jb_warp_excl_scan(w, lane, &t);
-        s_warp[lane] = wex;
-        if (lane == 0) s_warp[32] = t;
-    }
-    __syncthreads();
-    *total = s_warp[32];
-    return ex + s_warp[warp];
-}
-
 // ---- F0: tiles per stream -------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) jb_frame_prep_kernel(JbFrameArgs f) {
     __shared__ unsigned s_warp[33];
