@@ -51,30 +51,53 @@ struct JbBitWriter {
     uint32_t* out;
     uint64_t acc;     // low `nacc` bits are pending
     int nacc;         // < 32 between calls
-    int nwords;
+    int nwords;       // words produced so far (stored only while < cap)
+    int cap;          // capacity of `out` in words; bits beyond it are counted, not stored
 
-    JB_HD void init(uint32_t* o) { out = o; acc = 0; nacc = 0; nwords = 0; }
+    JB_HD void init(uint32_t* o, int cap_words = 0x7fffffff) { out = o; acc = 0; nacc = 0; nwords = 0; cap = cap_words; }
 
     JB_HD void put(uint32_t v, int k) {          // k <= 23
         acc = (acc << k) | (uint64_t)v;
         nacc += k;
         if (nacc >= 32) {
             nacc -= 32;
-            out[nwords++] = jb_bswap32((uint32_t)(acc >> nacc));
+            if (nwords < cap) out[nwords] = jb_bswap32((uint32_t)(acc >> nacc));
+            ++nwords;
         }
     }
 
     // returns the block length in bytes (after zero padding to a byte boundary)
     JB_HD uint32_t finish() {
         uint32_t bits = (uint32_t)nwords * 32u + (uint32_t)nacc;
-        if (nacc) out[nwords] = jb_bswap32((uint32_t)(acc << (32 - nacc)));
+        if (nacc && nwords < cap) out[nwords] = jb_bswap32((uint32_t)(acc << (32 - nacc)));
         return (bits + 7u) >> 3;
+    }
+};
+
+// Same interface, writing bytes to an arbitrary (unaligned) address: the slow path for
+// blocks that do not fit the fixed-size staging row of the specialised kernel.
+struct JbByteWriter {
+    uint8_t* out;
+    uint64_t acc;
+    int nacc;         // < 8 between calls
+    uint32_t nbytes;
+
+    JB_HD void init(uint8_t* o) { out = o; acc = 0; nacc = 0; nbytes = 0; }
+    JB_HD void put(uint32_t v, int k) {
+        acc = (acc << k) | (uint64_t)v;
+        nacc += k;
+        while (nacc >= 8) { nacc -= 8; out[nbytes++] = (uint8_t)(acc >> nacc); }
+    }
+    JB_HD uint32_t finish() {
+        if (nacc) { out[nbytes++] = (uint8_t)(acc << (8 - nacc)); nacc = 0; }
+        return nbytes;
     }
 };
 
 // Emit the code(s) for one non-zero coefficient.  Returns false if the amplitude
 // does not fit (BadRleCodeError in the reference); nothing is emitted then.
-JB_HD bool jb_put_coefficient(JbBitWriter& w, int run, int amp) {
+template <typename Writer>
+JB_HD bool jb_put_coefficient(Writer& w, int run, int amp) {
     uint32_t mag = (uint32_t)(amp < 0 ? -amp : amp);
     if (mag > JB_MAX_AMP) return false;
     while (run >= JB_MAX_RUN) { w.put(0xF0u, 8); run -= JB_MAX_RUN; }

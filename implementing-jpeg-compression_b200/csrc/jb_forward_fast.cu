@@ -14,9 +14,11 @@
 //     fp32 error bound of a rounding tie are re-evaluated in fp64 the way the reference
 //     computes them) -> int16 store at the zigzag position.
 //   * then lane t run-length-encodes and bit-packs block t of the chunk (util.py:146-160,
-//     203-221), the warp scans the 32 byte lengths and writes the packed bytes, compacted,
-//     to the chunk's slot of a temporary buffer; a device-wide exclusive scan of the chunk
-//     lengths and a gather (jb_forward.cu) then place every chunk in the output stream.
+//     203-221) into a 64-byte staging row, the warp scans the 32 byte lengths, compacts the
+//     rows in shared memory and writes the chunk with 128-bit stores to its slot of a
+//     temporary buffer (blocks longer than 64 bytes are packed again, straight to the slot);
+//     a device-wide exclusive scan of the chunk lengths and a gather (jb_forward.cu) then
+//     place every chunk in the output stream.
 // No block-level synchronisation: warps are independent after the table preload.
 #include <cuda.h>
 #include <string.h>
@@ -25,15 +27,16 @@
 #include "jb_fast_common.cuh"
 #include "jb_forward.cuh"
 
-#define FF_WARPS 8
-#define FF_RING 3
-#define FF_STAGE_W 49       // words per packed-bytes row: ceil(185 / 4) = 47 -> odd stride
+#define FF_WARPS 14
+#define FF_RING 2
+#define FF_STAGE_W 17       // words per packed-bytes row: 64 bytes + 1 word (odd stride)
+#define FF_STAGE_CAP 16     // words a block may occupy in its staging row; longer blocks take the slow path
 #define FF_BIG_CAP 8
+#define FF_COMPACT_BYTES (JB_CHUNK * FF_COEF_W * 4)   // the coefficient rows double as the compaction buffer
 
 struct __align__(128) FfWarpSmem {
     uint8_t tile[FF_RING][FF_TILE_BYTES];
-    float scr[4 * FF_BLK_W];            // row-pass results, [block][row][col]
-    float stash[4 * FF_BLK_W];          // box sums of the 4 blocks (fp64 re-evaluation input)
+    float scr[4 * FF_BLK_W];            // row-pass results [block][row][col]; on demand also the box sums
     uint32_t coef[JB_CHUNK * FF_COEF_W];
     uint32_t stage[JB_CHUNK * FF_STAGE_W];
     unsigned long long bar[FF_RING];
@@ -66,20 +69,40 @@ __device__ __noinline__ double ff_refine8(const float* X, int u, int v, const Ff
     return y;
 }
 
-// ---- tile classification and staging ----------------------------------------------------------
-// kind 0: whole 32x128 tile inside the image, 16-byte aligned rows -> TMA (or LDG.128 when TMA is off)
-// kind 2: touches an edge / wraps a block row / partial group     -> clamped byte loads
-__device__ __forceinline__ int ff_tile_kind(const JbGeom& g, int blk0, int nvalid, int it, bool aligned) {
-    const int n0 = blk0 + 4 * it;
-    if (!aligned || 4 * it + 4 > nvalid) return 2;
-    const int by = n0 / g.hb, bx = n0 - by * g.hb;
-    if (bx + 4 > g.hb || (bx + 4) * 32 > g.W || (by + 1) * 32 > g.H) return 2;
-    return 0;
+// ---- tile staging -----------------------------------------------------------------------------
+// kind 0: the 32 x 128 tile lies inside the image, rows 16-byte aligned  -> TMA (LDG.128 when TMA is off)
+// kind 1: same columns, but rows run past the bottom edge              -> LDG.128 with replicated rows
+// kind 2: right edge, block-row wrap, partial group or unaligned plane -> clamped byte loads
+struct FfCursor {           // position of a 4-block group inside the stream of chunks (warp-uniform)
+    unsigned chunk;
+    int plane, blk0, nvalid, nit, it;
+    int by, bx;             // block coordinates of the group's first block
+};
+
+__device__ __forceinline__ void ff_cursor_set(FfCursor& c, unsigned chunk, const JbGeom& g) {
+    c.chunk = chunk;
+    c.plane = (int)(chunk / (unsigned)g.cpp);
+    c.blk0 = (int)(chunk - (unsigned)c.plane * (unsigned)g.cpp) * JB_CHUNK;
+    c.nvalid = jb_min(JB_CHUNK, g.nblocks - c.blk0);
+    c.nit = (c.nvalid + 3) >> 2;
+    c.it = 0;
+    c.by = c.blk0 / g.hb;
+    c.bx = c.blk0 - c.by * g.hb;
+}
+__device__ __forceinline__ void ff_cursor_next(FfCursor& c, const JbGeom& g) {
+    ++c.it;
+    c.bx += 4;
+    while (c.bx >= g.hb) { c.bx -= g.hb; ++c.by; }
+}
+__device__ __forceinline__ int ff_cursor_kind(const FfCursor& c, const JbGeom& g, bool aligned) {
+    if (!aligned || 4 * c.it + 4 > c.nvalid || c.bx + 4 > g.hb || (c.bx + 4) * 32 > g.W) return 2;
+    return (c.by + 1) * 32 <= g.H ? 0 : 1;
 }
 
 // two-level edge replication of SURVEY.md section 8(a) rows A1-A3, written into the tile layout
-__device__ __forceinline__ void ff_fill_clamped(uint8_t* tile, const uint8_t* plane, size_t pitch, const JbGeom& g,
-                                                int n0, int nlive, int lane) {
+struct FfEdgeGeom { int hb, H, W, H1, W1; };     // by value: a reference to kernel parameters would force a local copy
+__device__ __noinline__ void ff_fill_clamped(uint8_t* tile, const uint8_t* plane, size_t pitch, const FfEdgeGeom g,
+                                             int n0, int nlive, int lane) {
     uint32_t* t32 = (uint32_t*)tile;
     for (int idx = lane; idx < 1024; idx += 32) {
         const int row = idx >> 5, wcol = idx & 31, b = wcol >> 3;
@@ -97,16 +120,18 @@ __device__ __forceinline__ void ff_fill_clamped(uint8_t* tile, const uint8_t* pl
     }
 }
 
-__device__ __forceinline__ void ff_fill_direct(uint8_t* tile, const uint8_t* plane, size_t pitch, const JbGeom& g,
-                                               int n0, int lane) {
-    const int by = n0 / g.hb, bx = n0 - by * g.hb;
-    const uint8_t* src = plane + (size_t)by * 32 * pitch + (size_t)bx * 32;
+// whole columns inside the image: 128-bit loads, rows replicated past the bottom edge (kind 0 / 1)
+__device__ __forceinline__ void ff_fill_rows(uint8_t* tile, const uint8_t* plane, size_t pitch, const JbGeom& g,
+                                             int by, int bx, int lane) {
+    const uint8_t* src = plane + (size_t)bx * 32;
     uint4* t16 = (uint4*)tile;
     uint4 v[8];
     #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const int idx = k * 32 + lane;
-        v[k] = __ldg((const uint4*)(src + (size_t)(idx >> 3) * pitch) + (idx & 7));
+        const int idx = k * 32 + lane, row = idx >> 3;
+        const int si = jb_min(by * 8 + (row >> 2), g.H1 - 1);
+        const int y = jb_min(si * 4 + (row & 3), g.H - 1);
+        v[k] = __ldg((const uint4*)(src + (size_t)y * pitch) + (idx & 7));
     }
     #pragma unroll
     for (int k = 0; k < 8; ++k) t16[k * 32 + lane] = v[k];
@@ -117,6 +142,37 @@ struct FfKernelArgs {
     int use_tma;        // tensor map valid
     int aligned;        // plane base / pitch / stride are multiples of 16 bytes
 };
+
+// Pack one block (64 int16 coefficients in zigzag order, row of FF_COEF_W words) with any writer.
+template <typename Writer>
+__device__ __forceinline__ void ff_pack_block(const uint32_t* rowp, Writer& bw, int& bad_pos, int& bad_run) {
+    uint32_t lo = 0, hi = 0;
+    #pragma unroll
+    for (int q4 = 0; q4 < 8; ++q4) {
+        const uint4 w = *(const uint4*)(rowp + 4 * q4);
+        const uint32_t m = ((w.x & 0xFFFFu) ? 1u : 0u) | ((w.x >> 16) ? 2u : 0u)
+                         | ((w.y & 0xFFFFu) ? 4u : 0u) | ((w.y >> 16) ? 8u : 0u)
+                         | ((w.z & 0xFFFFu) ? 16u : 0u) | ((w.z >> 16) ? 32u : 0u)
+                         | ((w.w & 0xFFFFu) ? 64u : 0u) | ((w.w >> 16) ? 128u : 0u);
+        if (q4 < 4) lo |= m << (8 * q4); else hi |= m << (8 * (q4 - 4));
+    }
+    const int16_t* c16 = (const int16_t*)rowp;
+    int prev = -1;
+    bad_pos = -1; bad_run = 0;
+    #pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        uint32_t m = half ? hi : lo;
+        while (m) {
+            const int p = half * 32 + __ffs((int)m) - 1;
+            m &= m - 1;
+            const int amp = c16[p];
+            const int run = p - prev - 1;
+            prev = p;
+            if (!jb_put_coefficient(bw, run, amp) && bad_pos < 0) { bad_pos = p; bad_run = run % JB_MAX_RUN; }
+        }
+    }
+    bw.put(0u, 8);
+}
 
 // ---- the kernel -------------------------------------------------------------------------------
 template <bool DFT, int MODE>
@@ -140,84 +196,84 @@ jb_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfKernelArgs 
     // lane roles: (i, b) for loads and the row pass, (c, b) for the column pass
     const int li = lane >> 2, lb = lane & 3;
     const int v = DFT ? (li < 5 ? li : 12 - li) : li;          // frequency column this lane quantises
-    float qm[8], qt[8];
-    int zz[8];
+    float qm[8];
+    uint32_t zzlo = 0, zzhi = 0;                               // zigzag positions of (u, v), one byte each
     #pragma unroll
     for (int u = 0; u < 8; ++u) {
         qm[u] = a.t.qmult[u * 8 + v];
-        qt[u] = a.t.qtol[u * 8 + v];
-        zz[u] = a.t.zz[u * 8 + v];
+        const uint32_t z = a.t.zz[u * 8 + v];
+        if (u < 4) zzlo |= z << (8 * u); else zzhi |= z << (8 * (u - 4));
+    }
+    // near-tie threshold: |frac - .5| < tolY[u][v] * qm[u] (+ relative term), tolY = row(u) * col(v) factor
+    float tol_row[8];
+    float tol_col;
+    {
+        // qtol[u*8+v] = tolY[u][v] * |qmult| + 1e-7 with tolY separable in (u, v): recover the two factors
+        // from the table itself so that the bound stays the one jb_tables.cu derived
+        #pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float m0 = fabsf(a.t.qmult[u * 8 + v]);
+            tol_row[u] = m0 > 0.f ? (a.t.qtol[u * 8 + v] - 1e-7f) / m0 : 0.f;     // = tolY[u][v]
+        }
+        tol_col = 1.0f;
     }
     const bool refine_on = !(g.flags & JB_FLAG_NO_REFINE);
+    const bool aligned = ka.aligned != 0;
+    const bool use_tma = ka.use_tma != 0;
 
-    // ---- chunk / tile cursors (all warp-uniform) ----
     auto claim = [&]() -> unsigned {
         unsigned c = 0;
         if (lane == 0) c = atomicAdd(a.ticket, 1u);
         return __shfl_sync(0xffffffffu, c, 0);
     };
-    auto chunk_nvalid = [&](unsigned chunk) -> int {
-        const int blk0 = (int)(chunk % (unsigned)g.cpp) * JB_CHUNK;
-        return jb_min(JB_CHUNK, g.nblocks - blk0);
-    };
-    auto issue_tile = [&](unsigned chunk, int it, int slot) {
-        const int plane = (int)(chunk / (unsigned)g.cpp);
-        const int blk0 = (int)(chunk % (unsigned)g.cpp) * JB_CHUNK;
-        const int nvalid = jb_min(JB_CHUNK, g.nblocks - blk0);
-        if (ka.use_tma && ff_tile_kind(g, blk0, nvalid, it, ka.aligned != 0) == 0) {
-            if (lane == 0) {
-                const int n0 = blk0 + 4 * it;
-                const int by = n0 / g.hb, bx = n0 - by * g.hb;
-                ff_fence_proxy_async();
-                ff_mbar_expect_tx(&ws.bar[slot], FF_TILE_BYTES);
-                ff_tma_load_3d(ws.tile[slot], &tmap, bx * 32, by * 32, plane, &ws.bar[slot]);
-            }
-        }
-    };
 
-    unsigned cur = claim();
-    if (cur >= a.n_chunks) return;
-    unsigned iss_chunk = cur;
-    int iss_it = 0, iss_nit = (chunk_nvalid(cur) + 3) >> 2;
-    unsigned seq_issue = 0, seq_consume = 0;
-    unsigned phasebits = 0;
+    FfCursor cc, ic;                       // consume / issue cursors
+    {
+        const unsigned first = claim();
+        if (first >= a.n_chunks) return;
+        ff_cursor_set(cc, first, g);
+        ic = cc;
+    }
+    unsigned seq_issue = 0, seq_consume = 0, phasebits = 0;
     bool no_more = false;
 
     for (;;) {
-        const int plane = (int)(cur / (unsigned)g.cpp);
-        const int blk0 = (int)(cur % (unsigned)g.cpp) * JB_CHUNK;
-        const int nvalid = jb_min(JB_CHUNK, g.nblocks - blk0);
-        const int nit = (nvalid + 3) >> 2;
-        const uint8_t* plane_ptr = a.planes + (size_t)plane * a.plane_stride;
-
-        for (int it = 0; it < nit; ++it) {
-            // keep the ring full: at most FF_RING tiles issued and not yet consumed, at most one chunk ahead
+        const uint8_t* plane_ptr = a.planes + (size_t)cc.plane * a.plane_stride;
+        for (; cc.it < cc.nit; ff_cursor_next(cc, g)) {
+            // keep the ring full: at most FF_RING tiles issued and not consumed, at most one chunk ahead
             while (seq_issue - seq_consume < FF_RING) {
-                if (iss_it == iss_nit) {
-                    if (iss_chunk != cur || no_more) break;
-                    unsigned nx = claim();
+                if (ic.it == ic.nit) {
+                    if (ic.chunk != cc.chunk || no_more) break;
+                    const unsigned nx = claim();
                     if (nx >= a.n_chunks) { no_more = true; break; }
-                    iss_chunk = nx; iss_it = 0; iss_nit = (chunk_nvalid(nx) + 3) >> 2;
+                    ff_cursor_set(ic, nx, g);
                 }
-                issue_tile(iss_chunk, iss_it, (int)(seq_issue % FF_RING));
-                ++seq_issue; ++iss_it;
+                if (use_tma && ff_cursor_kind(ic, g, aligned) == 0 && lane == 0) {
+                    const int slot = (int)(seq_issue % FF_RING);
+                    ff_fence_proxy_async();
+                    ff_mbar_expect_tx(&ws.bar[slot], FF_TILE_BYTES);
+                    ff_tma_load_3d(ws.tile[slot], &tmap, ic.bx * 32, ic.by * 32, ic.plane, &ws.bar[slot]);
+                }
+                ++seq_issue;
+                ff_cursor_next(ic, g);
             }
 
             const int slot = (int)(seq_consume % FF_RING);
             uint8_t* tile = ws.tile[slot];
-            const int kind = ff_tile_kind(g, blk0, nvalid, it, ka.aligned != 0);
-            if (kind == 0 && ka.use_tma) {
+            const int kind = ff_cursor_kind(cc, g, aligned);
+            if (kind == 0 && use_tma) {
                 const uint32_t par = (phasebits >> slot) & 1u;
                 int spins = 0;
                 while (!ff_mbar_try_wait(&ws.bar[slot], par)) {
                     if (++spins > (1 << 24)) { if (lane == 0) jb_set_error(a.status, JB_ERR_CUDA); break; }
                 }
                 phasebits ^= 1u << slot;
-            } else if (kind == 0) {
-                ff_fill_direct(tile, plane_ptr, a.row_pitch, g, blk0 + 4 * it, lane);
+            } else if (kind <= 1) {
+                ff_fill_rows(tile, plane_ptr, a.row_pitch, g, cc.by, cc.bx, lane);
                 __syncwarp();
             } else {
-                ff_fill_clamped(tile, plane_ptr, a.row_pitch, g, blk0 + 4 * it, jb_min(4, nvalid - 4 * it), lane);
+                const FfEdgeGeom eg = {g.hb, g.H, g.W, g.H1, g.W1};
+                ff_fill_clamped(tile, plane_ptr, a.row_pitch, eg, cc.blk0 + 4 * cc.it, jb_min(4, cc.nvalid - 4 * cc.it), lane);
                 __syncwarp();
             }
 
@@ -246,133 +302,122 @@ jb_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfKernelArgs 
                     x[4 + j] = h0 ? fa : fb;
                 }
             }
-            // ---- stash the sums, row pass, transpose ----
+            // ---- row pass, transpose through shared memory, column pass ----
             float r[8];
             if (DFT) ff_rdft8(x, r); else ff_dct8(x, r);
-            {
-                float4* st = (float4*)(ws.stash + lb * FF_BLK_W + li * 8);
-                float4* sc = (float4*)(ws.scr + lb * FF_BLK_W + li * 8);
-                const int h0 = li & 1;
-                const float4 x0 = make_float4(x[0], x[1], x[2], x[3]), x1 = make_float4(x[4], x[5], x[6], x[7]);
-                const float4 r0 = make_float4(r[0], r[1], r[2], r[3]), r1 = make_float4(r[4], r[5], r[6], r[7]);
-                st[h0] = h0 ? x1 : x0; st[h0 ^ 1] = h0 ? x0 : x1;
-                sc[h0] = h0 ? r1 : r0; sc[h0 ^ 1] = h0 ? r0 : r1;
-            }
+            const int h0 = li & 1;
+            float4* sc = (float4*)(ws.scr + lb * FF_BLK_W + li * 8);
+            sc[h0] = h0 ? make_float4(r[4], r[5], r[6], r[7]) : make_float4(r[0], r[1], r[2], r[3]);
+            sc[h0 ^ 1] = h0 ? make_float4(r[0], r[1], r[2], r[3]) : make_float4(r[4], r[5], r[6], r[7]);
             __syncwarp();
             float col[8], y[8];
             #pragma unroll
             for (int k = 0; k < 8; ++k) col[k] = ws.scr[lb * FF_BLK_W + k * 8 + li];
-            if (DFT) {
-                ff_dft_column_stage(col, li, y);
-            } else {
-                ff_dct8(col, y);
-            }
+            if (DFT) ff_dft_column_stage(col, li, y); else ff_dct8(col, y);
 
-            // ---- quantise, tie check, zigzag store ----
-            const int gblk = 4 * it + lb;                   // block inside the chunk
+            // ---- quantise, tie check ----
+            const int gblk = 4 * cc.it + lb;                // block inside the chunk
             int qi[8];
             unsigned nearmask = 0;
             #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const float val = y[u] * qm[u];
                 const float t = val + 12582912.0f;          // 1.5 * 2^23: rounds half-even to an integer
-                const float rr = t - 12582912.0f;
+                const float dd = val - (t - 12582912.0f);
                 qi[u] = __float_as_int(t) - 0x4B400000;
-                if (fabsf(fabsf(val - rr) - 0.5f) < qt[u] + 2.4e-7f * fabsf(val)) nearmask |= 1u << u;
+                // near a tie  <=>  |frac - .5| < tol + 2.4e-7 |val|   (tol = tolY * |qm| + 1e-7)
+                const float e = fmaf(fabsf(val), 2.4e-7f, fabsf(dd));
+                if (e > 0.5f - 1e-7f - tol_row[u] * fabsf(qm[u]) * tol_col) nearmask |= 1u << u;
             }
             if (refine_on && __any_sync(0xffffffffu, nearmask != 0)) {
+                // the box sums go back to shared memory only now: nearly every iteration skips this
+                __syncwarp();
+                sc[h0] = h0 ? make_float4(x[4], x[5], x[6], x[7]) : make_float4(x[0], x[1], x[2], x[3]);
+                sc[h0 ^ 1] = h0 ? make_float4(x[0], x[1], x[2], x[3]) : make_float4(x[4], x[5], x[6], x[7]);
+                __syncwarp();
                 if (nearmask) {
-                    const float* X = ws.stash + lb * FF_BLK_W;
-                    #pragma unroll 1
+                    const float* X = ws.scr + lb * FF_BLK_W;
+                    #pragma unroll
                     for (int u = 0; u < 8; ++u)
                         if (nearmask >> u & 1u)
                             qi[u] = (int)rint(ff_refine8<DFT>(X, u, v, cs, g.qmode, a.t.qrecip[u * 8 + v]));
                 }
                 __syncwarp();
             }
-            if (gblk < nvalid) {
+            // ---- zigzag store ----
+            if (gblk < cc.nvalid) {
                 if (MODE == 1) {
-                    int16_t* dst = a.coeffs_out + ((size_t)plane * g.nblocks + blk0 + gblk) * 64;
+                    int16_t* dst = a.coeffs_out + ((size_t)cc.plane * g.nblocks + cc.blk0 + gblk) * 64;
                     #pragma unroll
-                    for (int u = 0; u < 8; ++u) dst[zz[u]] = (int16_t)max(-32767, min(32767, qi[u]));
+                    for (int u = 0; u < 8; ++u)
+                        dst[((u < 4 ? zzlo : zzhi) >> (8 * (u & 3))) & 0xFFu] = (int16_t)max(-32767, min(32767, qi[u]));
                 } else {
                     int16_t* row = (int16_t*)(ws.coef + gblk * FF_COEF_W);
                     #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         int q = qi[u];
-                        if (q > JB_MAX_AMP || q < -JB_MAX_AMP) {
-                            int k = atomicAdd(&ws.nbig, 1);
-                            if (k < FF_BIG_CAP) { ws.big_blk[k] = gblk; ws.big_pos[k] = zz[u]; ws.big_amp[k] = q; }
+                        const int zp = ((u < 4 ? zzlo : zzhi) >> (8 * (u & 3))) & 0xFFu;
+                        if ((unsigned)(q + JB_MAX_AMP) > 2u * JB_MAX_AMP) {
+                            const int k = atomicAdd(&ws.nbig, 1);
+                            if (k < FF_BIG_CAP) { ws.big_blk[k] = gblk; ws.big_pos[k] = zp; ws.big_amp[k] = q; }
                             q = q > 0 ? 32767 : -32767;
                         }
-                        row[zz[u]] = (int16_t)q;
+                        row[zp] = (int16_t)q;
                     }
                 }
             }
-            __syncwarp();          // tile, scr and stash are free again
+            __syncwarp();          // tile and scr are free again
             ++seq_consume;
         }
 
         if (MODE == 0) {
-            // ---- A9 + A10: lane t packs block t ----
+            // ---- A9 + A10: lane t packs block t into its (small) staging row ----
             unsigned len = 0;
-            if (lane < nvalid) {
-                const uint32_t* rowp = ws.coef + lane * FF_COEF_W;
-                uint32_t lo = 0, hi = 0;
-                #pragma unroll
-                for (int q4 = 0; q4 < 8; ++q4) {
-                    const uint4 w = *(const uint4*)(rowp + 4 * q4);
-                    uint32_t m = ((w.x & 0xFFFFu) ? 1u : 0u) | ((w.x >> 16) ? 2u : 0u)
-                               | ((w.y & 0xFFFFu) ? 4u : 0u) | ((w.y >> 16) ? 8u : 0u)
-                               | ((w.z & 0xFFFFu) ? 16u : 0u) | ((w.z >> 16) ? 32u : 0u)
-                               | ((w.w & 0xFFFFu) ? 64u : 0u) | ((w.w >> 16) ? 128u : 0u);
-                    if (q4 < 4) lo |= m << (8 * q4); else hi |= m << (8 * (q4 - 4));
-                }
-                const int16_t* c16 = (const int16_t*)rowp;
+            if (lane < cc.nvalid) {
                 JbBitWriter bw;
-                bw.init(ws.stage + lane * FF_STAGE_W);
-                int prev = -1, bad_pos = -1, bad_run = 0;
-                #pragma unroll 1
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t m = half ? hi : lo;
-                    while (m) {
-                        const int p = half * 32 + __ffs((int)m) - 1;
-                        m &= m - 1;
-                        const int amp = c16[p];
-                        const int run = p - prev - 1;
-                        prev = p;
-                        if (!jb_put_coefficient(bw, run, amp) && bad_pos < 0) { bad_pos = p; bad_run = run % JB_MAX_RUN; }
-                    }
-                }
-                bw.put(0u, 8);
+                bw.init(ws.stage + lane * FF_STAGE_W, FF_STAGE_CAP);
+                int bad_pos, bad_run;
+                ff_pack_block(ws.coef + lane * FF_COEF_W, bw, bad_pos, bad_run);
                 len = bw.finish();
                 if (bad_pos >= 0) {
-                    long long amp = c16[bad_pos];
+                    long long amp = ((const int16_t*)(ws.coef + lane * FF_COEF_W))[bad_pos];
                     const int nb = jb_min(ws.nbig, FF_BIG_CAP);
                     for (int k = 0; k < nb; ++k)
                         if (ws.big_blk[k] == lane && ws.big_pos[k] == bad_pos) amp = ws.big_amp[k];
-                    jb_report_bad_code(a.status, (unsigned long long)plane * g.nblocks + blk0 + lane, bad_pos, bad_run, amp);
+                    jb_report_bad_code(a.status, (unsigned long long)cc.plane * g.nblocks + cc.blk0 + lane,
+                                       bad_pos, bad_run, amp);
                 }
             }
-            __syncwarp();
             unsigned incl = len;
             #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+                const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
                 if (lane >= o) incl += t;
             }
             const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
             const unsigned excl = incl - len;
-            // compacted copy into the chunk's slot; jb_launch_scan_gather moves it to its final place
-            if (lane == 0) a.chunk_len[cur] = total;
-            {
-                uint8_t* slot = a.tmp + (size_t)cur * a.chunk_cap;
-                for (int bk = 0; bk < nvalid; ++bk) {
-                    const unsigned l = __shfl_sync(0xffffffffu, len, bk);
-                    const unsigned o = __shfl_sync(0xffffffffu, excl, bk);
-                    const uint8_t* sb = (const uint8_t*)(ws.stage + bk * FF_STAGE_W);
-                    uint8_t* dst = slot + o;
-                    for (unsigned j = lane; j < l; j += 32) dst[j] = sb[j];
+            if (lane == 0) a.chunk_len[cc.chunk] = total;
+            uint8_t* slot = a.tmp + (size_t)cc.chunk * a.chunk_cap;
+            const bool small = total <= FF_COMPACT_BYTES && !__any_sync(0xffffffffu, len > FF_STAGE_CAP * 4);
+            if (small) {
+                // compact the 32 rows inside shared memory (the coefficient rows are dead now), then
+                // write the chunk with 128-bit stores; the slot is 16-byte aligned
+                __syncwarp();
+                uint8_t* cbuf = (uint8_t*)ws.coef;
+                const uint8_t* sb = (const uint8_t*)(ws.stage + lane * FF_STAGE_W);
+                for (unsigned j = 0; j < len; ++j) cbuf[excl + j] = sb[j];
+                __syncwarp();
+                const uint4* c16 = (const uint4*)cbuf;
+                for (unsigned i = lane; i < (total + 15u) >> 4; i += 32) ((uint4*)slot)[i] = c16[i];
+            } else {
+                // a block longer than its staging row (or a very dense chunk): pack again, bytes straight
+                // to the slot
+                if (lane < cc.nvalid) {
+                    JbByteWriter bw;
+                    bw.init(slot + excl);
+                    int bad_pos, bad_run;
+                    ff_pack_block(ws.coef + lane * FF_COEF_W, bw, bad_pos, bad_run);
+                    bw.finish();
                 }
             }
             if (lane == 0) ws.nbig = 0;
@@ -380,13 +425,17 @@ jb_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfKernelArgs 
         }
 
         // next chunk: either the one the issue cursor already moved into, or a fresh claim
-        if (iss_chunk != cur) {
-            cur = iss_chunk;
+        if (ic.chunk != cc.chunk) {
+            const int keep_it = ic.it, keep_by = ic.by, keep_bx = ic.bx;
+            cc = ic;
+            ff_cursor_set(cc, ic.chunk, g);
+            ic.it = keep_it; ic.by = keep_by; ic.bx = keep_bx;
         } else {
             if (no_more) break;
-            unsigned nx = claim();
+            const unsigned nx = claim();
             if (nx >= a.n_chunks) break;
-            cur = nx; iss_chunk = nx; iss_it = 0; iss_nit = (chunk_nvalid(nx) + 3) >> 2;
+            ff_cursor_set(cc, nx, g);
+            ic = cc;
         }
     }
 }
