@@ -207,17 +207,19 @@ static int jb_inverse_common(int mode, const uint8_t* d_in, size_t in_bytes, con
         f.plane_off = (const unsigned long long*)d_plane_off;
         f.plane_len = (const unsigned long long*)d_plane_len;
         f.n_planes = n_planes; f.n = g.n; f.nblocks = g.nblocks; f.maxblk = g.maxblk;
-        f.max_tiles = L.max_tiles; f.win_n = L.win_n;
+        f.max_tiles = L.max_tiles; f.tile_bytes = L.tile_bytes;
+        f.force_serial = (g.flags & JB_FLAG_SERIAL_FRAMING) ? 1 : 0;
         f.tile_first = (unsigned*)(ws + L.tile_first);
+        f.fallback = (unsigned*)(ws + L.fallback);
         f.block_start = (unsigned*)(ws + L.block_start);
-        f.tile_uniq = (unsigned*)(ws + L.tile_uniq);
+        f.tile_n = (unsigned*)(ws + L.tile_n);
+        f.tile_exit = (unsigned*)(ws + L.tile_exit);
         f.tile_entry = (unsigned*)(ws + L.tile_entry);
-        f.tile_base = (unsigned*)(ws + L.tile_base);
+        f.tile_from = (unsigned*)(ws + L.tile_from);
+        f.tile_npriv = (unsigned*)(ws + L.tile_npriv);
         f.tile_hops = (unsigned*)(ws + L.tile_hops);
-        f.tile_ncand = (unsigned*)(ws + L.tile_ncand);
-        f.win = (unsigned*)(ws + L.win);
-        f.cand_pos = (uint16_t*)(ws + L.cand_pos);
-        f.cand_next = (uint16_t*)(ws + L.cand_next);
+        f.tile_base = (unsigned*)(ws + L.tile_base);
+        f.visited = (uint16_t*)(ws + L.visited);
         f.status = (unsigned long long*)d_status;
         // a stream that fails framing leaves block_start unwritten: make it deterministic
         JB_CUDA_TRY(cudaMemsetAsync(f.block_start, 0xFF, (size_t)n_planes * g.nblocks * 4, s));

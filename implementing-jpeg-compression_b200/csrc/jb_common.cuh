@@ -7,7 +7,7 @@
 #include "jb_bits.h"
 
 #define JB_CHUNK 32            // blocks per chunk: one RLE/entropy thread per block, one warp per chunk
-#define JB_TILE_BYTES 4096     // stream bytes per framing tile (decoder)
+
 #define JB_U32_NONE 0xFFFFFFFFu
 #define JB_U16_NONE 0xFFFFu
 

@@ -5,39 +5,48 @@
 #define JB_FRAME_THREADS 256
 #define JB_INV_GENERIC_THREADS 256
 
+// Walk tile: a power of two >= the longest possible block, at least 256 bytes.
+static inline unsigned jb_frame_tile_bytes(int d) {
+    unsigned need = (unsigned)jb_max_block_bytes(d * d), t = 256;
+    while (t < need) t <<= 1;
+    return t;
+}
+
 // Workspace of the decoder behind the tables (all offsets 256-byte aligned).
 struct JbDecLayout {
     size_t tile_first;   // uint32 [n_planes + 1]   first tile of each stream; [n_planes] = tile count
+    size_t fallback;     // uint32 [n_planes]       stream needs the serial walk
     size_t block_start;  // uint32 [n_planes * nblocks]  byte offset of every block inside its stream
-    size_t tile_uniq;    // uint32 [max_tiles]  exit shared by every entry candidate, or NONE
-    size_t tile_entry;   // uint32 [max_tiles]  offset of the first true block start inside the tile
-    size_t tile_base;    // uint32 [max_tiles]  ordinal (within the stream) of that block
+    size_t tile_n;       // uint32 [max_tiles]  starts recorded by the tile's walk
+    size_t tile_exit;    // uint32 [max_tiles]  offset where the walk leaves the tile (or invalid)
+    size_t tile_entry;   // uint32 [max_tiles]  offset of the first true block start of the tile
+    size_t tile_from;    // uint32 [max_tiles]  index into the walk's list where the true chain joins it
+    size_t tile_npriv;   // uint32 [max_tiles]  true blocks before that point
     size_t tile_hops;    // uint32 [max_tiles]  true blocks that start inside the tile
-    size_t tile_ncand;   // uint32 [max_tiles]
-    size_t win;          // uint32 [max_tiles * win_n]  (hops << 16 | exit) per entry offset < win_n
-    size_t cand_pos;     // uint16 [max_tiles * JB_TILE_BYTES]
-    size_t cand_next;    // uint16 [max_tiles * JB_TILE_BYTES]
+    size_t tile_base;    // uint32 [max_tiles]  ordinal (within the stream) of the tile's first true block
+    size_t visited;      // uint16 [max_tiles * tile_bytes]
     size_t total;
     unsigned max_tiles;
-    unsigned win_n;
+    unsigned tile_bytes;
 };
 
 static inline JbDecLayout jb_dec_layout(int d, int n_planes, long long nblocks_per_plane, size_t in_bytes,
                                         size_t table_bytes) {
     JbDecLayout L;
     size_t o = jb_align_up(table_bytes, 256);
-    L.max_tiles = (unsigned)(in_bytes / JB_TILE_BYTES + (size_t)n_planes + 1);
-    L.win_n = (unsigned)jb_max_block_bytes(d * d);
+    L.tile_bytes = jb_frame_tile_bytes(d);
+    L.max_tiles = (unsigned)(in_bytes / L.tile_bytes + (size_t)n_planes + 1);
     L.tile_first = o;  o += jb_align_up(((size_t)n_planes + 1) * 4, 256);
+    L.fallback = o;    o += jb_align_up((size_t)n_planes * 4, 256);
     L.block_start = o; o += jb_align_up((size_t)n_planes * (size_t)nblocks_per_plane * 4, 256);
-    L.tile_uniq = o;   o += jb_align_up((size_t)L.max_tiles * 4, 256);
+    L.tile_n = o;      o += jb_align_up((size_t)L.max_tiles * 4, 256);
+    L.tile_exit = o;   o += jb_align_up((size_t)L.max_tiles * 4, 256);
     L.tile_entry = o;  o += jb_align_up((size_t)L.max_tiles * 4, 256);
-    L.tile_base = o;   o += jb_align_up((size_t)L.max_tiles * 4, 256);
+    L.tile_from = o;   o += jb_align_up((size_t)L.max_tiles * 4, 256);
+    L.tile_npriv = o;  o += jb_align_up((size_t)L.max_tiles * 4, 256);
     L.tile_hops = o;   o += jb_align_up((size_t)L.max_tiles * 4, 256);
-    L.tile_ncand = o;  o += jb_align_up((size_t)L.max_tiles * 4, 256);
-    L.win = o;         o += jb_align_up((size_t)L.max_tiles * L.win_n * 4, 256);
-    L.cand_pos = o;    o += jb_align_up((size_t)L.max_tiles * JB_TILE_BYTES * 2, 256);
-    L.cand_next = o;   o += jb_align_up((size_t)L.max_tiles * JB_TILE_BYTES * 2, 256);
+    L.tile_base = o;   o += jb_align_up((size_t)L.max_tiles * 4, 256);
+    L.visited = o;     o += jb_align_up((size_t)L.max_tiles * L.tile_bytes * 2, 256);
     L.total = o;
     return L;
 }
@@ -50,17 +59,19 @@ struct JbFrameArgs {
     int n;                 // coefficients per block
     int nblocks;           // blocks per plane expected
     int maxblk;
-    unsigned max_tiles, win_n;
+    unsigned max_tiles, tile_bytes;
+    int force_serial;      // JB_FLAG_SERIAL_FRAMING: every stream takes the serial walk (test hook)
     unsigned* tile_first;
+    unsigned* fallback;
     unsigned* block_start;
-    unsigned* tile_uniq;
+    unsigned* tile_n;
+    unsigned* tile_exit;
     unsigned* tile_entry;
-    unsigned* tile_base;
+    unsigned* tile_from;
+    unsigned* tile_npriv;
     unsigned* tile_hops;
-    unsigned* tile_ncand;
-    unsigned* win;
-    uint16_t* cand_pos;
-    uint16_t* cand_next;
+    unsigned* tile_base;
+    uint16_t* visited;
     unsigned long long* status;
 };
 

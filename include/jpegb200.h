@@ -79,6 +79,7 @@ typedef struct jb_params {
 #define JB_FLAG_FORCE_GENERIC 1  /* never take the specialised 8x8 / block_size 4 kernels */
 #define JB_FLAG_NO_TMA        2  /* specialised kernels stage tiles with plain loads/stores */
 #define JB_FLAG_NO_REFINE     4  /* skip the float64 re-evaluation of near-tie coefficients */
+#define JB_FLAG_SERIAL_FRAMING 8 /* decoder: find block boundaries with the serial fallback walk only */
 
 /* Derived sizes (pipeline/run_length_encoding.py:80-88, pipeline/dct_padding.py:11-21). */
 typedef struct jb_geometry {

@@ -143,6 +143,31 @@ def test_pack_unpack_random_coefficients(jb, n, density, bits):
     assert np.array_equal(back, zz)
 
 
+def test_serial_framing_fallback_matches(jb):
+    """JB_FLAG_SERIAL_FRAMING (8) routes every stream through the single-thread fallback walk."""
+    cfg, ocfg = _cfgs(jb, (200, 328, 4, 8, "DCT", "qtable", None))
+    planes = [synth_plane(200, 328, 3 + i) for i in range(3)]
+    streams = jb.compress_bands(planes, cfg)
+    assert np.array_equal(jb.decompress_bands(streams, cfg, flags=8), jb.decompress_bands(streams, cfg))
+    with pytest.raises(jb.BadStreamError):
+        jb.decompress_bands([streams[0], streams[1][:-2], streams[2]], cfg, flags=8)
+
+
+def test_framing_with_many_false_block_starts(jb):
+    """Streams full of 0x00 bytes inside amplitude fields: most candidate offsets are false."""
+    rng = np.random.default_rng(77)
+    zz = np.zeros((2, 3000, 64), dtype=np.int64)
+    pos = rng.integers(0, 64, (2, 3000, 6))
+    for p in range(2):
+        for b in range(3000):
+            zz[p, b, pos[p, b]] = rng.choice([256, 512, 1024, 2048, 4096, 8192, -256, -4096, 1, -1], 6)
+    streams = [rp.pack_blocks(zz[p]) for p in range(2)]
+    frac_zero = np.mean(np.frombuffer(streams[0], dtype=np.uint8) == 0)
+    assert frac_zero > 0.25
+    back = jb.stages.unpack_streams(streams, 3000, 8)
+    assert np.array_equal(back, zz)
+
+
 def test_zero_heavy_streams_every_byte_a_candidate(jb):
     # an all-black plane packs to one 0x00 per block: every byte is a block start
     cfg, ocfg = _cfgs(jb, (600, 800, 1, 8, "DCT", "qtable", None))
