@@ -147,7 +147,16 @@ __global__ void __launch_bounds__(JB_FRAME_THREADS) jb_frame_walk_kernel(JbFrame
         const uint32_t maxblk_bits = (uint32_t)f.maxblk * 8u;
         for (;;) {
             V[n++] = (uint16_t)(pos - tstart);
-            if (!w.block(f.n, maxblk_bits)) { exit_pos = JB_POS_INVALID; break; }
+            if (!w.block(f.n, maxblk_bits)) {
+                // `pos` was a false start (in a valid stream): resume at the next offset that
+                // follows a 0x00 byte; the list stays sorted and the true chain joins it later
+                uint32_t q = pos + 1;
+                while (q < tend && __ldg(stream + q - 1) != 0) ++q;
+                if (q >= tend) { exit_pos = JB_POS_INVALID; break; }
+                pos = q;
+                w.seek(pos);
+                continue;
+            }
             pos = w.bp >> 3;
             if (pos >= tend) { exit_pos = pos; break; }
         }
@@ -171,10 +180,13 @@ __global__ void __launch_bounds__(JB_FRAME_THREADS) jb_frame_link_kernel(JbFrame
 
     const uint32_t E = (t == 0) ? 0u : f.tile_exit[tile - 1];
     unsigned from = n, npriv = 0, hops = 0;
-    bool ok = (E != JB_POS_INVALID) && (my_exit != JB_POS_INVALID) && E >= tstart;
+    bool ok = (E != JB_POS_INVALID) && E >= tstart;
     if (ok && E >= tend) {
         // nothing starts in this tile: only legitimate as the tail of the stream's last block
+        // (whatever the walk of this tile found started on a false offset)
         ok = (E == len) && (tend == len);
+    } else if (ok && my_exit == JB_POS_INVALID) {
+        ok = false;
     } else if (ok) {
         const uint32_t rel = E - tstart;
         unsigned lo = 0, hi = n;
@@ -225,8 +237,13 @@ __global__ void __launch_bounds__(JB_FRAME_THREADS) jb_frame_scan_kernel(JbFrame
         carry += total;
     }
     if (tid == 0) {
-        const bool good = nt > 0 && f.fallback[s] == 0u && carry == (unsigned)f.nblocks &&
-                          f.tile_exit[t0 + nt - 1] == len;
+        // the chain must end exactly at the stream end: either the last tile's walk exits there,
+        // or the last tile holds only the tail of a block (its entry is the stream end)
+        bool good = nt > 0 && f.fallback[s] == 0u && carry == (unsigned)f.nblocks;
+        if (good) {
+            const uint32_t e_last = f.tile_entry[t0 + nt - 1];
+            good = (e_last >= len) ? (e_last == len) : (f.tile_exit[t0 + nt - 1] == len);
+        }
         if (!good) f.fallback[s] = 1u;
     }
 }
