@@ -231,6 +231,7 @@ def run_ours(args, rank, world, local_rank):
     total_bytes = comp.total_bytes()
     out, status = bc.decompress_device(comp, total_bytes)
     jb.check_status(status)
+    serial_streams = int(status.cpu()[2].item())
 
     sampler = None
     if rank == 0:
@@ -313,6 +314,7 @@ def run_ours(args, rank, world, local_rank):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
             "compress_mps": mp_total / (t_c * 1e-3), "decompress_mps": mp_total / (t_d * 1e-3),
             "ms_compress": t_c, "ms_decompress": t_d, "stream_bytes": stream_total,
+            "decoder_serial_fallback_streams_rank0": serial_streams,
             "bytes_per_pixel": stream_total / (N_IMAGES * H * W),
             "roofline": {"bound": "hbm", "kernel": "jb_fwd_fast_kernel (fused compress; timed with the table "
                          "builder and two memsets of the same call)", "achieved": ach_c, "peak": peak,

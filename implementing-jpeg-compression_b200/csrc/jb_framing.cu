@@ -28,29 +28,54 @@
 
 #define JB_POS_INVALID 0xFFFFFFFFu
 
-// ---- sequential extent parser over global memory (aligned 32-bit loads, 64-bit window) ---------
+// ---- sequential extent parser: aligned 32-bit big-endian-assembled words, 64-bit window ---------
+// The word source is either global memory (any tile size) or a per-thread slice of shared memory
+// that the warp filled with coalesced loads (small tiles: keeps thousands of concurrent walks
+// from thrashing L1 with one cache line each).
 struct JbWalker {
-    const uint32_t* words;      // 4-byte aligned base at or below the stream start
-    uint32_t shift_bits;        // bit offset of the stream start inside words[]
+    const uint32_t* words;      // 4-byte aligned base at or below byte `origin` of the stream
+    uint32_t origin;            // stream byte offset that words[0] (after shift) corresponds to
+    uint32_t shift_bits;        // bit offset of byte `origin` inside words[]
     uint32_t nwords;            // words that may be read
     uint32_t len_bits;          // stream length in bits
     uint32_t widx;
     uint64_t buf;
     int nb;
     uint32_t bp;                // bit position inside the stream of the next unread bit
+    bool in_smem;
 
-    __device__ __forceinline__ uint32_t load(uint32_t i) const { return i < nwords ? jb_bswap32(__ldg(words + i)) : 0u; }
-
+    __device__ __forceinline__ uint32_t load(uint32_t i) const {
+        if (i >= nwords) return 0u;
+        return jb_bswap32(in_smem ? words[i] : __ldg(words + i));
+    }
+    // whole stream in global memory
     __device__ __forceinline__ void init(const uint8_t* stream, uint32_t len_bytes) {
         const uintptr_t a = (uintptr_t)stream;
         words = (const uint32_t*)(a & ~(uintptr_t)3);
+        origin = 0;
         shift_bits = (uint32_t)(a & 3) * 8u;
         nwords = (uint32_t)((shift_bits / 8u + len_bytes + 3u) >> 2);
         len_bits = len_bytes * 8u;
+        in_smem = false;
+    }
+    // a staged window: smem_words[0] holds the aligned word that contains stream byte `first_byte`
+    __device__ __forceinline__ void init_window(const uint32_t* smem_words, uint32_t n_words, uint32_t first_byte,
+                                                uint32_t misalign_bytes, uint32_t len_bytes) {
+        words = smem_words;
+        origin = first_byte;
+        shift_bits = misalign_bytes * 8u;
+        nwords = n_words;
+        len_bits = len_bytes * 8u;
+        in_smem = true;
+    }
+    __device__ __forceinline__ uint32_t byte_at(uint32_t pos) const {       // stream byte `pos` (>= origin)
+        const uint32_t b = pos - origin + (shift_bits >> 3);
+        const uint32_t w = in_smem ? words[b >> 2] : __ldg(words + (b >> 2));
+        return (w >> ((b & 3u) * 8u)) & 0xFFu;
     }
     __device__ __forceinline__ void seek(uint32_t byte_pos) {
         bp = byte_pos * 8u;
-        const uint32_t abs_bits = bp + shift_bits;
+        const uint32_t abs_bits = (byte_pos - origin) * 8u + shift_bits;
         widx = abs_bits >> 5;
         buf = load(widx++);
         nb = 32 - (int)(abs_bits & 31u);
@@ -123,26 +148,19 @@ __global__ void __launch_bounds__(1024) jb_frame_prep_kernel(JbFrameArgs f) {
 }
 
 // ---- F1: walk ----------------------------------------------------------------------------------
-__global__ void __launch_bounds__(JB_FRAME_THREADS) jb_frame_walk_kernel(JbFrameArgs f) {
-    const unsigned tile = blockIdx.x * JB_FRAME_THREADS + threadIdx.x;
-    if (tile >= f.tile_first[f.n_planes]) return;
-    const int s = jb_stream_of_tile(f.tile_first, f.n_planes, tile);
-    const uint32_t len = (uint32_t)f.plane_len[s];
-    const uint8_t* stream = f.in + f.plane_off[s];
-    const uint32_t tstart = (tile - f.tile_first[s]) * f.tile_bytes;
-    const uint32_t tend = (uint32_t)jb_min((int)(tstart + f.tile_bytes), (int)len);
-    uint16_t* V = f.visited + (size_t)tile * f.tile_bytes;
+#define JB_WALK_THREADS 128
 
+__device__ __forceinline__ void jb_walk_tile(JbWalker& w, const JbFrameArgs& f, unsigned tile, uint32_t tstart,
+                                             uint32_t tend) {
+    uint16_t* V = f.visited + (size_t)tile * f.tile_bytes;
     // first offset of the tile that can start a block: 0, or the byte after a 0x00
     uint32_t pos = tstart;
     if (tstart != 0) {
-        while (pos < tend && __ldg(stream + pos - 1) != 0) ++pos;
+        while (pos < tend && w.byte_at(pos - 1) != 0) ++pos;
     }
     unsigned n = 0;
     uint32_t exit_pos = pos;                     // == tend if the tile holds no candidate
     if (pos < tend) {
-        JbWalker w;
-        w.init(stream, len);
         w.seek(pos);
         const uint32_t maxblk_bits = (uint32_t)f.maxblk * 8u;
         for (;;) {
@@ -151,7 +169,7 @@ __global__ void __launch_bounds__(JB_FRAME_THREADS) jb_frame_walk_kernel(JbFrame
                 // `pos` was a false start (in a valid stream): resume at the next offset that
                 // follows a 0x00 byte; the list stays sorted and the true chain joins it later
                 uint32_t q = pos + 1;
-                while (q < tend && __ldg(stream + q - 1) != 0) ++q;
+                while (q < tend && w.byte_at(q - 1) != 0) ++q;
                 if (q >= tend) { exit_pos = JB_POS_INVALID; break; }
                 pos = q;
                 w.seek(pos);
@@ -163,6 +181,57 @@ __global__ void __launch_bounds__(JB_FRAME_THREADS) jb_frame_walk_kernel(JbFrame
     }
     f.tile_n[tile] = n;
     f.tile_exit[tile] = exit_pos;
+}
+
+// any tile size: every thread reads its tile straight from global memory
+__global__ void __launch_bounds__(JB_WALK_THREADS) jb_frame_walk_kernel(JbFrameArgs f) {
+    const unsigned tile = blockIdx.x * JB_WALK_THREADS + threadIdx.x;
+    if (tile >= f.tile_first[f.n_planes]) return;
+    const int s = jb_stream_of_tile(f.tile_first, f.n_planes, tile);
+    const uint32_t len = (uint32_t)f.plane_len[s];
+    const uint32_t tstart = (tile - f.tile_first[s]) * f.tile_bytes;
+    const uint32_t tend = (uint32_t)jb_min((int)(tstart + f.tile_bytes), (int)len);
+    JbWalker w;
+    w.init(f.in + f.plane_off[s], len);
+    jb_walk_tile(w, f, tile, tstart, tend);
+}
+
+// small tiles: the warp first copies each lane's window (one byte before the tile, the tile, and
+// the longest block beyond it) into that lane's slice of shared memory with coalesced loads
+__global__ void __launch_bounds__(JB_WALK_THREADS) jb_frame_walk_smem_kernel(JbFrameArgs f, unsigned stride_words) {
+    extern __shared__ uint32_t s_words[];
+    const int lane = threadIdx.x & 31;
+    const unsigned total_tiles = f.tile_first[f.n_planes];
+    const unsigned tile = blockIdx.x * JB_WALK_THREADS + threadIdx.x;
+    const bool live = tile < total_tiles;
+    uint32_t len = 0, tstart = 0, tend = 0, first = 0, mis = 0, nw = 0;
+    unsigned long long abase = 0;                   // aligned global address of the window
+    if (live) {
+        const int s = jb_stream_of_tile(f.tile_first, f.n_planes, tile);
+        len = (uint32_t)f.plane_len[s];
+        tstart = (tile - f.tile_first[s]) * f.tile_bytes;
+        tend = (uint32_t)jb_min((int)(tstart + f.tile_bytes), (int)len);
+        first = tstart ? tstart - 1 : 0;
+        const uint32_t last = (uint32_t)jb_min((int)(tstart + f.tile_bytes + f.maxblk + 4), (int)len);
+        const unsigned long long a0 = (unsigned long long)(uintptr_t)(f.in + f.plane_off[s] + first);
+        mis = (uint32_t)(a0 & 3ull);
+        abase = a0 - mis;
+        nw = (last - first + mis + 3u) >> 2;
+        if (nw > stride_words) nw = stride_words;
+    }
+    uint32_t* mine = s_words + (size_t)threadIdx.x * stride_words;
+    for (int k = 0; k < 32; ++k) {
+        const unsigned long long src = __shfl_sync(0xffffffffu, abase, k);
+        const uint32_t cnt = __shfl_sync(0xffffffffu, nw, k);
+        uint32_t* dst = s_words + (size_t)((threadIdx.x & ~31) + k) * stride_words;
+        const uint32_t* g = (const uint32_t*)(uintptr_t)src;
+        for (uint32_t i = lane; i < cnt; i += 32) dst[i] = __ldg(g + i);
+    }
+    __syncwarp();
+    if (!live) return;
+    JbWalker w;
+    w.init_window(mine, nw, first, mis, len);
+    jb_walk_tile(w, f, tile, tstart, tend);
 }
 
 // ---- F2a: link each tile to the walk of the tile before it -----------------------------------------
@@ -244,7 +313,10 @@ __global__ void __launch_bounds__(JB_FRAME_THREADS) jb_frame_scan_kernel(JbFrame
             const uint32_t e_last = f.tile_entry[t0 + nt - 1];
             good = (e_last >= len) ? (e_last == len) : (f.tile_exit[t0 + nt - 1] == len);
         }
-        if (!good) f.fallback[s] = 1u;
+        if (!good) {
+            f.fallback[s] = 1u;
+            atomicAdd(f.status + 2, 1ull);        // status[2]: streams that took the serial walk
+        }
     }
 }
 
@@ -296,9 +368,19 @@ __global__ void __launch_bounds__(32) jb_frame_serial_kernel(JbFrameArgs f) {
 cudaError_t jb_launch_framing(const JbFrameArgs& f, cudaStream_t s) {
     cudaError_t e;
     const unsigned grid = (f.max_tiles + JB_FRAME_THREADS - 1) / JB_FRAME_THREADS;
+    const unsigned wgrid = (f.max_tiles + JB_WALK_THREADS - 1) / JB_WALK_THREADS;
     jb_frame_prep_kernel<<<1, 1024, 0, s>>>(f);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    jb_frame_walk_kernel<<<grid, JB_FRAME_THREADS, 0, s>>>(f);
+    // window of one walk: 1 byte before the tile + tile + longest block + slack, in words, odd stride
+    const unsigned stride_words = (((unsigned)f.tile_bytes + (unsigned)f.maxblk + 16u) / 4u) | 1u;
+    const size_t smem = (size_t)JB_WALK_THREADS * stride_words * 4;
+    if (smem <= 64 * 1024) {
+        e = cudaFuncSetAttribute(jb_frame_walk_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        jb_frame_walk_smem_kernel<<<wgrid, JB_WALK_THREADS, smem, s>>>(f, stride_words);
+    } else {
+        jb_frame_walk_kernel<<<wgrid, JB_WALK_THREADS, 0, s>>>(f);
+    }
     jb_frame_link_kernel<<<grid, JB_FRAME_THREADS, 0, s>>>(f);
     jb_frame_scan_kernel<<<f.n_planes, JB_FRAME_THREADS, 0, s>>>(f);
     jb_frame_emit_kernel<<<grid, JB_FRAME_THREADS, 0, s>>>(f);

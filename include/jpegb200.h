@@ -97,7 +97,8 @@ typedef struct jb_geometry {
  *   [1] for BAD_RLE_CODE: the first bad code in stream order, packed as
  *         global block index (30 bits) << 34 | zigzag position (10) << 24 | run (4) << 20 |
  *         (amplitude + 2^19) (20 bits);   all ones when there is none
- *   [2], [3] reserved                                                                        */
+ *   [2] decoder: number of streams whose block boundaries were found by the serial fallback walk
+ *   [3] reserved                                                                        */
 #define JB_STATUS_WORDS 4
 
 int jb_version(void);
