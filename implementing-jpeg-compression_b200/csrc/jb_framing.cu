@@ -85,26 +85,28 @@ struct JbWalker {
     __device__ __forceinline__ bool block(int n, uint32_t maxblk_bits) {
         const uint32_t start = bp;
         int count = 0;
-        for (;;) {
+        for (;;) {                      // every pass adds at least 1 to `count`: at most n + 1 passes
             if (nb < 23) { buf = (buf << 32) | load(widx++); nb += 32; }
             const uint32_t head = (uint32_t)(buf >> (nb - 8)) & 0xFFu;
-            const uint32_t run = head >> 4, size = head & 15u;
+            const uint32_t size = head & 15u;
             if (size == 0u) {
-                nb -= 8; bp += 8;
-                if (run == 0u) {
-                    const int pad = (int)((8u - (bp & 7u)) & 7u);
-                    nb -= pad; bp += (uint32_t)pad;
-                    break;
-                }
-                if (run != (uint32_t)JB_MAX_RUN) return false;
+                nb -= 8;
+                if (head == 0u) break;                                   // EOB
+                if (head != 0xF0u) return false;                         // (r, 0), 0 < r < 15
                 count += JB_MAX_RUN;
             } else {
                 if (size == 1u) return false;
-                count += (int)run + 1;
-                nb -= 8 + (int)size; bp += 8u + size;
+                count += (int)(head >> 4) + 1;
+                nb -= 8 + (int)size;
             }
-            if (count > n || bp - start > maxblk_bits) return false;
+            if (count > n) return false;
         }
+        // bits consumed from words[0] = 32 * widx - nb; skip the zero padding to the byte boundary
+        uint32_t abs_bits = widx * 32u - (uint32_t)nb;
+        const uint32_t pad = (8u - (abs_bits & 7u)) & 7u;
+        nb -= (int)pad;
+        abs_bits += pad;
+        bp = origin * 8u + abs_bits - shift_bits;
         return bp <= len_bits && bp - start <= maxblk_bits;
     }
 };
@@ -148,7 +150,7 @@ __global__ void __launch_bounds__(1024) jb_frame_prep_kernel(JbFrameArgs f) {
 }
 
 // ---- F1: walk ----------------------------------------------------------------------------------
-#define JB_WALK_THREADS 128
+#define JB_WALK_THREADS 96
 
 __device__ __forceinline__ void jb_walk_tile(JbWalker& w, const JbFrameArgs& f, unsigned tile, uint32_t tstart,
                                              uint32_t tend) {
@@ -220,12 +222,35 @@ __global__ void __launch_bounds__(JB_WALK_THREADS) jb_frame_walk_smem_kernel(JbF
         if (nw > stride_words) nw = stride_words;
     }
     uint32_t* mine = s_words + (size_t)threadIdx.x * stride_words;
-    for (int k = 0; k < 32; ++k) {
-        const unsigned long long src = __shfl_sync(0xffffffffu, abase, k);
-        const uint32_t cnt = __shfl_sync(0xffffffffu, nw, k);
-        uint32_t* dst = s_words + (size_t)((threadIdx.x & ~31) + k) * stride_words;
-        const uint32_t* g = (const uint32_t*)(uintptr_t)src;
-        for (uint32_t i = lane; i < cnt; i += 32) dst[i] = __ldg(g + i);
+    // four tiles at a time, up to sixteen loads in flight per lane
+    const int iters = (int)((stride_words + 31u) / 32u);
+    for (int k0 = 0; k0 < 32; k0 += 4) {
+        const uint32_t* g[4];
+        uint32_t cnt[4];
+        uint32_t* dst[4];
+        #pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            g[q] = (const uint32_t*)(uintptr_t)__shfl_sync(0xffffffffu, abase, k0 + q);
+            cnt[q] = __shfl_sync(0xffffffffu, nw, k0 + q);
+            dst[q] = s_words + (size_t)((threadIdx.x & ~31) + k0 + q) * stride_words;
+        }
+        for (int ib = 0; ib < iters; ib += 4) {
+            uint32_t v[4][4];
+            #pragma unroll
+            for (int q = 0; q < 4; ++q)
+                #pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t idx = (uint32_t)(ib + j) * 32u + (uint32_t)lane;
+                    v[q][j] = idx < cnt[q] ? __ldg(g[q] + idx) : 0u;
+                }
+            #pragma unroll
+            for (int q = 0; q < 4; ++q)
+                #pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t idx = (uint32_t)(ib + j) * 32u + (uint32_t)lane;
+                    if (idx < cnt[q]) dst[q][idx] = v[q][j];
+                }
+        }
     }
     __syncwarp();
     if (!live) return;

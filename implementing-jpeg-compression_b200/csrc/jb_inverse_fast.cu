@@ -20,9 +20,10 @@
 #include "jb_fast_common.cuh"
 #include "jb_inverse.cuh"
 
-#define FI_WARPS 8
+#define FI_WARPS 14
 #define FI_RING 2
-#define FI_STREAM_WORDS 1488            // 32 blocks * 185 bytes worst case + alignment slack
+#define FI_STREAM_WORDS 400             // staged chunk bytes (1.6 KB; the average chunk is ~0.6 KB); denser
+                                        // chunks are decoded straight from global memory
 
 struct __align__(128) FiWarpSmem {
     uint8_t tile[FI_RING][FF_TILE_BYTES];
@@ -37,35 +38,38 @@ struct FiKernelArgs {
     int aligned;
 };
 
-// Decode one block from big-endian words staged in shared memory (bit `bitpos` of the staged
-// range) into natural order.  Returns 0 or 1 (malformed).
-__device__ __forceinline__ int fi_decode_block(const uint32_t* words, uint32_t bitpos, uint32_t bitlimit,
-                                               int16_t* row, const uint8_t* izz) {
+// Decode one block from 32-bit words (staged in shared memory, or in global memory for chunks too
+// dense to stage) into natural order.  `bitpos` / `bitlimit` count from words[0].  Returns 0 or 1
+// (malformed).
+template <bool GLOBAL>
+__device__ __forceinline__ int fi_decode_block(const uint32_t* words, uint32_t nwords, uint32_t bitpos,
+                                               uint32_t bitlimit, int16_t* row, const uint8_t* izz) {
     uint32_t widx = bitpos >> 5;
+    auto ld = [&](uint32_t i) -> uint32_t {
+        if (i >= nwords) return 0u;
+        return jb_bswap32(GLOBAL ? __ldg(words + i) : words[i]);
+    };
     int nb = 32 - (int)(bitpos & 31u);
-    uint64_t buf = jb_bswap32(words[widx < FI_STREAM_WORDS ? widx : FI_STREAM_WORDS - 1]);
-    ++widx;
+    uint64_t buf = ld(widx++);
     uint32_t used = bitpos;
     int count = 0;
     for (;;) {
-        if (nb < 8) { buf = (buf << 32) | jb_bswap32(words[widx < FI_STREAM_WORDS ? widx : FI_STREAM_WORDS - 1]); ++widx; nb += 32; }
+        if (nb < 23) { buf = (buf << 32) | ld(widx++); nb += 32; }
         const uint32_t head = (uint32_t)(buf >> (nb - 8)) & 0xFFu;
-        nb -= 8; used += 8;
-        if (used > bitlimit) return 1;
         const uint32_t run = head >> 4, size = head & 15u;
         if (size == 0u) {
-            if (run == 0u) return 0;                     // EOB
+            nb -= 8; used += 8;
+            if (run == 0u) return used > bitlimit ? 1 : 0;            // EOB
             if (run != (uint32_t)JB_MAX_RUN) return 1;
             count += JB_MAX_RUN;
-            if (count > 64) return 1;
+            if (count > 64 || used > bitlimit) return 1;
             continue;
         }
         if (size == 1u) return 1;
         count += (int)run;
         if (count >= 64) return 1;
-        if (nb < (int)size) { buf = (buf << 32) | jb_bswap32(words[widx < FI_STREAM_WORDS ? widx : FI_STREAM_WORDS - 1]); ++widx; nb += 32; }
-        const uint32_t raw = (uint32_t)(buf >> (nb - (int)size)) & ((1u << size) - 1u);
-        nb -= (int)size; used += size;
+        const uint32_t raw = (uint32_t)(buf >> (nb - 8 - (int)size)) & ((1u << size) - 1u);
+        nb -= 8 + (int)size; used += 8u + size;
         if (used > bitlimit) return 1;
         const int mag = (int)(raw & ((1u << (size - 1)) - 1u));
         row[izz[count]] = (int16_t)((raw >> (size - 1)) ? mag : -mag);
@@ -73,13 +77,14 @@ __device__ __forceinline__ int fi_decode_block(const uint32_t* words, uint32_t b
     }
 }
 
-__device__ __forceinline__ int fi_tile_kind(const JbGeom& g, int blk0, int nvalid, int it, bool aligned) {
-    const int n0 = blk0 + 4 * it;
-    if (!aligned || 4 * it + 4 > nvalid) return 2;
-    const int by = n0 / g.hb, bx = n0 - by * g.hb;
-    if (bx + 4 > g.hb) return 2;
-    // fully inside -> 0 (TMA or STG.128); crossing the right / bottom edge -> 1 (TMA clips, else bounded)
-    return ((bx + 4) * 32 <= g.W && (by + 1) * 32 <= g.H) ? 0 : 1;
+struct FiCursor { int it, by, bx; };
+
+// kind 0: 4 blocks of one block row, all inside the image -> TMA store or STG.128
+// kind 1: same, but crossing the right / bottom edge     -> TMA store (clips) or bounded stores
+// kind 2: block-row wrap, partial group, unaligned plane -> bounded stores
+__device__ __forceinline__ int fi_tile_kind(const JbGeom& g, int nvalid, const FiCursor& c, bool aligned) {
+    if (!aligned || 4 * c.it + 4 > nvalid || c.bx + 4 > g.hb) return 2;
+    return ((c.bx + 4) * 32 <= g.W && (c.by + 1) * 32 <= g.H) ? 0 : 1;
 }
 
 template <bool DFT, int MODE>
@@ -132,28 +137,32 @@ jb_inv_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FiKernelArgs 
             c_end = __shfl_sync(0xffffffffu, c_end, 0);
             const unsigned long long addr0 = (unsigned long long)(uintptr_t)(stream + c_start);
             const unsigned mis = (unsigned)(addr0 & 3ull);
-            bool ok = c_start <= c_end && c_end <= len && (c_end - c_start) + mis <= (FI_STREAM_WORDS - 1) * 4u;
-            if (ok) {
-                const uint32_t* wsrc = (const uint32_t*)(uintptr_t)(addr0 - mis);
-                const unsigned nwords = ((c_end - c_start) + mis + 3u) >> 2;
+            const bool ok = c_start <= c_end && c_end <= len;
+            const uint32_t* wsrc = (const uint32_t*)(uintptr_t)(addr0 - mis);
+            const unsigned nwords = ok ? (((c_end - c_start) + mis + 3u) >> 2) : 0u;
+            const bool staged = nwords <= FI_STREAM_WORDS;
+            if (ok && staged)
                 for (unsigned i = lane; i < nwords; i += 32) ws.sbytes[i] = __ldg(wsrc + i);
-            }
             __syncwarp();
             int bad = ok ? 0 : 1;
             if (ok && lane < nvalid) {
+                int16_t* row = (int16_t*)(ws.coef + lane * FF_COEF_W);
+                const uint32_t bit0 = (my_start - c_start + mis) * 8u, bitl = (c_end - c_start + mis) * 8u;
                 if (my_start < c_start || my_start >= c_end) bad = 1;
-                else bad = fi_decode_block(ws.sbytes, (my_start - c_start + mis) * 8u, (c_end - c_start + mis) * 8u,
-                                           (int16_t*)(ws.coef + lane * FF_COEF_W), s_izz);
+                else if (staged) bad = fi_decode_block<false>(ws.sbytes, nwords, bit0, bitl, row, s_izz);
+                else bad = fi_decode_block<true>(wsrc, nwords, bit0, bitl, row, s_izz);
             }
             if (__any_sync(0xffffffffu, bad) && lane == 0) jb_set_error(a.status, JB_ERR_BAD_STREAM);
         }
         __syncwarp();
 
         // ---- 4 blocks per iteration ----
+        FiCursor cur;
+        cur.it = 0; cur.by = blk0 / g.hb; cur.bx = blk0 - cur.by * g.hb;
         for (int it = 0; it < nit; ++it) {
             const int slot = (int)(store_seq % FI_RING);
             uint8_t* tile = ws.tile[slot];
-            const int kind = fi_tile_kind(g, blk0, nvalid, it, ka.aligned != 0);
+            const int kind = fi_tile_kind(g, nvalid, cur, ka.aligned != 0);
             // the TMA store issued FI_RING tiles ago must have finished reading this slot
             if (lane == 0) ff_bulk_wait_read<FI_RING - 1>();
             __syncwarp();
@@ -195,14 +204,12 @@ jb_inv_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FiKernelArgs 
             uint8_t* plane_ptr = a.planes_out + (size_t)plane * a.plane_stride;
             if (kind <= 1 && ka.use_tma) {
                 if (lane == 0) {
-                    const int by = n0 / g.hb, bx = n0 - by * g.hb;
                     ff_fence_proxy_async();
-                    ff_tma_store_3d(&tmap, bx * 32, by * 32, plane, tile);
+                    ff_tma_store_3d(&tmap, cur.bx * 32, cur.by * 32, plane, tile);
                     ff_bulk_commit();
                 }
             } else if (kind == 0) {
-                const int by = n0 / g.hb, bx = n0 - by * g.hb;
-                uint8_t* dst = plane_ptr + (size_t)by * 32 * a.row_pitch + (size_t)bx * 32;
+                uint8_t* dst = plane_ptr + (size_t)cur.by * 32 * a.row_pitch + (size_t)cur.bx * 32;
                 const uint4* t16 = (const uint4*)tile;
                 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
@@ -225,6 +232,9 @@ jb_inv_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FiKernelArgs 
                 }
             }
             ++store_seq;
+            ++cur.it;
+            cur.bx += 4;
+            while (cur.bx >= g.hb) { cur.bx -= g.hb; ++cur.by; }
             __syncwarp();
         }
     }
