@@ -200,6 +200,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")       # keep NCCL's version banner off stdout
         dist.init_process_group("nccl", device_id=device)
 
     i0, i1 = jb.sharding.image_slice(N_IMAGES, rank, world)

@@ -164,21 +164,43 @@ __device__ __forceinline__ void jb_walk_tile(JbWalker& w, const JbFrameArgs& f, 
     uint32_t exit_pos = pos;                     // == tend if the tile holds no candidate
     if (pos < tend) {
         w.seek(pos);
-        const uint32_t maxblk_bits = (uint32_t)f.maxblk * 8u;
+        V[n++] = (uint16_t)(pos - tstart);
+        int count = 0;
+        // one flat loop over codes (not one loop per block): the 32 lanes of a warp stay converged
+        // although their blocks end at different codes
         for (;;) {
-            V[n++] = (uint16_t)(pos - tstart);
-            if (!w.block(f.n, maxblk_bits)) {
-                // `pos` was a false start (in a valid stream): resume at the next offset that
-                // follows a 0x00 byte; the list stays sorted and the true chain joins it later
-                uint32_t q = pos + 1;
+            if (w.nb < 23) { w.buf = (w.buf << 32) | w.load(w.widx++); w.nb += 32; }
+            const uint32_t head = (uint32_t)(w.buf >> (w.nb - 8)) & 0xFFu;
+            const uint32_t size = head & 15u;
+            const bool zero_size = size == 0u, eob = head == 0u;
+            w.nb -= zero_size ? 8 : 8 + (int)size;
+            count += zero_size ? (eob ? 0 : JB_MAX_RUN) : (int)(head >> 4) + 1;
+            bool bad = (zero_size && !eob && head != 0xF0u) || size == 1u || count > f.n;
+            uint32_t next = 0;
+            if (eob) {
+                uint32_t abs_bits = w.widx * 32u - (uint32_t)w.nb;
+                const uint32_t pad = (8u - (abs_bits & 7u)) & 7u;
+                w.nb -= (int)pad;
+                abs_bits += pad;
+                next = w.origin + ((abs_bits - w.shift_bits) >> 3);
+                bad = bad || next * 8u > w.len_bits;
+            }
+            if (bad) {
+                // the last recorded start was false (in a valid stream): resume at the next offset
+                // that follows a 0x00 byte; the list stays sorted, the true chain joins it later
+                uint32_t q = (uint32_t)V[n - 1] + tstart + 1u;
                 while (q < tend && w.byte_at(q - 1) != 0) ++q;
                 if (q >= tend) { exit_pos = JB_POS_INVALID; break; }
-                pos = q;
-                w.seek(pos);
+                w.seek(q);
+                V[n++] = (uint16_t)(q - tstart);
+                count = 0;
                 continue;
             }
-            pos = w.bp >> 3;
-            if (pos >= tend) { exit_pos = pos; break; }
+            if (eob) {
+                if (next >= tend) { exit_pos = next; break; }
+                V[n++] = (uint16_t)(next - tstart);
+                count = 0;
+            }
         }
     }
     f.tile_n[tile] = n;
