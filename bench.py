@@ -320,10 +320,15 @@ def run_ours(args, rank, world, local_rank):
             "roofline": {"bound": "hbm", "kernel": "jb_fwd_fast_kernel (fused compress; timed with the table "
                          "builder and two memsets of the same call)", "achieved": ach_c, "peak": peak,
                          "unit": "GB/s", "frac": ach_c / peak, "frac_of_nominal_8000": ach_c / 8000.0,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": a_c},
+                         # dram__bytes_read+write of one launch from `ncu --set full` at 1024 images on one GPU
+                         # (profiles/r1_ncu_full_prof_fwd_full_r1.csv: 6.389 GB + 0.127 GB), scaled to this rank's share
+                         "traffic": 6.516e9 * n_img / 1024.0, "traffic_source": "profiles/r1_ncu_full_prof_fwd_full_r1.csv",
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": a_c},
             "roofline_decompress": {"bound": "hbm", "kernel": "framing kernels + jb_inv_fast_kernel",
                                     "achieved": ach_d, "peak": peak, "unit": "GB/s", "frac": ach_d / peak,
-                                    "frac_of_nominal_8000": ach_d / 8000.0, "traffic": None,
+                                    "frac_of_nominal_8000": ach_d / 8000.0,
+                                    "traffic": 6.470e9 * n_img / 1024.0,
+                                    "traffic_source": "profiles/r1_ncu_full_prof_inv_full_r1.csv (fused inverse kernel only)",
                                     "algorithmic_bytes_per_launch": a_d},
             "cpu_baseline": cpu,
             "e2e": e2e,
