@@ -77,6 +77,7 @@ struct FfCursor {           // position of a 4-block group inside the stream of 
     unsigned chunk;
     int plane, blk0, nvalid, nit, it;
     int by, bx;             // block coordinates of the group's first block
+    int kind;               // ff_cursor_kind of this group (computed once, when the tile is issued)
 };
 
 __device__ __forceinline__ void ff_cursor_set(FfCursor& c, unsigned chunk, const JbGeom& g) {
@@ -227,40 +228,46 @@ jb_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfKernelArgs 
         return __shfl_sync(0xffffffffu, c, 0);
     };
 
-    FfCursor cc, ic;                       // consume / issue cursors
+    // The warp walks a stream of 4-block tiles (chunk after chunk) one tile ahead of itself: while tile
+    // `cc` is transformed, the TMA load of tile `nx` is in flight in the other ring slot.
+    FfCursor cc;
     {
         const unsigned first = claim();
         if (first >= a.n_chunks) return;
         ff_cursor_set(cc, first, g);
-        ic = cc;
     }
-    unsigned seq_issue = 0, seq_consume = 0, phasebits = 0;
-    bool no_more = false;
+    auto issue = [&](FfCursor& c, int slot) {
+        c.kind = ff_cursor_kind(c, g, aligned);
+        if (use_tma && c.kind == 0 && lane == 0) {
+            ff_fence_proxy_async();
+            ff_mbar_expect_tx(&ws.bar[slot], FF_TILE_BYTES);
+            ff_tma_load_3d(ws.tile[slot], &tmap, c.bx * 32, c.by * 32, c.plane, &ws.bar[slot]);
+        }
+    };
+    int slot = 0;
+    unsigned phasebits = 0;
+    issue(cc, 0);
+    bool have = true;
 
-    for (;;) {
-        const uint8_t* plane_ptr = a.planes + (size_t)cc.plane * a.plane_stride;
-        for (; cc.it < cc.nit; ff_cursor_next(cc, g)) {
-            // keep the ring full: at most FF_RING tiles issued and not consumed, at most one chunk ahead
-            while (seq_issue - seq_consume < FF_RING) {
-                if (ic.it == ic.nit) {
-                    if (ic.chunk != cc.chunk || no_more) break;
-                    const unsigned nx = claim();
-                    if (nx >= a.n_chunks) { no_more = true; break; }
-                    ff_cursor_set(ic, nx, g);
-                }
-                if (use_tma && ff_cursor_kind(ic, g, aligned) == 0 && lane == 0) {
-                    const int slot = (int)(seq_issue % FF_RING);
-                    ff_fence_proxy_async();
-                    ff_mbar_expect_tx(&ws.bar[slot], FF_TILE_BYTES);
-                    ff_tma_load_3d(ws.tile[slot], &tmap, ic.bx * 32, ic.by * 32, ic.plane, &ws.bar[slot]);
-                }
-                ++seq_issue;
-                ff_cursor_next(ic, g);
-            }
+    while (have) {
+        // ---- the tile after this one: same chunk, or the first tile of a freshly claimed chunk ----
+        FfCursor nx = cc;
+        bool have_next = true;
+        if (cc.it + 1 < cc.nit) {
+            ++nx.it;
+            nx.bx += 4;
+            while (nx.bx >= g.hb) { nx.bx -= g.hb; ++nx.by; }
+        } else {
+            const unsigned c2 = claim();
+            have_next = c2 < a.n_chunks;
+            if (have_next) ff_cursor_set(nx, c2, g);
+        }
+        if (have_next) issue(nx, slot ^ 1);
 
-            const int slot = (int)(seq_consume % FF_RING);
+        {
+            const uint8_t* plane_ptr = a.planes + (size_t)cc.plane * a.plane_stride;
             uint8_t* tile = ws.tile[slot];
-            const int kind = ff_cursor_kind(cc, g, aligned);
+            const int kind = cc.kind;
             if (kind == 0 && use_tma) {
                 const uint32_t par = (phasebits >> slot) & 1u;
                 int spins = 0;
@@ -319,9 +326,11 @@ jb_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfKernelArgs 
             const int gblk = 4 * cc.it + lb;                // block inside the chunk
             int qi[8];
             unsigned nearmask = 0;
+            float vmax = 0.f;
             #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const float val = y[u] * qm[u];
+                vmax = fmaxf(vmax, fabsf(val));
                 const float t = val + 12582912.0f;          // 1.5 * 2^23: rounds half-even to an integer
                 const float dd = val - (t - 12582912.0f);
                 qi[u] = __float_as_int(t) - 0x4B400000;
@@ -353,24 +362,29 @@ jb_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfKernelArgs 
                         dst[((u < 4 ? zzlo : zzhi) >> (8 * (u & 3))) & 0xFFu] = (int16_t)max(-32767, min(32767, qi[u]));
                 } else {
                     int16_t* row = (int16_t*)(ws.coef + gblk * FF_COEF_W);
-                    #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        int q = qi[u];
-                        const int zp = ((u < 4 ? zzlo : zzhi) >> (8 * (u & 3))) & 0xFFu;
-                        if ((unsigned)(q + JB_MAX_AMP) > 2u * JB_MAX_AMP) {
-                            const int k = atomicAdd(&ws.nbig, 1);
-                            if (k < FF_BIG_CAP) { ws.big_blk[k] = gblk; ws.big_pos[k] = zp; ws.big_amp[k] = q; }
-                            q = q > 0 ? 32767 : -32767;
+                    if (vmax > (float)JB_MAX_AMP - 0.75f) {
+                        // some amplitude may not fit the 15-bit size field: remember the true values for
+                        // the error report, store saturated ones (run_length_encoding stage will flag them)
+                        #pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int zp = ((u < 4 ? zzlo : zzhi) >> (8 * (u & 3))) & 0xFFu;
+                            int q = qi[u];
+                            if (q > JB_MAX_AMP || q < -JB_MAX_AMP) {
+                                const int k = atomicAdd(&ws.nbig, 1);
+                                if (k < FF_BIG_CAP) { ws.big_blk[k] = gblk; ws.big_pos[k] = zp; ws.big_amp[k] = q; }
+                                qi[u] = q > 0 ? 32767 : -32767;
+                            }
                         }
-                        row[zp] = (int16_t)q;
                     }
+                    #pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        row[((u < 4 ? zzlo : zzhi) >> (8 * (u & 3))) & 0xFFu] = (int16_t)qi[u];
                 }
             }
             __syncwarp();          // tile and scr are free again
-            ++seq_consume;
         }
 
-        if (MODE == 0) {
+        if (MODE == 0 && cc.it + 1 == cc.nit) {
             // ---- A9 + A10: lane t packs block t into its (small) staging row ----
             unsigned len = 0;
             if (lane < cc.nvalid) {
@@ -424,19 +438,9 @@ jb_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfKernelArgs 
             __syncwarp();
         }
 
-        // next chunk: either the one the issue cursor already moved into, or a fresh claim
-        if (ic.chunk != cc.chunk) {
-            const int keep_it = ic.it, keep_by = ic.by, keep_bx = ic.bx;
-            cc = ic;
-            ff_cursor_set(cc, ic.chunk, g);
-            ic.it = keep_it; ic.by = keep_by; ic.bx = keep_bx;
-        } else {
-            if (no_more) break;
-            const unsigned nx = claim();
-            if (nx >= a.n_chunks) break;
-            ff_cursor_set(cc, nx, g);
-            ic = cc;
-        }
+        cc = nx;
+        have = have_next;
+        slot ^= 1;
     }
 }
 
