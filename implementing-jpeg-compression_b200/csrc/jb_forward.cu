@@ -286,18 +286,30 @@ __global__ void __launch_bounds__(256) jb_gather_chunks_kernel(JbFwdArgs a) {
     const unsigned long long base = a.seg_total[c / JB_SCAN_SEG] + a.chunk_off[c];
     if (lane == 0 && c % (unsigned)a.g.cpp == 0) a.plane_off[c / (unsigned)a.g.cpp] = base;
     if (base + len > a.out_cap) return;                       // flagged by the segment scan
-    const uint8_t* src = a.tmp + (size_t)c * a.chunk_cap;
+    const uint8_t* src = a.tmp + (size_t)c * a.chunk_cap;        // 16-byte aligned, >= 32 bytes of slack
     uint8_t* dst = a.out + base;
-    // head bytes up to a 4-byte boundary of dst, then word stores fed by unaligned byte gathers
-    const unsigned head = jb_min((int)len, (int)((4u - (unsigned)((uintptr_t)dst & 3u)) & 3u));
+    // head bytes up to a 4-byte boundary of dst; then every lane moves 16 bytes per pass: one
+    // 128-bit load + the following word, funnel-shifted into four aligned words; then the tail
+    const unsigned head = (unsigned)jb_min((int)len, (int)((4u - (unsigned)((uintptr_t)dst & 3u)) & 3u));
     if (lane < (int)head) dst[lane] = src[lane];
     const unsigned nwords = (len - head) >> 2;
-    const uint32_t* s32 = (const uint32_t*)src;               // slot is 16-byte aligned
+    const uint4* s16 = (const uint4*)src;
+    const uint32_t* s32 = (const uint32_t*)src;
     uint32_t* d32 = (uint32_t*)(dst + head);
-    const unsigned sh = (head & 3u) * 8u;
-    for (unsigned i = lane; i < nwords; i += 32) {
-        const unsigned w0 = s32[(head >> 2) + i], w1 = s32[(head >> 2) + i + 1];
-        d32[i] = sh ? __funnelshift_r(w0, w1, sh) : w0;
+    const unsigned sh = head * 8u;
+    for (unsigned j = lane; j * 4u < nwords; j += 32) {
+        const uint4 v = __ldg(s16 + j);
+        const uint32_t nx = __ldg(s32 + 4u * j + 4u);
+        uint32_t w0 = v.x, w1 = v.y, w2 = v.z, w3 = v.w;
+        if (sh) {
+            w0 = __funnelshift_r(v.x, v.y, sh); w1 = __funnelshift_r(v.y, v.z, sh);
+            w2 = __funnelshift_r(v.z, v.w, sh); w3 = __funnelshift_r(v.w, nx, sh);
+        }
+        const unsigned w = 4u * j;
+        d32[w] = w0;
+        if (w + 1 < nwords) d32[w + 1] = w1;
+        if (w + 2 < nwords) d32[w + 2] = w2;
+        if (w + 3 < nwords) d32[w + 3] = w3;
     }
     const unsigned tail0 = head + nwords * 4u;
     if (tail0 + lane < len) dst[tail0 + lane] = src[tail0 + lane];

@@ -43,10 +43,15 @@ struct JbWalker {
     int nb;
     uint32_t bp;                // bit position inside the stream of the next unread bit
     bool in_smem;
+    const uint32_t* gwords;     // staged window only: the same words in global memory ...
+    uint32_t gnwords;           // ... which reach further (a block longer than the staged halo)
 
     __device__ __forceinline__ uint32_t load(uint32_t i) const {
-        if (i >= nwords) return 0u;
-        return jb_bswap32(in_smem ? words[i] : __ldg(words + i));
+        if (in_smem) {
+            if (i < nwords) return jb_bswap32(words[i]);
+            return i < gnwords ? jb_bswap32(__ldg(gwords + i)) : 0u;
+        }
+        return i < nwords ? jb_bswap32(__ldg(words + i)) : 0u;
     }
     // whole stream in global memory
     __device__ __forceinline__ void init(const uint8_t* stream, uint32_t len_bytes) {
@@ -59,9 +64,12 @@ struct JbWalker {
         in_smem = false;
     }
     // a staged window: smem_words[0] holds the aligned word that contains stream byte `first_byte`
-    __device__ __forceinline__ void init_window(const uint32_t* smem_words, uint32_t n_words, uint32_t first_byte,
-                                                uint32_t misalign_bytes, uint32_t len_bytes) {
+    __device__ __forceinline__ void init_window(const uint32_t* smem_words, uint32_t n_words,
+                                                const uint32_t* global_words, uint32_t n_global_words,
+                                                uint32_t first_byte, uint32_t misalign_bytes, uint32_t len_bytes) {
         words = smem_words;
+        gwords = global_words;
+        gnwords = n_global_words;
         origin = first_byte;
         shift_bits = misalign_bytes * 8u;
         nwords = n_words;
@@ -70,7 +78,7 @@ struct JbWalker {
     }
     __device__ __forceinline__ uint32_t byte_at(uint32_t pos) const {       // stream byte `pos` (>= origin)
         const uint32_t b = pos - origin + (shift_bits >> 3);
-        const uint32_t w = in_smem ? words[b >> 2] : __ldg(words + (b >> 2));
+        const uint32_t w = (in_smem && (b >> 2) < nwords) ? words[b >> 2] : __ldg((in_smem ? gwords : words) + (b >> 2));
         return (w >> ((b & 3u) * 8u)) & 0xFFu;
     }
     __device__ __forceinline__ void seek(uint32_t byte_pos) {
@@ -150,7 +158,8 @@ __global__ void __launch_bounds__(1024) jb_frame_prep_kernel(JbFrameArgs f) {
 }
 
 // ---- F1: walk ----------------------------------------------------------------------------------
-#define JB_WALK_THREADS 96
+#define JB_WALK_THREADS 128
+#define JB_WALK_HALO 64           // bytes staged beyond the tile; longer blocks continue from global memory
 
 __device__ __forceinline__ void jb_walk_tile(JbWalker& w, const JbFrameArgs& f, unsigned tile, uint32_t tstart,
                                              uint32_t tend) {
@@ -221,14 +230,14 @@ __global__ void __launch_bounds__(JB_WALK_THREADS) jb_frame_walk_kernel(JbFrameA
 }
 
 // small tiles: the warp first copies each lane's window (one byte before the tile, the tile, and
-// the longest block beyond it) into that lane's slice of shared memory with coalesced loads
+// JB_WALK_HALO bytes beyond it) into that lane's slice of shared memory with coalesced loads
 __global__ void __launch_bounds__(JB_WALK_THREADS) jb_frame_walk_smem_kernel(JbFrameArgs f, unsigned stride_words) {
     extern __shared__ uint32_t s_words[];
     const int lane = threadIdx.x & 31;
     const unsigned total_tiles = f.tile_first[f.n_planes];
     const unsigned tile = blockIdx.x * JB_WALK_THREADS + threadIdx.x;
     const bool live = tile < total_tiles;
-    uint32_t len = 0, tstart = 0, tend = 0, first = 0, mis = 0, nw = 0;
+    uint32_t len = 0, tstart = 0, tend = 0, first = 0, mis = 0, nw = 0, gnw = 0;
     unsigned long long abase = 0;                   // aligned global address of the window
     if (live) {
         const int s = jb_stream_of_tile(f.tile_first, f.n_planes, tile);
@@ -236,12 +245,13 @@ __global__ void __launch_bounds__(JB_WALK_THREADS) jb_frame_walk_smem_kernel(JbF
         tstart = (tile - f.tile_first[s]) * f.tile_bytes;
         tend = (uint32_t)jb_min((int)(tstart + f.tile_bytes), (int)len);
         first = tstart ? tstart - 1 : 0;
-        const uint32_t last = (uint32_t)jb_min((int)(tstart + f.tile_bytes + f.maxblk + 4), (int)len);
+        const uint32_t last = (uint32_t)jb_min((int)(tstart + f.tile_bytes + JB_WALK_HALO), (int)len);
         const unsigned long long a0 = (unsigned long long)(uintptr_t)(f.in + f.plane_off[s] + first);
         mis = (uint32_t)(a0 & 3ull);
         abase = a0 - mis;
         nw = (last - first + mis + 3u) >> 2;
         if (nw > stride_words) nw = stride_words;
+        gnw = (len - first + mis + 3u) >> 2;
     }
     uint32_t* mine = s_words + (size_t)threadIdx.x * stride_words;
     // four tiles at a time, up to sixteen loads in flight per lane
@@ -277,7 +287,7 @@ __global__ void __launch_bounds__(JB_WALK_THREADS) jb_frame_walk_smem_kernel(JbF
     __syncwarp();
     if (!live) return;
     JbWalker w;
-    w.init_window(mine, nw, first, mis, len);
+    w.init_window(mine, nw, (const uint32_t*)(uintptr_t)abase, gnw, first, mis, len);
     jb_walk_tile(w, f, tile, tstart, tend);
 }
 
@@ -418,8 +428,8 @@ cudaError_t jb_launch_framing(const JbFrameArgs& f, cudaStream_t s) {
     const unsigned wgrid = (f.max_tiles + JB_WALK_THREADS - 1) / JB_WALK_THREADS;
     jb_frame_prep_kernel<<<1, 1024, 0, s>>>(f);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    // window of one walk: 1 byte before the tile + tile + longest block + slack, in words, odd stride
-    const unsigned stride_words = (((unsigned)f.tile_bytes + (unsigned)f.maxblk + 16u) / 4u) | 1u;
+    // staged window of one walk: 1 byte before the tile + tile + JB_WALK_HALO + slack, in words, odd stride
+    const unsigned stride_words = (((unsigned)f.tile_bytes + JB_WALK_HALO + 16u) / 4u) | 1u;
     const size_t smem = (size_t)JB_WALK_THREADS * stride_words * 4;
     if (smem <= 64 * 1024) {
         e = cudaFuncSetAttribute(jb_frame_walk_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
