@@ -58,6 +58,7 @@ static JbFwdWs jb_fwd_ws(int d, size_t n_chunks) {
     JbFwdWs w;
     size_t o = jb_align_up(jb_table_layout(d).total, 256);
     w.chunk_cap = (unsigned)jb_align_up((size_t)JB_CHUNK * jb_max_block_bytes(d * d) + 32, 16);
+    if (w.chunk_cap < 1024 + 32) w.chunk_cap = 1024 + 32;      // the gather kernel reads 1 KB ahead
     w.ticket = o;    o += 256;
     w.chunk_len = o; o += jb_align_up(n_chunks * 4, 256);
     w.chunk_off = o; o += jb_align_up(n_chunks * 4, 256);

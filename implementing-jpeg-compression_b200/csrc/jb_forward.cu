@@ -282,24 +282,37 @@ __global__ void __launch_bounds__(256) jb_gather_chunks_kernel(JbFwdArgs a) {
     const int lane = threadIdx.x & 31;
     const unsigned c = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (c >= a.n_chunks) return;
+    const uint8_t* src = a.tmp + (size_t)c * a.chunk_cap;        // 16-byte aligned, >= 1 KB + 32 B per slot
+    const uint4* s16 = (const uint4*)src;
+    const uint32_t* s32 = (const uint32_t*)src;
+    // the first kilobyte of the slot is fetched before its length is known: the two round trips
+    // (metadata, data) overlap; an average chunk is ~0.6 KB
+    uint4 pv[2];
+    uint32_t pn[2];
+    #pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        pv[k] = __ldg(s16 + lane + 32 * k);
+        pn[k] = __ldg(s32 + 4 * (lane + 32 * k) + 4);
+    }
     const unsigned len = a.chunk_len[c];
     const unsigned long long base = a.seg_total[c / JB_SCAN_SEG] + a.chunk_off[c];
     if (lane == 0 && c % (unsigned)a.g.cpp == 0) a.plane_off[c / (unsigned)a.g.cpp] = base;
     if (base + len > a.out_cap) return;                       // flagged by the segment scan
-    const uint8_t* src = a.tmp + (size_t)c * a.chunk_cap;        // 16-byte aligned, >= 32 bytes of slack
     uint8_t* dst = a.out + base;
     // head bytes up to a 4-byte boundary of dst; then every lane moves 16 bytes per pass: one
     // 128-bit load + the following word, funnel-shifted into four aligned words; then the tail
     const unsigned head = (unsigned)jb_min((int)len, (int)((4u - (unsigned)((uintptr_t)dst & 3u)) & 3u));
     if (lane < (int)head) dst[lane] = src[lane];
     const unsigned nwords = (len - head) >> 2;
-    const uint4* s16 = (const uint4*)src;
-    const uint32_t* s32 = (const uint32_t*)src;
     uint32_t* d32 = (uint32_t*)(dst + head);
     const unsigned sh = head * 8u;
-    for (unsigned j = lane; j * 4u < nwords; j += 32) {
-        const uint4 v = __ldg(s16 + j);
-        const uint32_t nx = __ldg(s32 + 4u * j + 4u);
+    unsigned pass = 0;
+    for (unsigned j = lane; j * 4u < nwords; j += 32, ++pass) {
+        uint4 v;
+        uint32_t nx;
+        if (pass == 0) { v = pv[0]; nx = pn[0]; }
+        else if (pass == 1) { v = pv[1]; nx = pn[1]; }
+        else { v = __ldg(s16 + j); nx = __ldg(s32 + 4u * j + 4u); }
         uint32_t w0 = v.x, w1 = v.y, w2 = v.z, w3 = v.w;
         if (sh) {
             w0 = __funnelshift_r(v.x, v.y, sh); w1 = __funnelshift_r(v.y, v.z, sh);
