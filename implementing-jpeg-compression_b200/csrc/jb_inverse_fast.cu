@@ -109,14 +109,15 @@ jb_inv_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FiKernelArgs 
         dq[v] = a.t.dqmult[li * 8 + v] * sc;
     }
 
-    // Every warp owns a contiguous run of chunks, so its stream bytes and block offsets are read
-    // sequentially, and the next chunk's inputs are fetched while the current chunk is transformed:
+    // The next chunk's inputs are fetched while the current chunk is transformed:
     // block offsets at the first tile, stream words (into registers) two tiles later, the words go to
     // shared memory once the current chunk no longer needs them.
+    // (chunks are dealt round-robin: the warps of the whole grid then write neighbouring tiles at
+    // about the same time, which DRAM likes better than 2000 far-apart write streams)
     const unsigned total_warps = gridDim.x * FI_WARPS;
-    const unsigned per_warp = (a.n_chunks + total_warps - 1) / total_warps;
-    const unsigned chunk_lo = (blockIdx.x * FI_WARPS + warp) * per_warp;
-    const unsigned chunk_hi = chunk_lo + per_warp < a.n_chunks ? chunk_lo + per_warp : a.n_chunks;
+    const unsigned chunk_lo = blockIdx.x * FI_WARPS + warp;
+    const unsigned chunk_hi = a.n_chunks;
+    const unsigned chunk_step = total_warps;
     unsigned store_seq = 0;
 
     // description of the chunk being staged (warp-uniform except my_start)
@@ -176,12 +177,12 @@ jb_inv_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FiKernelArgs 
         fetch_words(cur_s);
     }
 
-    for (unsigned chunk = chunk_lo; chunk < chunk_hi; ++chunk) {
+    for (unsigned chunk = chunk_lo; chunk < chunk_hi; chunk += chunk_step) {
         if (MODE == 2) describe(cur_s, chunk);
         const int plane = cur_s.plane, blk0 = cur_s.blk0, nvalid = cur_s.nvalid;
         const int nit = (nvalid + 3) >> 2;
-        const bool has_next = MODE != 2 && chunk + 1 < chunk_hi;
-        if (has_next) describe(nxt_s, chunk + 1);
+        const bool has_next = MODE != 2 && chunk + chunk_step < chunk_hi;
+        if (has_next) describe(nxt_s, chunk + chunk_step);
 
         // ---- coefficients of the chunk in natural order ----
         {
