@@ -109,102 +109,48 @@ jb_inv_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FiKernelArgs 
         dq[v] = a.t.dqmult[li * 8 + v] * sc;
     }
 
-    // The next chunk's inputs are fetched while the current chunk is transformed:
-    // block offsets at the first tile, stream words (into registers) two tiles later, the words go to
-    // shared memory once the current chunk no longer needs them.
-    // (chunks are dealt round-robin: the warps of the whole grid then write neighbouring tiles at
-    // about the same time, which DRAM likes better than 2000 far-apart write streams)
     const unsigned total_warps = gridDim.x * FI_WARPS;
-    const unsigned chunk_lo = blockIdx.x * FI_WARPS + warp;
-    const unsigned chunk_hi = a.n_chunks;
-    const unsigned chunk_step = total_warps;
     unsigned store_seq = 0;
-
-    // description of the chunk being staged (warp-uniform except my_start)
-    struct Staged {
-        int plane, blk0, nvalid;
-        unsigned my_start, c_start, c_end, mis, nwords;
-        bool ok, staged;
-        const uint32_t* wsrc;
-    };
-    constexpr int PFW = (FI_STREAM_WORDS + 31) / 32;
-    uint32_t pf[PFW];
-    Staged cur_s, nxt_s;
-    unsigned n_my_start = 0, n_cend_raw = 0;
-    unsigned long long n_len = 0;
-
-    auto describe = [&](Staged& st, unsigned chunk) {
-        st.plane = (int)(chunk / (unsigned)g.cpp);
-        st.blk0 = (int)(chunk - (unsigned)st.plane * (unsigned)g.cpp) * JB_CHUNK;
-        st.nvalid = jb_min(JB_CHUNK, g.nblocks - st.blk0);
-    };
-    auto load_offsets = [&](const Staged& st) {               // step A
-        const unsigned* bs = a.block_start + (size_t)st.plane * g.nblocks + st.blk0;
-        n_len = a.plane_len[st.plane];
-        n_my_start = lane < st.nvalid ? __ldg(bs + lane) : 0u;
-        n_cend_raw = (st.blk0 + st.nvalid < g.nblocks) ? __ldg(bs + st.nvalid) : (unsigned)n_len;
-    };
-    auto locate = [&](Staged& st) {                           // step B, part 1
-        st.my_start = n_my_start;
-        st.c_start = __shfl_sync(0xffffffffu, n_my_start, 0);
-        st.c_end = __shfl_sync(0xffffffffu, n_cend_raw, 0);
-        const unsigned long long addr0 = (unsigned long long)(uintptr_t)(a.in + a.plane_off[st.plane] + st.c_start);
-        st.mis = (unsigned)(addr0 & 3ull);
-        st.ok = st.c_start <= st.c_end && st.c_end <= n_len;
-        st.wsrc = (const uint32_t*)(uintptr_t)(addr0 - st.mis);
-        st.nwords = st.ok ? (((st.c_end - st.c_start) + st.mis + 3u) >> 2) : 0u;
-        st.staged = st.nwords <= FI_STREAM_WORDS;
-    };
-    auto fetch_words = [&](const Staged& st) {                // step B, part 2: stream words -> registers
-        #pragma unroll
-        for (int k = 0; k < PFW; ++k) {
-            const unsigned idx = (unsigned)lane + 32u * k;
-            pf[k] = (st.ok && st.staged && idx < st.nwords) ? __ldg(st.wsrc + idx) : 0u;
-        }
-    };
-    auto commit_words = [&](const Staged& st) {               // registers -> shared memory
-        #pragma unroll
-        for (int k = 0; k < PFW; ++k) {
-            const unsigned idx = (unsigned)lane + 32u * k;
-            if (st.ok && st.staged && idx < st.nwords) ws.sbytes[idx] = pf[k];
-        }
-    };
-
-    if (MODE != 2 && chunk_lo < chunk_hi) {
-        describe(cur_s, chunk_lo);
-        load_offsets(cur_s);
-        locate(cur_s);
-        fetch_words(cur_s);
-    }
-
-    for (unsigned chunk = chunk_lo; chunk < chunk_hi; chunk += chunk_step) {
-        if (MODE == 2) describe(cur_s, chunk);
-        const int plane = cur_s.plane, blk0 = cur_s.blk0, nvalid = cur_s.nvalid;
+    for (unsigned chunk = blockIdx.x * FI_WARPS + warp; chunk < a.n_chunks; chunk += total_warps) {
+        const int plane = (int)(chunk / (unsigned)g.cpp);
+        const int blk0 = (int)(chunk % (unsigned)g.cpp) * JB_CHUNK;
+        const int nvalid = jb_min(JB_CHUNK, g.nblocks - blk0);
         const int nit = (nvalid + 3) >> 2;
-        const bool has_next = MODE != 2 && chunk + chunk_step < chunk_hi;
-        if (has_next) describe(nxt_s, chunk + chunk_step);
 
         // ---- coefficients of the chunk in natural order ----
         {
             uint4* z = (uint4*)ws.coef;
             for (int i = lane; i < JB_CHUNK * FF_COEF_W / 4; i += 32) z[i] = make_uint4(0, 0, 0, 0);
         }
+        __syncwarp();
         if (MODE == 2) {
-            __syncwarp();
             const int16_t* src = a.coeffs_in + ((size_t)plane * g.nblocks + blk0) * 64;
             for (int idx = lane; idx < nvalid * 64; idx += 32)
                 ((int16_t*)(ws.coef + (idx >> 6) * FF_COEF_W))[s_izz[idx & 63]] = src[idx];
         } else {
-            commit_words(cur_s);
+            const unsigned long long len = a.plane_len[plane];
+            const uint8_t* stream = a.in + a.plane_off[plane];
+            const unsigned* bs = a.block_start + (size_t)plane * g.nblocks + blk0;
+            const unsigned my_start = lane < nvalid ? bs[lane] : 0u;
+            const unsigned c_start = __shfl_sync(0xffffffffu, my_start, 0);
+            unsigned c_end = (blk0 + nvalid < g.nblocks) ? bs[nvalid] : (unsigned)len;
+            c_end = __shfl_sync(0xffffffffu, c_end, 0);
+            const unsigned long long addr0 = (unsigned long long)(uintptr_t)(stream + c_start);
+            const unsigned mis = (unsigned)(addr0 & 3ull);
+            const bool ok = c_start <= c_end && c_end <= len;
+            const uint32_t* wsrc = (const uint32_t*)(uintptr_t)(addr0 - mis);
+            const unsigned nwords = ok ? (((c_end - c_start) + mis + 3u) >> 2) : 0u;
+            const bool staged = nwords <= FI_STREAM_WORDS;
+            if (ok && staged)
+                for (unsigned i = lane; i < nwords; i += 32) ws.sbytes[i] = __ldg(wsrc + i);
             __syncwarp();
-            int bad = cur_s.ok ? 0 : 1;
-            if (cur_s.ok && lane < nvalid) {
+            int bad = ok ? 0 : 1;
+            if (ok && lane < nvalid) {
                 int16_t* row = (int16_t*)(ws.coef + lane * FF_COEF_W);
-                const uint32_t bit0 = (cur_s.my_start - cur_s.c_start + cur_s.mis) * 8u;
-                const uint32_t bitl = (cur_s.c_end - cur_s.c_start + cur_s.mis) * 8u;
-                if (cur_s.my_start < cur_s.c_start || cur_s.my_start >= cur_s.c_end) bad = 1;
-                else if (cur_s.staged) bad = fi_decode_block<false>(ws.sbytes, cur_s.nwords, bit0, bitl, row, s_izz);
-                else bad = fi_decode_block<true>(cur_s.wsrc, cur_s.nwords, bit0, bitl, row, s_izz);
+                const uint32_t bit0 = (my_start - c_start + mis) * 8u, bitl = (c_end - c_start + mis) * 8u;
+                if (my_start < c_start || my_start >= c_end) bad = 1;
+                else if (staged) bad = fi_decode_block<false>(ws.sbytes, nwords, bit0, bitl, row, s_izz);
+                else bad = fi_decode_block<true>(wsrc, nwords, bit0, bitl, row, s_izz);
             }
             if (__any_sync(0xffffffffu, bad) && lane == 0) jb_set_error(a.status, JB_ERR_BAD_STREAM);
         }
@@ -220,10 +166,6 @@ jb_inv_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FiKernelArgs 
             // the TMA store issued FI_RING tiles ago must have finished reading this slot
             if (lane == 0) ff_bulk_wait_read<FI_RING - 1>();
             __syncwarp();
-            if (has_next) {
-                if (it == 0) load_offsets(nxt_s);
-                if (it == jb_min(2, nit - 1)) { locate(nxt_s); fetch_words(nxt_s); }
-            }
 
             float z[8], r[8];
             {
@@ -295,7 +237,6 @@ jb_inv_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FiKernelArgs 
             while (cur.bx >= g.hb) { cur.bx -= g.hb; ++cur.by; }
             __syncwarp();
         }
-        if (has_next) cur_s = nxt_s;
     }
     if (lane == 0) ff_bulk_wait_read<0>();
     __syncwarp();
