@@ -103,6 +103,9 @@ def run(name, h, w, bs, d, transform, qname, qparam, n_images, steps=10, warmup=
 
 def main():
     out = []
+    if len(sys.argv) > 1 and sys.argv[1] == "config3":
+        run("3b: 3840x2160 bs5 d24 divide 1000, batch of 8", 2160, 3840, 5, 24, "DCT", "divide", 1000, 8, steps=2, warmup=1)
+        return
     out.append(run("1: 512x512 defaults, single image", 512, 512, 4, 8, "DCT", "qtable", None, 1, check_planes=3))
     out.append(run("1b: 512x512 defaults, batch of 1024", 512, 512, 4, 8, "DCT", "qtable", None, 1024))
     out.append(run("2: 3840x2160 DCT qtable, single image", 2160, 3840, 4, 8, "DCT", "qtable", None, 1))
