@@ -119,6 +119,8 @@ static int jb_forward_common(int mode, const uint8_t* d_planes, size_t plane_str
     if (mode != 2) JB_CUDA_TRY(jb_launch_build_tables(g, a.t, s));
     if (mode != 2 && !(g.flags & JB_FLAG_FORCE_GENERIC) && jb_fwd_fast_eligible(g))
         JB_CUDA_TRY(jb_launch_fwd_fast(a, mode, s));
+    else if (mode != 2 && !(g.flags & JB_FLAG_FORCE_GENERIC) && jb_fwd_mid_eligible(g))
+        JB_CUDA_TRY(jb_launch_fwd_mid(a, mode, s));
     else
         JB_CUDA_TRY(jb_launch_fwd_generic(a, mode, s));
     return JB_OK;
@@ -234,6 +236,8 @@ static int jb_inverse_common(int mode, const uint8_t* d_in, size_t in_bytes, con
     if (mode != 1) JB_CUDA_TRY(jb_launch_build_tables(g, a.t, s));
     if (mode != 1 && !(g.flags & JB_FLAG_FORCE_GENERIC) && jb_inv_fast_eligible(g))
         JB_CUDA_TRY(jb_launch_inv_fast(a, mode, s));
+    else if (mode != 1 && !(g.flags & JB_FLAG_FORCE_GENERIC) && jb_inv_mid_eligible(g))
+        JB_CUDA_TRY(jb_launch_inv_mid(a, mode, s));
     else
         JB_CUDA_TRY(jb_launch_inv_generic(a, mode, s));
     return JB_OK;

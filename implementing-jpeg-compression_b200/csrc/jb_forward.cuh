@@ -32,6 +32,10 @@ size_t jb_fwd_generic_smem_bytes(int d, bool dft);
 cudaError_t jb_launch_scan_gather(const JbFwdArgs& a, cudaStream_t s);
 cudaError_t jb_launch_fwd_generic(const JbFwdArgs& a, int mode, cudaStream_t s);
 
+// large-block path: dct_size a multiple of 4, source tile in shared memory (jb_forward_mid.cu)
+bool jb_fwd_mid_eligible(const JbGeom& g);
+cudaError_t jb_launch_fwd_mid(const JbFwdArgs& a, int mode, cudaStream_t s);
+
 // specialised path: dct_size 8, block_size 4 (jb_forward_fast.cu)
 bool jb_fwd_fast_eligible(const JbGeom& g);
 cudaError_t jb_launch_fwd_fast(const JbFwdArgs& a, int mode, cudaStream_t s);

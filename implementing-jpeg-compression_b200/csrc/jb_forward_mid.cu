@@ -1,0 +1,335 @@
+// jb_forward_mid.cu -- compress direction for "large block" configurations: dct_size a multiple of 4
+// (8..32), any block_size whose source tile (d*bs)^2 fits shared memory -- BASELINE.json config 3
+// (--block_size 5 --dct_size 24).  One CTA per chunk of 32 blocks, the blocks go through the CTA one
+// after another:
+//   1. the (d*bs) x (d*bs) source tile is copied to shared memory with 8-byte coalesced loads
+//      (edge / misaligned tiles: clamped byte loads -- padding.py:8-12, dct_padding.py:8-9);
+//   2. separable box sums: horizontal sums of bs bytes per (row, column), then vertical sums of bs
+//      rows -> exact integer sums X (subsampling.py:9-11 without the division);
+//   3. C.X.C^T as two register-tiled contractions out of shared memory (transforms.py:46-58):
+//      each thread owns 4 outputs and streams X and 4-wide slices of C^T -- 2 shared loads per 4 FFMA.
+//      fp32 on exact integers; coefficients within the fp32 error bound of a rounding tie are
+//      re-evaluated in fp64 (jb_tables.cu);
+//   4. quantise, zigzag, int16 rows; a non-zero bitmap per block is built with ballots so that
+//   5. the run-length / bit-packing stage (one lane per block, util.py:146-160,203-221) visits only
+//      the non-zero coefficients;
+//   6. the chunk's bytes go, compacted, to its slot; jb_launch_scan_gather places them.
+// A tensor-core variant was considered and rejected: the contraction is ~2 MAC per source byte, far
+// below the FFMA roof at HBM speed, and tf32/bf16 cannot carry a 576-term sum of 8-bit data to
+// rounding accuracy.
+#include "jb_common.cuh"
+#include "jb_forward.cuh"
+
+#define FM_THREADS 256
+#define FM_STAGE_BYTES 128            // staging row per block; longer blocks are packed again, bytes to the slot
+#define FM_BIG_CAP 16
+
+struct FmLayout {
+    int side;            // d * bs: rows and bytes per row of the source tile
+    int pitch;           // bytes per tile row in shared memory (multiple of 8)
+    int coefW;           // words per coefficient row (odd)
+    int maskW;           // words of non-zero bitmap per block
+    int stageW;          // words per staging row (odd)
+    size_t at, bt, qm, qt, zz, tile, hsum, x, t, t2, coef, mask, stage, total;
+};
+
+__host__ __device__ inline FmLayout fm_layout(int d, int bs, bool dft) {
+    FmLayout L;
+    const int n = d * d;
+    L.side = d * bs;
+    L.pitch = (L.side + 7) / 8 * 8;
+    L.coefW = ((n + 1) / 2) | 1;
+    L.maskW = (n + 31) / 32;
+    L.stageW = (FM_STAGE_BYTES / 4) | 1;
+    size_t o = 0;
+    L.at = o;    o += (size_t)n * 4;
+    L.bt = o;    o += dft ? (size_t)n * 4 : 0;
+    L.qm = o;    o += (size_t)n * 4;
+    L.qt = o;    o += (size_t)n * 4;
+    L.zz = o;    o += jb_align_up((size_t)n * 2, 16);
+    L.tile = o;  o += jb_align_up((size_t)L.side * L.pitch, 16);
+    L.hsum = o;  o += jb_align_up((size_t)L.side * d * 2, 16);
+    L.x = o;     o += (size_t)n * 4;
+    L.t = o;     o += (size_t)n * 4;
+    L.t2 = o;    o += dft ? (size_t)n * 4 : 0;
+    L.coef = o;  o += (size_t)JB_CHUNK * L.coefW * 4;
+    L.mask = o;  o += (size_t)JB_CHUNK * L.maskW * 4;
+    L.stage = o; o += (size_t)JB_CHUNK * L.stageW * 4;
+    L.total = o;
+    return L;
+}
+
+bool jb_fwd_mid_eligible(const JbGeom& g) {
+    if (g.d < 8 || g.d % 4 != 0 || g.d > JB_MAX_DCT_SIZE) return false;
+    return fm_layout(g.d, g.bs, g.transform == JB_TRANSFORM_DFT).total <= 200 * 1024;
+}
+
+// fp64 re-evaluation from float box sums (same order as jb_refine_coefficient in jb_forward.cu)
+__device__ __noinline__ double fm_refine(const float* X, int u, int v, int d, int bs, int transform, int qmode,
+                                         const double* A64, const double* B64, double recip) {
+    const double bs2 = (double)(bs * bs);
+    double y = 0.0;
+    for (int i = 0; i < d; ++i) {
+        double mc = 0.0, ms = 0.0;
+        for (int j = 0; j < d; ++j) {
+            const double x = (double)X[i * d + j] / bs2;
+            mc += A64[v * d + j] * x;
+            if (transform == JB_TRANSFORM_DFT) ms += B64[v * d + j] * x;
+        }
+        y += A64[u * d + i] * mc;
+        if (transform == JB_TRANSFORM_DFT) y -= B64[u * d + i] * ms;
+    }
+    if (qmode == JB_Q_QTABLE) return y * recip;
+    if (qmode == JB_Q_DIVIDE) return y / recip;
+    return y;
+}
+
+template <typename Writer>
+__device__ __forceinline__ void fm_pack_masked(const int16_t* c, const uint32_t* mask, int mask_words, Writer& bw,
+                                               int& bad_pos, int& bad_run) {
+    int prev = -1;
+    bad_pos = -1; bad_run = 0;
+    for (int wi = 0; wi < mask_words; ++wi) {
+        uint32_t m = mask[wi];
+        while (m) {
+            const int p = wi * 32 + __ffs((int)m) - 1;
+            m &= m - 1;
+            const int amp = c[p];
+            const int run = p - prev - 1;
+            prev = p;
+            if (!jb_put_coefficient(bw, run, amp) && bad_pos < 0) { bad_pos = p; bad_run = run % JB_MAX_RUN; }
+        }
+    }
+    bw.put(0u, 8);
+}
+
+template <bool DFT, int MODE>
+__global__ void __launch_bounds__(FM_THREADS)
+jb_fwd_mid_kernel(const JbFwdArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const JbGeom& g = a.g;
+    const int d = g.d, n = g.n, bs = g.bs, q4 = d >> 2;
+    const FmLayout L = fm_layout(d, bs, DFT);
+    float* sAt = (float*)(smem + L.at);          // At[j][v] = A[v][j]
+    float* sBt = (float*)(smem + L.bt);
+    float* sQm = (float*)(smem + L.qm);
+    float* sQt = (float*)(smem + L.qt);
+    uint16_t* sZz = (uint16_t*)(smem + L.zz);
+    uint8_t* sTile = smem + L.tile;
+    uint16_t* sH = (uint16_t*)(smem + L.hsum);
+    float* sX = (float*)(smem + L.x);
+    float* sT = (float*)(smem + L.t);
+    float* sT2 = (float*)(smem + L.t2);
+    uint32_t* sCoef = (uint32_t*)(smem + L.coef);
+    uint32_t* sMask = (uint32_t*)(smem + L.mask);
+    uint32_t* sStage = (uint32_t*)(smem + L.stage);
+
+    __shared__ unsigned s_chunk;
+    __shared__ unsigned s_blen[JB_CHUNK], s_boff[JB_CHUNK];
+    __shared__ int s_big_blk[FM_BIG_CAP], s_big_pos[FM_BIG_CAP], s_big_amp[FM_BIG_CAP];
+    __shared__ int s_nbig, s_slow;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { s_chunk = atomicAdd(a.ticket, 1u); s_nbig = 0; s_slow = 0; }
+    for (int idx = tid; idx < n; idx += FM_THREADS) {
+        const int v = idx / d, j = idx - v * d;
+        sAt[j * d + v] = a.t.fA[idx];
+        if (DFT) sBt[j * d + v] = a.t.fB[idx];
+        sQm[idx] = a.t.qmult[idx];
+        sQt[idx] = a.t.qtol[idx];
+        sZz[idx] = a.t.zz[idx];
+    }
+    __syncthreads();
+    const unsigned chunk = s_chunk;
+    if (chunk >= a.n_chunks) return;
+    const int plane = chunk / g.cpp;
+    const int blk0 = (chunk % g.cpp) * JB_CHUNK;
+    const int nvalid = jb_min(JB_CHUNK, g.nblocks - blk0);
+    const uint8_t* src = a.planes + (size_t)plane * a.plane_stride;
+    const int side = L.side, pitch = L.pitch;
+    const bool vec_ok = (side % 8 == 0) && (((uintptr_t)src & 7) == 0) && (a.row_pitch % 8 == 0);
+    const bool refine_on = !(g.flags & JB_FLAG_NO_REFINE);
+
+    // thread roles of the two contractions: (row/col index, group of 4 outputs)
+    const int ci = tid / q4, cq = tid - ci * q4;
+    const bool c_live = ci < d;
+
+    for (int gi = 0; gi < nvalid; ++gi) {
+        const int blk = blk0 + gi;
+        const int by = blk / g.hb, bx = blk - by * g.hb;
+        // ---- 1. source tile -> shared memory ----
+        const bool interior = (by + 1) * side <= g.H && (bx + 1) * side <= g.W;
+        if (interior && vec_ok) {
+            const int w8 = side >> 3;
+            const uint8_t* base = src + (size_t)by * side * a.row_pitch + (size_t)bx * side;
+            for (int idx = tid; idx < side * w8; idx += FM_THREADS) {
+                const int r = idx / w8, c = idx - r * w8;
+                *(uint2*)(sTile + r * pitch + c * 8) = __ldg((const uint2*)(base + (size_t)r * a.row_pitch) + c);
+            }
+        } else {
+            for (int idx = tid; idx < side * side; idx += FM_THREADS) {
+                const int r = idx / side, c = idx - r * side;
+                const int si = jb_min(by * d + r / bs, g.H1 - 1), sj = jb_min(bx * d + c / bs, g.W1 - 1);
+                const int y = jb_min(si * bs + r % bs, g.H - 1), x = jb_min(sj * bs + c % bs, g.W - 1);
+                sTile[r * pitch + c] = src[(size_t)y * a.row_pitch + x];
+            }
+        }
+        __syncthreads();
+        // ---- 2a. horizontal sums: lane = column j, warps stride over the tile rows ----
+        if (lane < d) {
+            for (int r = warp; r < side; r += FM_THREADS / 32) {
+                const uint8_t* p = sTile + r * pitch + lane * bs;
+                int s = 0;
+                for (int k = 0; k < bs; ++k) s += p[k];
+                sH[r * d + lane] = (uint16_t)s;
+            }
+        }
+        __syncthreads();
+        // ---- 2b. vertical sums -> X (exact integers, as float) ----
+        if (lane < d) {
+            for (int i = warp; i < d; i += FM_THREADS / 32) {
+                int s = 0;
+                for (int k = 0; k < bs; ++k) s += sH[(i * bs + k) * d + lane];
+                sX[i * d + lane] = (float)s;
+            }
+        }
+        __syncthreads();
+        // ---- 3a. T[i][v] = sum_j X[i][j] A[v][j]: thread (i, group of 4 v) ----
+        if (c_live) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), acc2 = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float* xr = sX + ci * d;
+            for (int j = 0; j < d; ++j) {
+                const float x = xr[j];
+                const float4 c4 = *(const float4*)(sAt + j * d + 4 * cq);
+                acc.x = fmaf(x, c4.x, acc.x); acc.y = fmaf(x, c4.y, acc.y);
+                acc.z = fmaf(x, c4.z, acc.z); acc.w = fmaf(x, c4.w, acc.w);
+                if (DFT) {
+                    const float4 s4 = *(const float4*)(sBt + j * d + 4 * cq);
+                    acc2.x = fmaf(x, s4.x, acc2.x); acc2.y = fmaf(x, s4.y, acc2.y);
+                    acc2.z = fmaf(x, s4.z, acc2.z); acc2.w = fmaf(x, s4.w, acc2.w);
+                }
+            }
+            *(float4*)(sT + ci * d + 4 * cq) = acc;
+            if (DFT) *(float4*)(sT2 + ci * d + 4 * cq) = acc2;
+        }
+        __syncthreads();
+        // ---- 3b. Y[u][v] = sum_i A[u][i] T[i][v] (- B[u][i] T2[i][v]): thread (v, group of 4 u) ----
+        if (c_live) {
+            const int v = ci;
+            float y4[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int i = 0; i < d; ++i) {
+                const float t = sT[i * d + v];
+                const float4 c4 = *(const float4*)(sAt + i * d + 4 * cq);
+                y4[0] = fmaf(c4.x, t, y4[0]); y4[1] = fmaf(c4.y, t, y4[1]);
+                y4[2] = fmaf(c4.z, t, y4[2]); y4[3] = fmaf(c4.w, t, y4[3]);
+                if (DFT) {
+                    const float t2 = sT2[i * d + v];
+                    const float4 s4 = *(const float4*)(sBt + i * d + 4 * cq);
+                    y4[0] = fmaf(-s4.x, t2, y4[0]); y4[1] = fmaf(-s4.y, t2, y4[1]);
+                    y4[2] = fmaf(-s4.z, t2, y4[2]); y4[3] = fmaf(-s4.w, t2, y4[3]);
+                }
+            }
+            // ---- 4. quantise, tie check, zigzag ----
+            #pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int u = 4 * cq + k, idx = u * d + v;
+                const float val = y4[k] * sQm[idx];
+                float r = rintf(val);
+                if (refine_on && fabsf(fabsf(val - r) - 0.5f) < sQt[idx] + 2.4e-7f * fabsf(val))
+                    r = (float)rint(fm_refine(sX, u, v, d, bs, g.transform, g.qmode, a.t.fA64, a.t.fB64, a.t.qrecip[idx]));
+                int q = (int)r;
+                const int zp = sZz[idx];
+                if (MODE == 1) {
+                    a.coeffs_out[((size_t)plane * g.nblocks + blk) * n + zp] = (int16_t)max(-32767, min(32767, q));
+                } else {
+                    if (q > JB_MAX_AMP || q < -JB_MAX_AMP) {
+                        const int kk = atomicAdd(&s_nbig, 1);
+                        if (kk < FM_BIG_CAP) { s_big_blk[kk] = gi; s_big_pos[kk] = zp; s_big_amp[kk] = q; }
+                        q = q > 0 ? 32767 : -32767;
+                    }
+                    ((int16_t*)(sCoef + gi * L.coefW))[zp] = (int16_t)q;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- non-zero bitmap of the block (zigzag order) ----
+        if (MODE != 1) {
+            const int16_t* row = (const int16_t*)(sCoef + gi * L.coefW);
+            for (int w0 = warp; w0 < L.maskW; w0 += FM_THREADS / 32) {
+                const int p = w0 * 32 + lane;
+                const unsigned m = __ballot_sync(0xffffffffu, p < n && row[p] != 0);
+                if (lane == 0) sMask[gi * L.maskW + w0] = m;
+            }
+        }
+        // (the next block's tile load does not touch anything the bitmap pass reads)
+    }
+    if (MODE == 1) return;
+    __syncthreads();
+
+    // ---- 5. run-length + bit packing, one lane per block, non-zero coefficients only ----
+    if (tid < JB_CHUNK) {
+        unsigned len = 0;
+        if (tid < nvalid) {
+            const int16_t* c = (const int16_t*)(sCoef + tid * L.coefW);
+            JbBitWriter bw;
+            bw.init(sStage + tid * L.stageW, FM_STAGE_BYTES / 4);
+            int bad_pos, bad_run;
+            fm_pack_masked(c, sMask + tid * L.maskW, L.maskW, bw, bad_pos, bad_run);
+            len = bw.finish();
+            if (len > FM_STAGE_BYTES) s_slow = 1;
+            if (bad_pos >= 0) {
+                long long amp = c[bad_pos];
+                const int nb = jb_min(s_nbig, FM_BIG_CAP);
+                for (int k = 0; k < nb; ++k)
+                    if (s_big_blk[k] == tid && s_big_pos[k] == bad_pos) amp = s_big_amp[k];
+                jb_report_bad_code(a.status, (unsigned long long)plane * g.nblocks + blk0 + tid, bad_pos, bad_run, amp);
+            }
+        }
+        unsigned incl = len;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (tid >= o) incl += y;
+        }
+        s_blen[tid] = len;
+        s_boff[tid] = incl - len;
+        if (tid == 31) a.chunk_len[chunk] = incl;
+    }
+    __syncthreads();
+    // ---- 6. chunk bytes -> slot ----
+    uint8_t* slot = a.tmp + (size_t)chunk * a.chunk_cap;
+    if (!s_slow) {
+        for (int gi = 0; gi < nvalid; ++gi) {
+            const uint8_t* sb = (const uint8_t*)(sStage + gi * L.stageW);
+            uint8_t* dst = slot + s_boff[gi];
+            for (unsigned j = tid; j < s_blen[gi]; j += FM_THREADS) dst[j] = sb[j];
+        }
+    } else if (tid < nvalid) {
+        const int16_t* c = (const int16_t*)(sCoef + tid * L.coefW);
+        JbByteWriter bw;
+        bw.init(slot + s_boff[tid]);
+        int bad_pos, bad_run;
+        fm_pack_masked(c, sMask + tid * L.maskW, L.maskW, bw, bad_pos, bad_run);
+        bw.finish();
+    }
+}
+
+template <bool DFT, int MODE>
+static cudaError_t fm_launch_t(const JbFwdArgs& a, cudaStream_t s) {
+    const size_t smem = fm_layout(a.g.d, a.g.bs, DFT).total;
+    cudaError_t e = cudaFuncSetAttribute(jb_fwd_mid_kernel<DFT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    jb_fwd_mid_kernel<DFT, MODE><<<a.n_chunks, FM_THREADS, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t jb_launch_fwd_mid(const JbFwdArgs& a, int mode, cudaStream_t s) {
+    if (a.n_chunks == 0) return cudaSuccess;
+    const bool dft = a.g.transform == JB_TRANSFORM_DFT;
+    if (mode == 0) {
+        cudaError_t e = dft ? fm_launch_t<true, 0>(a, s) : fm_launch_t<false, 0>(a, s);
+        if (e != cudaSuccess) return e;
+        return jb_launch_scan_gather(a, s);
+    }
+    return dft ? fm_launch_t<true, 1>(a, s) : fm_launch_t<false, 1>(a, s);
+}

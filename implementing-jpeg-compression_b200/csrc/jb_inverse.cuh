@@ -95,5 +95,8 @@ cudaError_t jb_launch_framing(const JbFrameArgs& f, cudaStream_t s);
 cudaError_t jb_launch_inv_generic(const JbInvArgs& a, int mode, cudaStream_t s);
 size_t jb_inv_generic_smem_bytes(int d, bool dft);
 
+bool jb_inv_mid_eligible(const JbGeom& g);
+cudaError_t jb_launch_inv_mid(const JbInvArgs& a, int mode, cudaStream_t s);
+
 bool jb_inv_fast_eligible(const JbGeom& g);
 cudaError_t jb_launch_inv_fast(const JbInvArgs& a, int mode, cudaStream_t s);

@@ -1,0 +1,227 @@
+// jb_inverse_mid.cu -- decompress direction for "large block" configurations (dct_size a multiple of
+// 4, 8..32; any block_size whose (d*bs)^2 output tile fits shared memory): BASELINE.json config 3.
+// One CTA per chunk of 32 blocks:
+//   * lanes of warp 0 decode one block each (rle_byte_stream.py:74-88, run_length_encoding.py:31-41)
+//     into natural-order int16 rows;
+//   * per block, the whole CTA: dequantise (quantizers.py restore) -> X = B.Y.B^T as two register-tiled
+//     contractions out of shared memory (transforms.py:60-69) -> np.round, clamp (basis_change.py:43,
+//     normalization.py:10-14) -> bs x bs replication into a (d*bs)^2 byte tile in shared memory
+//     (util.inflate) -> 8-byte coalesced row stores, cropped at the plane edges
+//     (dct_padding.py:11-21, padding.py:14-16).
+#include "jb_common.cuh"
+#include "jb_inverse.cuh"
+
+#define IM_THREADS 256
+
+struct ImLayout {
+    int side, pitch, coefW;
+    size_t at, bt, dq, izz, y, p, p2, tile, coef, total;
+};
+
+__host__ __device__ inline ImLayout im_layout(int d, int bs, bool dft) {
+    ImLayout L;
+    const int n = d * d;
+    L.side = d * bs;
+    L.pitch = (L.side + 7) / 8 * 8;
+    L.coefW = ((n + 1) / 2) | 1;
+    size_t o = 0;
+    L.at = o;   o += (size_t)n * 4;
+    L.bt = o;   o += dft ? (size_t)n * 4 : 0;
+    L.dq = o;   o += (size_t)n * 4;
+    L.izz = o;  o += jb_align_up((size_t)n * 2, 16);
+    L.y = o;    o += (size_t)n * 4;
+    L.p = o;    o += (size_t)n * 4;
+    L.p2 = o;   o += dft ? (size_t)n * 4 : 0;
+    L.tile = o; o += jb_align_up((size_t)L.side * L.pitch, 16);
+    L.coef = o; o += (size_t)JB_CHUNK * L.coefW * 4;
+    L.total = o;
+    return L;
+}
+
+bool jb_inv_mid_eligible(const JbGeom& g) {
+    if (g.d < 8 || g.d % 4 != 0 || g.d > JB_MAX_DCT_SIZE) return false;
+    return im_layout(g.d, g.bs, g.transform == JB_TRANSFORM_DFT).total <= 200 * 1024;
+}
+
+// word-based block decoder over global memory (same logic as fi_decode_block, any n)
+__device__ __forceinline__ int im_decode_block(const uint8_t* stream, uint32_t start, uint32_t len, int n,
+                                               int16_t* row, const uint16_t* izz) {
+    const uintptr_t a0 = (uintptr_t)(stream + start);
+    const uint32_t mis = (uint32_t)(a0 & 3);
+    const uint32_t* words = (const uint32_t*)(a0 - mis);
+    const uint32_t nwords = (len - start + mis + 3u) >> 2;
+    const uint32_t bitlimit = (len - start + mis) * 8u;
+    uint32_t widx = 0, used = mis * 8u;
+    auto ld = [&](uint32_t i) -> uint32_t { return i < nwords ? jb_bswap32(__ldg(words + i)) : 0u; };
+    uint64_t buf = ld(widx++);
+    int nb = 32 - (int)used;
+    int count = 0;
+    for (;;) {
+        if (nb < 23) { buf = (buf << 32) | ld(widx++); nb += 32; }
+        const uint32_t head = (uint32_t)(buf >> (nb - 8)) & 0xFFu;
+        const uint32_t run = head >> 4, size = head & 15u;
+        if (size == 0u) {
+            nb -= 8; used += 8;
+            if (run == 0u) return used > bitlimit ? 1 : 0;
+            if (run != (uint32_t)JB_MAX_RUN) return 1;
+            count += JB_MAX_RUN;
+            if (count > n || used > bitlimit) return 1;
+            continue;
+        }
+        if (size == 1u) return 1;
+        count += (int)run;
+        if (count >= n) return 1;
+        const uint32_t raw = (uint32_t)(buf >> (nb - 8 - (int)size)) & ((1u << size) - 1u);
+        nb -= 8 + (int)size; used += 8u + size;
+        if (used > bitlimit) return 1;
+        const int mag = (int)(raw & ((1u << (size - 1)) - 1u));
+        row[izz[count]] = (int16_t)((raw >> (size - 1)) ? mag : -mag);
+        ++count;
+    }
+}
+
+template <bool DFT, int MODE>
+__global__ void __launch_bounds__(IM_THREADS)
+jb_inv_mid_kernel(const JbInvArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const JbGeom& g = a.g;
+    const int d = g.d, n = g.n, bs = g.bs, q4 = d >> 2;
+    const ImLayout L = im_layout(d, bs, DFT);
+    float* sAt = (float*)(smem + L.at);          // At[k][s] = iA[s][k]  (s = sample, k = frequency)
+    float* sBt = (float*)(smem + L.bt);
+    float* sDq = (float*)(smem + L.dq);
+    uint16_t* sIzz = (uint16_t*)(smem + L.izz);
+    float* sY = (float*)(smem + L.y);
+    float* sP = (float*)(smem + L.p);
+    float* sP2 = (float*)(smem + L.p2);
+    uint8_t* sTile = smem + L.tile;
+    uint32_t* sCoef = (uint32_t*)(smem + L.coef);
+
+    const int tid = threadIdx.x;
+    const unsigned chunk = blockIdx.x;
+    if (chunk >= a.n_chunks) return;
+    const int plane = chunk / g.cpp;
+    const int blk0 = (chunk % g.cpp) * JB_CHUNK;
+    const int nvalid = jb_min(JB_CHUNK, g.nblocks - blk0);
+
+    for (int idx = tid; idx < n; idx += IM_THREADS) {
+        const int s = idx / d, k = idx - s * d;
+        sAt[k * d + s] = a.t.iA[idx];
+        if (DFT) sBt[k * d + s] = a.t.iB[idx];
+        sDq[idx] = a.t.dqmult[idx];
+        sIzz[idx] = a.t.izz[idx];
+    }
+    for (int i = tid; i < JB_CHUNK * L.coefW; i += IM_THREADS) sCoef[i] = 0u;
+    __syncthreads();
+
+    if (MODE == 2) {
+        for (int idx = tid; idx < nvalid * n; idx += IM_THREADS) {
+            const int gi = idx / n, zp = idx - gi * n;
+            ((int16_t*)(sCoef + gi * L.coefW))[sIzz[zp]] = a.coeffs_in[((size_t)plane * g.nblocks + blk0 + gi) * n + zp];
+        }
+    } else if (tid < nvalid) {
+        const unsigned long long len = a.plane_len[plane];
+        const unsigned start = a.block_start[(size_t)plane * g.nblocks + blk0 + tid];
+        int rc = 1;
+        if (len <= 0xFFFFFFFFull && start < (unsigned)len)
+            rc = im_decode_block(a.in + a.plane_off[plane], start, (unsigned)len, n,
+                                 (int16_t*)(sCoef + tid * L.coefW), sIzz);
+        if (rc) jb_set_error(a.status, JB_ERR_BAD_STREAM);
+    }
+    __syncthreads();
+
+    uint8_t* dst = a.planes_out + (size_t)plane * a.plane_stride;
+    const int side = L.side, pitch = L.pitch;
+    const bool vec_ok = (side % 8 == 0) && (((uintptr_t)dst & 7) == 0) && (a.row_pitch % 8 == 0);
+    const int ci = tid / q4, cq = tid - ci * q4;
+    const bool c_live = ci < d;
+
+    for (int gi = 0; gi < nvalid; ++gi) {
+        const int blk = blk0 + gi;
+        const int by = blk / g.hb, bx = blk - by * g.hb;
+        // dequantise: integer coefficient * quantiser step (exact in fp32)
+        {
+            const int16_t* row = (const int16_t*)(sCoef + gi * L.coefW);
+            for (int idx = tid; idx < n; idx += IM_THREADS) sY[idx] = (float)row[idx] * sDq[idx];
+        }
+        __syncthreads();
+        // P[u][c] = sum_v Y[u][v] iA[c][v]: thread (u, group of 4 c)
+        if (c_live) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), acc2 = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float* yr = sY + ci * d;
+            for (int v = 0; v < d; ++v) {
+                const float y = yr[v];
+                const float4 c4 = *(const float4*)(sAt + v * d + 4 * cq);
+                acc.x = fmaf(y, c4.x, acc.x); acc.y = fmaf(y, c4.y, acc.y);
+                acc.z = fmaf(y, c4.z, acc.z); acc.w = fmaf(y, c4.w, acc.w);
+                if (DFT) {
+                    const float4 s4 = *(const float4*)(sBt + v * d + 4 * cq);
+                    acc2.x = fmaf(y, s4.x, acc2.x); acc2.y = fmaf(y, s4.y, acc2.y);
+                    acc2.z = fmaf(y, s4.z, acc2.z); acc2.w = fmaf(y, s4.w, acc2.w);
+                }
+            }
+            *(float4*)(sP + ci * d + 4 * cq) = acc;
+            if (DFT) *(float4*)(sP2 + ci * d + 4 * cq) = acc2;
+        }
+        __syncthreads();
+        // X[r][c] = sum_u iA[r][u] P[u][c] (- iB[r][u] P2[u][c]): thread (c, group of 4 r) -> pixels
+        if (c_live) {
+            const int c = ci;
+            float x4[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int u = 0; u < d; ++u) {
+                const float p = sP[u * d + c];
+                const float4 c4 = *(const float4*)(sAt + u * d + 4 * cq);
+                x4[0] = fmaf(c4.x, p, x4[0]); x4[1] = fmaf(c4.y, p, x4[1]);
+                x4[2] = fmaf(c4.z, p, x4[2]); x4[3] = fmaf(c4.w, p, x4[3]);
+                if (DFT) {
+                    const float p2 = sP2[u * d + c];
+                    const float4 s4 = *(const float4*)(sBt + u * d + 4 * cq);
+                    x4[0] = fmaf(-s4.x, p2, x4[0]); x4[1] = fmaf(-s4.y, p2, x4[1]);
+                    x4[2] = fmaf(-s4.z, p2, x4[2]); x4[3] = fmaf(-s4.w, p2, x4[3]);
+                }
+            }
+            #pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float xr = fminf(fmaxf(rintf(x4[k]), 0.f), 255.f);
+                const uint8_t pix = (uint8_t)xr;
+                uint8_t* t0 = sTile + (size_t)(4 * cq + k) * bs * pitch + c * bs;
+                for (int di = 0; di < bs; ++di)
+                    for (int dj = 0; dj < bs; ++dj) t0[di * pitch + dj] = pix;
+            }
+        }
+        __syncthreads();
+        // tile -> plane, cropped to the subsampled extent and to the plane
+        const int y0 = by * side, x0 = bx * side;
+        const int rows = jb_min(side, jb_min(g.H, g.H1 * bs) - y0), cols = jb_min(side, jb_min(g.W, g.W1 * bs) - x0);
+        if (rows == side && cols == side && vec_ok) {
+            const int w8 = side >> 3;
+            uint8_t* base = dst + (size_t)y0 * a.row_pitch + x0;
+            for (int idx = tid; idx < side * w8; idx += IM_THREADS) {
+                const int r = idx / w8, c = idx - r * w8;
+                *((uint2*)(base + (size_t)r * a.row_pitch) + c) = *(const uint2*)(sTile + r * pitch + c * 8);
+            }
+        } else if (rows > 0 && cols > 0) {
+            for (int idx = tid; idx < rows * cols; idx += IM_THREADS) {
+                const int r = idx / cols, c = idx - r * cols;
+                dst[(size_t)(y0 + r) * a.row_pitch + x0 + c] = sTile[r * pitch + c];
+            }
+        }
+        // the next iteration's first barrier separates these tile reads from the next tile writes
+    }
+}
+
+template <bool DFT, int MODE>
+static cudaError_t im_launch_t(const JbInvArgs& a, cudaStream_t s) {
+    const size_t smem = im_layout(a.g.d, a.g.bs, DFT).total;
+    cudaError_t e = cudaFuncSetAttribute(jb_inv_mid_kernel<DFT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    jb_inv_mid_kernel<DFT, MODE><<<a.n_chunks, IM_THREADS, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t jb_launch_inv_mid(const JbInvArgs& a, int mode, cudaStream_t s) {
+    if (a.n_chunks == 0) return cudaSuccess;
+    const bool dft = a.g.transform == JB_TRANSFORM_DFT;
+    if (mode == 0) return dft ? im_launch_t<true, 0>(a, s) : im_launch_t<false, 0>(a, s);
+    return dft ? im_launch_t<true, 2>(a, s) : im_launch_t<false, 2>(a, s);
+}
