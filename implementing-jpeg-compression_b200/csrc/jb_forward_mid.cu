@@ -47,7 +47,7 @@ __host__ __device__ inline FmLayout fm_layout(int d, int bs, bool dft) {
     L.qm = o;    o += (size_t)n * 4;
     L.qt = o;    o += (size_t)n * 4;
     L.zz = o;    o += jb_align_up((size_t)n * 2, 16);
-    L.tile = o;  o += jb_align_up((size_t)L.side * L.pitch, 16);
+    L.tile = o;  o += 2 * jb_align_up((size_t)L.side * L.pitch, 16);      // double buffered
     L.hsum = o;  o += jb_align_up((size_t)L.side * d * 2, 16);
     L.x = o;     o += (size_t)n * 4;
     L.t = o;     o += (size_t)n * 4;
@@ -154,31 +154,43 @@ jb_fwd_mid_kernel(const JbFwdArgs a) {
     const int ci = tid / q4, cq = tid - ci * q4;
     const bool c_live = ci < d;
 
-    for (int gi = 0; gi < nvalid; ++gi) {
+    // ---- 1. source tile -> shared memory, one block ahead of the arithmetic (cp.async) ----
+    const size_t tile_bytes = jb_align_up((size_t)side * pitch, 16);
+    auto stage_tile = [&](int gi, uint8_t* buf) {
         const int blk = blk0 + gi;
         const int by = blk / g.hb, bx = blk - by * g.hb;
-        // ---- 1. source tile -> shared memory ----
         const bool interior = (by + 1) * side <= g.H && (bx + 1) * side <= g.W;
         if (interior && vec_ok) {
             const int w8 = side >> 3;
             const uint8_t* base = src + (size_t)by * side * a.row_pitch + (size_t)bx * side;
             for (int idx = tid; idx < side * w8; idx += FM_THREADS) {
                 const int r = idx / w8, c = idx - r * w8;
-                *(uint2*)(sTile + r * pitch + c * 8) = __ldg((const uint2*)(base + (size_t)r * a.row_pitch) + c);
+                const unsigned sdst = (unsigned)__cvta_generic_to_shared(buf + r * pitch + c * 8);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;"
+                             :: "r"(sdst), "l"(base + (size_t)r * a.row_pitch + (size_t)c * 8) : "memory");
             }
         } else {
             for (int idx = tid; idx < side * side; idx += FM_THREADS) {
                 const int r = idx / side, c = idx - r * side;
                 const int si = jb_min(by * d + r / bs, g.H1 - 1), sj = jb_min(bx * d + c / bs, g.W1 - 1);
                 const int y = jb_min(si * bs + r % bs, g.H - 1), x = jb_min(sj * bs + c % bs, g.W - 1);
-                sTile[r * pitch + c] = src[(size_t)y * a.row_pitch + x];
+                buf[r * pitch + c] = src[(size_t)y * a.row_pitch + x];
             }
         }
-        __syncthreads();
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    stage_tile(0, sTile);
+
+    for (int gi = 0; gi < nvalid; ++gi) {
+        const int blk = blk0 + gi;
+        uint8_t* tile = sTile + (size_t)(gi & 1) * tile_bytes;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                       // tile gi complete; everyone is done with block gi - 1
+        if (gi + 1 < nvalid) stage_tile(gi + 1, sTile + (size_t)((gi + 1) & 1) * tile_bytes);
         // ---- 2a. horizontal sums: lane = column j, warps stride over the tile rows ----
         if (lane < d) {
             for (int r = warp; r < side; r += FM_THREADS / 32) {
-                const uint8_t* p = sTile + r * pitch + lane * bs;
+                const uint8_t* p = tile + r * pitch + lane * bs;
                 int s = 0;
                 for (int k = 0; k < bs; ++k) s += p[k];
                 sH[r * d + lane] = (uint16_t)s;

@@ -5,9 +5,9 @@
 //     into natural-order int16 rows;
 //   * per block, the whole CTA: dequantise (quantizers.py restore) -> X = B.Y.B^T as two register-tiled
 //     contractions out of shared memory (transforms.py:60-69) -> np.round, clamp (basis_change.py:43,
-//     normalization.py:10-14) -> bs x bs replication into a (d*bs)^2 byte tile in shared memory
-//     (util.inflate) -> 8-byte coalesced row stores, cropped at the plane edges
-//     (dct_padding.py:11-21, padding.py:14-16).
+//     normalization.py:10-14) -> d x d samples in shared memory -> bs x bs replication (util.inflate)
+//     as 8-byte row stores, each word built once and written to the bs rows it covers, cropped at
+//     the plane edges (dct_padding.py:11-21, padding.py:14-16).
 #include "jb_common.cuh"
 #include "jb_inverse.cuh"
 
@@ -15,7 +15,7 @@
 
 struct ImLayout {
     int side, pitch, coefW;
-    size_t at, bt, dq, izz, y, p, p2, tile, coef, total;
+    size_t at, bt, dq, izz, y, p, p2, pix, coef, total;
 };
 
 __host__ __device__ inline ImLayout im_layout(int d, int bs, bool dft) {
@@ -32,7 +32,7 @@ __host__ __device__ inline ImLayout im_layout(int d, int bs, bool dft) {
     L.y = o;    o += (size_t)n * 4;
     L.p = o;    o += (size_t)n * 4;
     L.p2 = o;   o += dft ? (size_t)n * 4 : 0;
-    L.tile = o; o += jb_align_up((size_t)L.side * L.pitch, 16);
+    L.pix = o;  o += jb_align_up((size_t)n, 16);
     L.coef = o; o += (size_t)JB_CHUNK * L.coefW * 4;
     L.total = o;
     return L;
@@ -94,7 +94,7 @@ jb_inv_mid_kernel(const JbInvArgs a) {
     float* sY = (float*)(smem + L.y);
     float* sP = (float*)(smem + L.p);
     float* sP2 = (float*)(smem + L.p2);
-    uint8_t* sTile = smem + L.tile;
+    uint8_t* sPix = smem + L.pix;                  // d x d reconstructed samples of the current block
     uint32_t* sCoef = (uint32_t*)(smem + L.coef);
 
     const int tid = threadIdx.x;
@@ -131,7 +131,7 @@ jb_inv_mid_kernel(const JbInvArgs a) {
     __syncthreads();
 
     uint8_t* dst = a.planes_out + (size_t)plane * a.plane_stride;
-    const int side = L.side, pitch = L.pitch;
+    const int side = L.side;
     const bool vec_ok = (side % 8 == 0) && (((uintptr_t)dst & 7) == 0) && (a.row_pitch % 8 == 0);
     const int ci = tid / q4, cq = tid - ci * q4;
     const bool c_live = ci < d;
@@ -181,32 +181,37 @@ jb_inv_mid_kernel(const JbInvArgs a) {
                 }
             }
             #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float xr = fminf(fmaxf(rintf(x4[k]), 0.f), 255.f);
-                const uint8_t pix = (uint8_t)xr;
-                uint8_t* t0 = sTile + (size_t)(4 * cq + k) * bs * pitch + c * bs;
-                for (int di = 0; di < bs; ++di)
-                    for (int dj = 0; dj < bs; ++dj) t0[di * pitch + dj] = pix;
-            }
+            for (int k = 0; k < 4; ++k)
+                sPix[(4 * cq + k) * d + c] = (uint8_t)fminf(fmaxf(rintf(x4[k]), 0.f), 255.f);
         }
         __syncthreads();
-        // tile -> plane, cropped to the subsampled extent and to the plane
+        // bs x bs replication straight to the plane (util.inflate), cropped to the subsampled extent
+        // and to the plane.  Interior blocks: thread (sample row i, 8-byte column word) builds the word
+        // once from the d samples of row i and stores it to the bs plane rows it covers.
         const int y0 = by * side, x0 = bx * side;
         const int rows = jb_min(side, jb_min(g.H, g.H1 * bs) - y0), cols = jb_min(side, jb_min(g.W, g.W1 * bs) - x0);
         if (rows == side && cols == side && vec_ok) {
             const int w8 = side >> 3;
             uint8_t* base = dst + (size_t)y0 * a.row_pitch + x0;
-            for (int idx = tid; idx < side * w8; idx += IM_THREADS) {
-                const int r = idx / w8, c = idx - r * w8;
-                *((uint2*)(base + (size_t)r * a.row_pitch) + c) = *(const uint2*)(sTile + r * pitch + c * 8);
+            for (int idx = tid; idx < d * w8; idx += IM_THREADS) {
+                const int i = idx / w8, c8 = idx - i * w8;
+                const uint8_t* prow = sPix + i * d;
+                uint32_t lo = 0, hi = 0;
+                #pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    lo |= (uint32_t)prow[(8 * c8 + k) / bs] << (8 * k);
+                    hi |= (uint32_t)prow[(8 * c8 + 4 + k) / bs] << (8 * k);
+                }
+                uint8_t* o = base + (size_t)i * bs * a.row_pitch + 8 * c8;
+                for (int di = 0; di < bs; ++di) *(uint2*)(o + (size_t)di * a.row_pitch) = make_uint2(lo, hi);
             }
         } else if (rows > 0 && cols > 0) {
             for (int idx = tid; idx < rows * cols; idx += IM_THREADS) {
                 const int r = idx / cols, c = idx - r * cols;
-                dst[(size_t)(y0 + r) * a.row_pitch + x0 + c] = sTile[r * pitch + c];
+                dst[(size_t)(y0 + r) * a.row_pitch + x0 + c] = sPix[(r / bs) * d + c / bs];
             }
         }
-        // the next iteration's first barrier separates these tile reads from the next tile writes
+        // the next iteration's barriers separate these sPix reads from the next block's sPix writes
     }
 }
 
