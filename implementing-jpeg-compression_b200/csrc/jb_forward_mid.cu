@@ -156,18 +156,21 @@ jb_fwd_mid_kernel(const JbFwdArgs a) {
 
     // ---- 1. source tile -> shared memory, one block ahead of the arithmetic (cp.async) ----
     const size_t tile_bytes = jb_align_up((size_t)side * pitch, 16);
+    const int w8 = jb_min(side >> 3, FM_THREADS) > 0 ? (side >> 3) : 1;
+    const int vr0 = tid / w8, vc0 = tid - vr0 * w8, vdr = FM_THREADS / w8, vdc = FM_THREADS - vdr * w8;
     auto stage_tile = [&](int gi, uint8_t* buf) {
         const int blk = blk0 + gi;
         const int by = blk / g.hb, bx = blk - by * g.hb;
         const bool interior = (by + 1) * side <= g.H && (bx + 1) * side <= g.W;
         if (interior && vec_ok) {
-            const int w8 = side >> 3;
             const uint8_t* base = src + (size_t)by * side * a.row_pitch + (size_t)bx * side;
-            for (int idx = tid; idx < side * w8; idx += FM_THREADS) {
-                const int r = idx / w8, c = idx - r * w8;
+            int r = vr0, c = vc0;                       // (row, 8-byte word) of this thread, stepped without divisions
+            while (r < side) {
                 const unsigned sdst = (unsigned)__cvta_generic_to_shared(buf + r * pitch + c * 8);
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8;"
                              :: "r"(sdst), "l"(base + (size_t)r * a.row_pitch + (size_t)c * 8) : "memory");
+                r += vdr; c += vdc;
+                if (c >= w8) { c -= w8; ++r; }
             }
         } else {
             for (int idx = tid; idx < side * side; idx += FM_THREADS) {

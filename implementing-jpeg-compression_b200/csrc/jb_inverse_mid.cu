@@ -15,7 +15,7 @@
 
 struct ImLayout {
     int side, pitch, coefW;
-    size_t at, bt, dq, izz, y, p, p2, pix, coef, total;
+    size_t at, bt, dq, izz, y, p, p2, pix, lut, coef, total;
 };
 
 __host__ __device__ inline ImLayout im_layout(int d, int bs, bool dft) {
@@ -33,6 +33,7 @@ __host__ __device__ inline ImLayout im_layout(int d, int bs, bool dft) {
     L.p = o;    o += (size_t)n * 4;
     L.p2 = o;   o += dft ? (size_t)n * 4 : 0;
     L.pix = o;  o += jb_align_up((size_t)n, 16);
+    L.lut = o;  o += jb_align_up((size_t)L.side, 16);
     L.coef = o; o += (size_t)JB_CHUNK * L.coefW * 4;
     L.total = o;
     return L;
@@ -95,6 +96,7 @@ jb_inv_mid_kernel(const JbInvArgs a) {
     float* sP = (float*)(smem + L.p);
     float* sP2 = (float*)(smem + L.p2);
     uint8_t* sPix = smem + L.pix;                  // d x d reconstructed samples of the current block
+    uint8_t* sLut = smem + L.lut;                  // sLut[x] = x / bs: sample column of tile byte column x
     uint32_t* sCoef = (uint32_t*)(smem + L.coef);
 
     const int tid = threadIdx.x;
@@ -112,6 +114,7 @@ jb_inv_mid_kernel(const JbInvArgs a) {
         sIzz[idx] = a.t.izz[idx];
     }
     for (int i = tid; i < JB_CHUNK * L.coefW; i += IM_THREADS) sCoef[i] = 0u;
+    for (int x = tid; x < L.side; x += IM_THREADS) sLut[x] = (uint8_t)(x / bs);
     __syncthreads();
 
     if (MODE == 2) {
@@ -135,6 +138,8 @@ jb_inv_mid_kernel(const JbInvArgs a) {
     const bool vec_ok = (side % 8 == 0) && (((uintptr_t)dst & 7) == 0) && (a.row_pitch % 8 == 0);
     const int ci = tid / q4, cq = tid - ci * q4;
     const bool c_live = ci < d;
+    const int w8 = (side >> 3) > 0 ? (side >> 3) : 1;
+    const int vr0 = tid / w8, vc0 = tid - vr0 * w8, vdr = IM_THREADS / w8, vdc = IM_THREADS - vdr * w8;
 
     for (int gi = 0; gi < nvalid; ++gi) {
         const int blk = blk0 + gi;
@@ -191,19 +196,19 @@ jb_inv_mid_kernel(const JbInvArgs a) {
         const int y0 = by * side, x0 = bx * side;
         const int rows = jb_min(side, jb_min(g.H, g.H1 * bs) - y0), cols = jb_min(side, jb_min(g.W, g.W1 * bs) - x0);
         if (rows == side && cols == side && vec_ok) {
-            const int w8 = side >> 3;
             uint8_t* base = dst + (size_t)y0 * a.row_pitch + x0;
-            for (int idx = tid; idx < d * w8; idx += IM_THREADS) {
-                const int i = idx / w8, c8 = idx - i * w8;
+            int i = vr0, c8 = vc0;                      // (sample row, 8-byte word), stepped without divisions
+            while (i < d) {
                 const uint8_t* prow = sPix + i * d;
-                uint32_t lo = 0, hi = 0;
-                #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    lo |= (uint32_t)prow[(8 * c8 + k) / bs] << (8 * k);
-                    hi |= (uint32_t)prow[(8 * c8 + 4 + k) / bs] << (8 * k);
-                }
+                const uint2 l = *(const uint2*)(sLut + 8 * c8);
+                const uint32_t lo = (uint32_t)prow[l.x & 255u] | ((uint32_t)prow[(l.x >> 8) & 255u] << 8) |
+                                    ((uint32_t)prow[(l.x >> 16) & 255u] << 16) | ((uint32_t)prow[l.x >> 24] << 24);
+                const uint32_t hi = (uint32_t)prow[l.y & 255u] | ((uint32_t)prow[(l.y >> 8) & 255u] << 8) |
+                                    ((uint32_t)prow[(l.y >> 16) & 255u] << 16) | ((uint32_t)prow[l.y >> 24] << 24);
                 uint8_t* o = base + (size_t)i * bs * a.row_pitch + 8 * c8;
                 for (int di = 0; di < bs; ++di) *(uint2*)(o + (size_t)di * a.row_pitch) = make_uint2(lo, hi);
+                i += vdr; c8 += vdc;
+                if (c8 >= w8) { c8 -= w8; ++i; }
             }
         } else if (rows > 0 && cols > 0) {
             for (int idx = tid; idx < rows * cols; idx += IM_THREADS) {
