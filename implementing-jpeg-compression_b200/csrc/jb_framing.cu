@@ -7,18 +7,20 @@
 //
 //   * every block ends with a 0x00 byte (the EOB's eight zero bits reach the end of a byte and
 //     the padding is zero), so a block can only start at offset 0 or right after a 0x00 byte;
-//   * each stream is cut into tiles of T bytes (T a power of two >= the longest possible
-//     block).  WALK: one thread per tile starts at the first such offset in its tile and
-//     follows block extents to the tile end, recording every start it visits and where it
-//     leaves the tile.  The walk of tile 0 starts at offset 0, which is a true block start;
-//     a walk that starts on a false offset re-synchronises with the true chain within a
-//     block or two (it lands after a 0x00 byte, and nearly all of those are true ends);
-//   * LINK: one thread per tile takes the exit of the previous tile's walk as its entry E.
-//     If E is among the starts the walk visited, everything from there on is true; if not,
-//     the thread follows the chain from E until it meets the walk (a few blocks).  Either way
-//     the tile's true exit equals its walk's exit, so by induction from tile 0 every entry is
-//     true -- and all tiles are linked in parallel.  A tile whose entry never meets the walk
-//     marks its stream for the serial fallback;
+//   * each stream is cut into tiles of T = 256 bytes.  WALK: one thread per tile starts at the first
+//     such offset in its tile and follows block extents to the tile end, recording every start it
+//     visits and where it leaves the tile (its exit; a long block may carry it over several tiles).
+//     The walk of tile 0 starts at offset 0, which is a true block start; a walk that starts on a
+//     false offset re-synchronises with the true chain within a block or two (it lands after a 0x00
+//     byte, and nearly all of those are true ends);
+//   * REACH: the tiles in which a true block starts form a chain: tile 0, then the tile holding the
+//     exit of tile 0's walk, and so on.  Per stream that chain is marked by pointer doubling over the
+//     "tile of my exit" links, and every tile on it receives its entry E = the exit of its predecessor;
+//   * LINK: one thread per tile on the chain checks E against its own walk: if E is among the starts
+//     the walk visited, everything from there on is true; if not, the thread follows the chain from
+//     E until it meets the walk (a few blocks).  Either way the tile's true exit equals its walk's
+//     exit, so by induction from tile 0 every entry is true -- and all tiles are linked in parallel.
+//     A tile whose entry never meets the walk marks its stream for the serial fallback;
 //   * SCAN: per stream, an exclusive scan of the per-tile block counts gives each tile the
 //     ordinal of its first block; EMIT writes block_start[ordinal] = offset;
 //   * SERIAL: a stream that failed any check is walked once by a single thread (correct for
@@ -291,7 +293,61 @@ __global__ void __launch_bounds__(JB_WALK_THREADS) jb_frame_walk_smem_kernel(JbF
     jb_walk_tile(w, f, tile, tstart, tend);
 }
 
-// ---- F2a: link each tile to the walk of the tile before it -----------------------------------------
+// ---- F2: chain of tiles per stream (pointer doubling over "tile of my exit") -----------------------
+// CAP = tiles of one stream this instantiation handles in shared memory; longer streams are left to
+// the larger instantiation (or, beyond that, to the serial fallback).
+template <unsigned CAP, unsigned MIN_TILES>
+__global__ void __launch_bounds__(JB_FRAME_THREADS) jb_frame_reach_kernel(JbFrameArgs f) {
+    extern __shared__ __align__(16) unsigned char reach_smem[];
+    uint16_t* J[2] = {(uint16_t*)reach_smem, (uint16_t*)reach_smem + CAP};
+    uint8_t* R = (uint8_t*)(reach_smem + 4 * (size_t)CAP);
+    const int s = blockIdx.x, tid = threadIdx.x;
+    if (f.tile_first[f.n_planes] == 0) return;
+    const unsigned t0 = f.tile_first[s];
+    const unsigned nt = f.tile_first[s + 1] - t0;
+    if (nt < MIN_TILES) return;                              // the smaller instantiation took it
+    if (nt > CAP) { if (CAP >= 40000u && tid == 0) f.fallback[s] = 1u; return; }
+    if (nt == 0) { if (tid == 0) f.fallback[s] = 1u; return; }
+    const uint32_t len = (uint32_t)f.plane_len[s];
+    const unsigned T = f.tile_bytes;
+    for (unsigned t = tid; t < nt; t += JB_FRAME_THREADS) {
+        const uint32_t ex = f.tile_exit[t0 + t];
+        uint16_t nx = 0xFFFFu;
+        if (ex != JB_POS_INVALID && ex < len) { const unsigned k = ex / T; if (k > t && k < nt) nx = (uint16_t)k; }
+        J[0][t] = nx;
+        R[t] = t == 0 ? 1 : 0;
+        f.tile_entry[t0 + t] = t == 0 ? 0u : JB_POS_INVALID;
+    }
+    __syncthreads();
+    int cur = 0;
+    for (unsigned span = 1; span < nt; span <<= 1) {
+        for (unsigned t = tid; t < nt; t += JB_FRAME_THREADS) {
+            const uint16_t j = J[cur][t];
+            if (j != 0xFFFFu) {
+                if (R[t]) R[j] = 1;                          // marks only tiles that are on the chain
+                J[cur ^ 1][t] = J[cur][j];
+            } else {
+                J[cur ^ 1][t] = 0xFFFFu;
+            }
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
+    // entries of the tiles on the chain, and the end of the chain
+    int bad = 0, ends = 0;
+    for (unsigned t = tid; t < nt; t += JB_FRAME_THREADS) {
+        if (!R[t]) continue;
+        const uint32_t ex = f.tile_exit[t0 + t];
+        if (ex == len) ++ends;
+        else if (ex == JB_POS_INVALID || ex > len || ex / T <= t || ex / T >= nt) bad = 1;
+        else f.tile_entry[t0 + ex / T] = ex;
+    }
+    bad = __syncthreads_or(bad);
+    const int total_ends = __syncthreads_count(ends);
+    if (tid == 0 && (bad || total_ends != 1)) f.fallback[s] = 1u;
+}
+
+// ---- F2a: link each tile on the chain to its entry -----------------------------------------
 __global__ void __launch_bounds__(JB_FRAME_THREADS) jb_frame_link_kernel(JbFrameArgs f) {
     const unsigned tile = blockIdx.x * JB_FRAME_THREADS + threadIdx.x;
     if (tile >= f.tile_first[f.n_planes]) return;
@@ -304,14 +360,13 @@ __global__ void __launch_bounds__(JB_FRAME_THREADS) jb_frame_link_kernel(JbFrame
     const unsigned n = f.tile_n[tile];
     const uint32_t my_exit = f.tile_exit[tile];
 
-    const uint32_t E = (t == 0) ? 0u : f.tile_exit[tile - 1];
+    const uint32_t E = f.tile_entry[tile];                  // JB_POS_INVALID: no true block starts here
     unsigned from = n, npriv = 0, hops = 0;
-    bool ok = (E != JB_POS_INVALID) && E >= tstart;
-    if (ok && E >= tend) {
-        // nothing starts in this tile: only legitimate as the tail of the stream's last block
-        // (whatever the walk of this tile found started on a false offset)
-        ok = (E == len) && (tend == len);
-    } else if (ok && my_exit == JB_POS_INVALID) {
+    (void)t;
+    bool ok = true;
+    if (E == JB_POS_INVALID) {
+        // not on the chain of tiles: a block that started earlier covers this tile
+    } else if (E < tstart || E >= tend || my_exit == JB_POS_INVALID) {
         ok = false;
     } else if (ok) {
         const uint32_t rel = E - tstart;
@@ -339,7 +394,6 @@ __global__ void __launch_bounds__(JB_FRAME_THREADS) jb_frame_link_kernel(JbFrame
         hops = npriv + (n - from);
     }
     if (!ok) { f.fallback[s] = 1u; hops = 0; from = n; npriv = 0; }
-    f.tile_entry[tile] = E;
     f.tile_from[tile] = from;
     f.tile_npriv[tile] = npriv;
     f.tile_hops[tile] = hops;
@@ -363,13 +417,8 @@ __global__ void __launch_bounds__(JB_FRAME_THREADS) jb_frame_scan_kernel(JbFrame
         carry += total;
     }
     if (tid == 0) {
-        // the chain must end exactly at the stream end: either the last tile's walk exits there,
-        // or the last tile holds only the tail of a block (its entry is the stream end)
-        bool good = nt > 0 && f.fallback[s] == 0u && carry == (unsigned)f.nblocks;
-        if (good) {
-            const uint32_t e_last = f.tile_entry[t0 + nt - 1];
-            good = (e_last >= len) ? (e_last == len) : (f.tile_exit[t0 + nt - 1] == len);
-        }
+        // (that the chain of tiles ends exactly at the stream end was checked by jb_frame_reach_kernel)
+        const bool good = nt > 0 && f.fallback[s] == 0u && carry == (unsigned)f.nblocks;
         if (!good) {
             f.fallback[s] = 1u;
             atomicAdd(f.status + 2, 1ull);        // status[2]: streams that took the serial walk
@@ -437,6 +486,13 @@ cudaError_t jb_launch_framing(const JbFrameArgs& f, cudaStream_t s) {
         jb_frame_walk_smem_kernel<<<wgrid, JB_WALK_THREADS, smem, s>>>(f, stride_words);
     } else {
         jb_frame_walk_kernel<<<wgrid, JB_WALK_THREADS, 0, s>>>(f);
+    }
+    {   // chain of tiles: streams of up to 4096 tiles (1 MB) in 20 KB of shared memory, longer ones in 200 KB
+        const size_t sm_small = 5 * 4096, sm_big = 5 * 40000;
+        jb_frame_reach_kernel<4096, 0><<<f.n_planes, JB_FRAME_THREADS, sm_small, s>>>(f);
+        e = cudaFuncSetAttribute(jb_frame_reach_kernel<40000, 4097>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_big);
+        if (e != cudaSuccess) return e;
+        jb_frame_reach_kernel<40000, 4097><<<f.n_planes, JB_FRAME_THREADS, sm_big, s>>>(f);
     }
     jb_frame_link_kernel<<<grid, JB_FRAME_THREADS, 0, s>>>(f);
     jb_frame_scan_kernel<<<f.n_planes, JB_FRAME_THREADS, 0, s>>>(f);

@@ -5,11 +5,11 @@
 #define JB_FRAME_THREADS 256
 #define JB_INV_GENERIC_THREADS 256
 
-// Walk tile: a power of two >= the longest possible block, at least 256 bytes.
+// Walk tile (bytes of stream per walking thread).  Blocks may be longer than a tile: tiles that a
+// block spans entirely are simply not on the chain of tiles (jb_frame_reach_kernel).
 static inline unsigned jb_frame_tile_bytes(int d) {
-    unsigned need = (unsigned)jb_max_block_bytes(d * d), t = 256;
-    while (t < need) t <<= 1;
-    return t;
+    (void)d;
+    return 256;
 }
 
 // Workspace of the decoder behind the tables (all offsets 256-byte aligned).
