@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(JB_WALK_THREADS) jb_frame_walk_smem_kernel(JbF
     extern __shared__ uint32_t s_words[];
     const int lane = threadIdx.x & 31;
     const unsigned total_tiles = f.tile_first[f.n_planes];
-    const unsigned tile = blockIdx.x * JB_WALK_THREADS + threadIdx.x;
+    const unsigned tile = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = tile < total_tiles;
     uint32_t len = 0, tstart = 0, tend = 0, first = 0, mis = 0, nw = 0, gnw = 0;
     unsigned long long abase = 0;                   // aligned global address of the window
@@ -301,13 +301,14 @@ __global__ void __launch_bounds__(JB_FRAME_THREADS) jb_frame_reach_kernel(JbFram
     extern __shared__ __align__(16) unsigned char reach_smem[];
     uint16_t* J[2] = {(uint16_t*)reach_smem, (uint16_t*)reach_smem + CAP};
     uint8_t* R = (uint8_t*)(reach_smem + 4 * (size_t)CAP);
-    const int s = blockIdx.x, tid = threadIdx.x;
+    const int tid = threadIdx.x;
     if (f.tile_first[f.n_planes] == 0) return;
+    for (int s = blockIdx.x; s < f.n_planes; s += gridDim.x) {
     const unsigned t0 = f.tile_first[s];
     const unsigned nt = f.tile_first[s + 1] - t0;
-    if (nt < MIN_TILES) return;                              // the smaller instantiation took it
-    if (nt > CAP) { if (CAP >= 40000u && tid == 0) f.fallback[s] = 1u; return; }
-    if (nt == 0) { if (tid == 0) f.fallback[s] = 1u; return; }
+    if (nt < MIN_TILES) continue;                            // the smaller instantiation took it
+    if (nt > CAP) { if (CAP >= 40000u && tid == 0) f.fallback[s] = 1u; continue; }
+    if (nt == 0) { if (tid == 0) f.fallback[s] = 1u; continue; }
     const uint32_t len = (uint32_t)f.plane_len[s];
     const unsigned T = f.tile_bytes;
     for (unsigned t = tid; t < nt; t += JB_FRAME_THREADS) {
@@ -345,6 +346,8 @@ __global__ void __launch_bounds__(JB_FRAME_THREADS) jb_frame_reach_kernel(JbFram
     bad = __syncthreads_or(bad);
     const int total_ends = __syncthreads_count(ends);
     if (tid == 0 && (bad || total_ends != 1)) f.fallback[s] = 1u;
+    __syncthreads();
+    }
 }
 
 // ---- F2a: link each tile on the chain to its entry -----------------------------------------
@@ -451,48 +454,72 @@ __global__ void __launch_bounds__(JB_FRAME_THREADS) jb_frame_emit_kernel(JbFrame
     for (unsigned j = from; j < n && idx < (unsigned)f.nblocks; ++j) out[idx++] = tstart + V[j];
 }
 
-// ---- F4: serial fallback, one thread per marked stream --------------------------------------------------
+// ---- F4: serial fallback, one warp per marked stream ------------------------------------------------------
+// The warp stages the stream through shared memory 4 KB at a time (coalesced); lane 0 walks it.
+#define JB_SERIAL_WORDS 1024
 __global__ void __launch_bounds__(32) jb_frame_serial_kernel(JbFrameArgs f) {
-    const int s = blockIdx.x;
-    if (threadIdx.x != 0 || f.fallback[s] == 0u) return;
+    __shared__ uint32_t sw[JB_SERIAL_WORDS + 8];
+    const int s = blockIdx.x, lane = threadIdx.x;
+    if (f.fallback[s] == 0u) return;
     const uint32_t len = (uint32_t)f.plane_len[s];
+    const uint8_t* stream = f.in + f.plane_off[s];
     unsigned* out = f.block_start + (size_t)s * f.nblocks;
-    JbWalker w;
-    w.init(f.in + f.plane_off[s], len);
-    w.seek(0);
     const uint32_t maxblk_bits = (uint32_t)f.maxblk * 8u;
+    uint32_t pos = 0;
     unsigned k = 0;
-    bool ok = len > 0 && f.tile_first[f.n_planes] != 0;
-    while (ok && (w.bp >> 3) < len) {
-        if (k >= (unsigned)f.nblocks) { ok = false; break; }
-        out[k++] = w.bp >> 3;
-        ok = w.block(f.n, maxblk_bits);
+    int ok = (len > 0 && f.tile_first[f.n_planes] != 0) ? 1 : 0;
+    while (ok && pos < len) {
+        const unsigned long long a0 = (unsigned long long)(uintptr_t)(stream + pos);
+        const uint32_t mis = (uint32_t)(a0 & 3ull);
+        const uint32_t* g = (const uint32_t*)(uintptr_t)(a0 - mis);
+        const uint32_t gnw = (len - pos + mis + 3u) >> 2;
+        const uint32_t nw = gnw < JB_SERIAL_WORDS ? gnw : JB_SERIAL_WORDS;
+        for (uint32_t i = lane; i < nw; i += 32) sw[i] = __ldg(g + i);
+        __syncwarp();
+        if (lane == 0) {
+            JbWalker w;
+            w.init_window(sw, nw, g, gnw, pos, mis, len);
+            w.seek(pos);
+            const uint32_t stop = pos + (JB_SERIAL_WORDS - 64) * 4u;       // blocks that start before this
+            while (ok && (w.bp >> 3) < len && (w.bp >> 3) < stop) {
+                if (k >= (unsigned)f.nblocks) { ok = 0; break; }
+                out[k++] = w.bp >> 3;
+                ok = w.block(f.n, maxblk_bits) ? 1 : 0;
+            }
+            pos = w.bp >> 3;
+        }
+        pos = __shfl_sync(0xffffffffu, pos, 0);
+        ok = __shfl_sync(0xffffffffu, ok, 0);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        __syncwarp();
     }
-    if (!ok || k != (unsigned)f.nblocks) jb_set_error(f.status, JB_ERR_BAD_STREAM);
+    if (lane == 0 && (!ok || k != (unsigned)f.nblocks)) jb_set_error(f.status, JB_ERR_BAD_STREAM);
 }
 
 cudaError_t jb_launch_framing(const JbFrameArgs& f, cudaStream_t s) {
     cudaError_t e;
     const unsigned grid = (f.max_tiles + JB_FRAME_THREADS - 1) / JB_FRAME_THREADS;
-    const unsigned wgrid = (f.max_tiles + JB_WALK_THREADS - 1) / JB_WALK_THREADS;
     jb_frame_prep_kernel<<<1, 1024, 0, s>>>(f);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    // staged window of one walk: 1 byte before the tile + tile + JB_WALK_HALO + slack, in words, odd stride
+    // staged window of one walk: 1 byte before the tile + tile + JB_WALK_HALO + slack, in words, odd stride;
+    // as many threads per block (a multiple of 32, at most JB_WALK_THREADS) as fit ~56 KB of shared memory
     const unsigned stride_words = (((unsigned)f.tile_bytes + JB_WALK_HALO + 16u) / 4u) | 1u;
-    const size_t smem = (size_t)JB_WALK_THREADS * stride_words * 4;
-    if (smem <= 64 * 1024) {
+    unsigned wthreads = (56u * 1024u / (stride_words * 4u)) / 32u * 32u;
+    if (wthreads > JB_WALK_THREADS) wthreads = JB_WALK_THREADS;
+    if (wthreads >= 32) {
+        const size_t smem = (size_t)wthreads * stride_words * 4;
         e = cudaFuncSetAttribute(jb_frame_walk_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        jb_frame_walk_smem_kernel<<<wgrid, JB_WALK_THREADS, smem, s>>>(f, stride_words);
+        jb_frame_walk_smem_kernel<<<(f.max_tiles + wthreads - 1) / wthreads, wthreads, smem, s>>>(f, stride_words);
     } else {
-        jb_frame_walk_kernel<<<wgrid, JB_WALK_THREADS, 0, s>>>(f);
+        jb_frame_walk_kernel<<<(f.max_tiles + JB_WALK_THREADS - 1) / JB_WALK_THREADS, JB_WALK_THREADS, 0, s>>>(f);
     }
     {   // chain of tiles: streams of up to 4096 tiles (1 MB) in 20 KB of shared memory, longer ones in 200 KB
         const size_t sm_small = 5 * 4096, sm_big = 5 * 40000;
         jb_frame_reach_kernel<4096, 0><<<f.n_planes, JB_FRAME_THREADS, sm_small, s>>>(f);
         e = cudaFuncSetAttribute(jb_frame_reach_kernel<40000, 4097>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_big);
         if (e != cudaSuccess) return e;
-        jb_frame_reach_kernel<40000, 4097><<<f.n_planes, JB_FRAME_THREADS, sm_big, s>>>(f);
+        jb_frame_reach_kernel<40000, 4097><<<f.n_planes < 32 ? f.n_planes : 32, JB_FRAME_THREADS, sm_big, s>>>(f);
     }
     jb_frame_link_kernel<<<grid, JB_FRAME_THREADS, 0, s>>>(f);
     jb_frame_scan_kernel<<<f.n_planes, JB_FRAME_THREADS, 0, s>>>(f);

@@ -5,11 +5,16 @@
 #define JB_FRAME_THREADS 256
 #define JB_INV_GENERIC_THREADS 256
 
-// Walk tile (bytes of stream per walking thread).  Blocks may be longer than a tile: tiles that a
-// block spans entirely are simply not on the chain of tiles (jb_frame_reach_kernel).
-static inline unsigned jb_frame_tile_bytes(int d) {
-    (void)d;
-    return 256;
+// Walk tile (bytes of stream per walking thread): about twelve average blocks, so that a walk which
+// starts on a false offset has re-joined the true chain well before its tile ends (a walk that has
+// not sends its whole stream to the serial fallback).  Blocks may be longer than a tile: tiles that
+// a block spans entirely are simply not on the chain of tiles (jb_frame_reach_kernel).
+static inline unsigned jb_frame_tile_bytes(size_t in_bytes, int n_planes, long long nblocks_per_plane) {
+    const double blocks = (double)n_planes * (double)nblocks_per_plane;
+    const double avg = blocks > 0 ? (double)in_bytes / blocks : 16.0;
+    unsigned t = 256;
+    while (t < 4096 && (double)t < 12.0 * avg) t <<= 1;
+    return t;
 }
 
 // Workspace of the decoder behind the tables (all offsets 256-byte aligned).
@@ -34,7 +39,8 @@ static inline JbDecLayout jb_dec_layout(int d, int n_planes, long long nblocks_p
                                         size_t table_bytes) {
     JbDecLayout L;
     size_t o = jb_align_up(table_bytes, 256);
-    L.tile_bytes = jb_frame_tile_bytes(d);
+    (void)d;
+    L.tile_bytes = jb_frame_tile_bytes(in_bytes, n_planes, nblocks_per_plane);
     L.max_tiles = (unsigned)(in_bytes / L.tile_bytes + (size_t)n_planes + 1);
     L.tile_first = o;  o += jb_align_up(((size_t)n_planes + 1) * 4, 256);
     L.fallback = o;    o += jb_align_up((size_t)n_planes * 4, 256);
