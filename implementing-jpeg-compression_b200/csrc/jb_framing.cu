@@ -131,10 +131,13 @@ __device__ __forceinline__ int jb_stream_of_tile(const unsigned* tile_first, int
 }
 
 // ---- F0: tiles per stream ----------------------------------------------------------------------
+#define JB_REACH_SMALL_CAP 4096u
 __global__ void __launch_bounds__(1024) jb_frame_prep_kernel(JbFrameArgs f) {
     __shared__ unsigned s_warp[33];
     unsigned carry = 0;
     bool bad = false;
+    if (threadIdx.x == 0) f.big_list[0] = 0u;
+    __syncthreads();
     for (int base = 0; base < f.n_planes; base += 1024) {
         int s = base + threadIdx.x;
         unsigned nt = 0;
@@ -143,6 +146,7 @@ __global__ void __launch_bounds__(1024) jb_frame_prep_kernel(JbFrameArgs f) {
             if (len > 0x1FFFFFF0ull) { bad = true; len = 0; }           // bit positions are 32-bit
             nt = (unsigned)((len + f.tile_bytes - 1) / f.tile_bytes);
             f.fallback[s] = f.force_serial ? 1u : 0u;
+            if (nt > JB_REACH_SMALL_CAP) f.big_list[1 + atomicAdd(f.big_list, 1u)] = (unsigned)s;
         }
         unsigned total;
         unsigned ex = jb_block_excl_scan(nt, s_warp, &total);
@@ -303,7 +307,10 @@ __global__ void __launch_bounds__(JB_FRAME_THREADS) jb_frame_reach_kernel(JbFram
     uint8_t* R = (uint8_t*)(reach_smem + 4 * (size_t)CAP);
     const int tid = threadIdx.x;
     if (f.tile_first[f.n_planes] == 0) return;
-    for (int s = blockIdx.x; s < f.n_planes; s += gridDim.x) {
+    // small instantiation: one CTA per stream; large one: a few CTAs share the list of long streams
+    const unsigned n_work = MIN_TILES ? f.big_list[0] : (unsigned)f.n_planes;
+    for (unsigned wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+    const int s = MIN_TILES ? (int)f.big_list[1 + wi] : (int)wi;
     const unsigned t0 = f.tile_first[s];
     const unsigned nt = f.tile_first[s + 1] - t0;
     if (nt < MIN_TILES) continue;                            // the smaller instantiation took it
@@ -516,10 +523,10 @@ cudaError_t jb_launch_framing(const JbFrameArgs& f, cudaStream_t s) {
     }
     {   // chain of tiles: streams of up to 4096 tiles (1 MB) in 20 KB of shared memory, longer ones in 200 KB
         const size_t sm_small = 5 * 4096, sm_big = 5 * 40000;
-        jb_frame_reach_kernel<4096, 0><<<f.n_planes, JB_FRAME_THREADS, sm_small, s>>>(f);
-        e = cudaFuncSetAttribute(jb_frame_reach_kernel<40000, 4097>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_big);
+        jb_frame_reach_kernel<JB_REACH_SMALL_CAP, 0><<<f.n_planes, JB_FRAME_THREADS, sm_small, s>>>(f);
+        e = cudaFuncSetAttribute(jb_frame_reach_kernel<40000, JB_REACH_SMALL_CAP + 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_big);
         if (e != cudaSuccess) return e;
-        jb_frame_reach_kernel<40000, 4097><<<f.n_planes < 32 ? f.n_planes : 32, JB_FRAME_THREADS, sm_big, s>>>(f);
+        jb_frame_reach_kernel<40000, JB_REACH_SMALL_CAP + 1><<<f.n_planes < 32 ? f.n_planes : 32, JB_FRAME_THREADS, sm_big, s>>>(f);
     }
     jb_frame_link_kernel<<<grid, JB_FRAME_THREADS, 0, s>>>(f);
     jb_frame_scan_kernel<<<f.n_planes, JB_FRAME_THREADS, 0, s>>>(f);

@@ -21,6 +21,7 @@ static inline unsigned jb_frame_tile_bytes(size_t in_bytes, int n_planes, long l
 struct JbDecLayout {
     size_t tile_first;   // uint32 [n_planes + 1]   first tile of each stream; [n_planes] = tile count
     size_t fallback;     // uint32 [n_planes]       stream needs the serial walk
+    size_t big_list;     // uint32 [n_planes + 1]   [0] = count, then the streams with more than 4096 tiles
     size_t block_start;  // uint32 [n_planes * nblocks]  byte offset of every block inside its stream
     size_t tile_n;       // uint32 [max_tiles]  starts recorded by the tile's walk
     size_t tile_exit;    // uint32 [max_tiles]  offset where the walk leaves the tile (or invalid)
@@ -44,6 +45,7 @@ static inline JbDecLayout jb_dec_layout(int d, int n_planes, long long nblocks_p
     L.max_tiles = (unsigned)(in_bytes / L.tile_bytes + (size_t)n_planes + 1);
     L.tile_first = o;  o += jb_align_up(((size_t)n_planes + 1) * 4, 256);
     L.fallback = o;    o += jb_align_up((size_t)n_planes * 4, 256);
+    L.big_list = o;    o += jb_align_up(((size_t)n_planes + 1) * 4, 256);
     L.block_start = o; o += jb_align_up((size_t)n_planes * (size_t)nblocks_per_plane * 4, 256);
     L.tile_n = o;      o += jb_align_up((size_t)L.max_tiles * 4, 256);
     L.tile_exit = o;   o += jb_align_up((size_t)L.max_tiles * 4, 256);
@@ -69,6 +71,7 @@ struct JbFrameArgs {
     int force_serial;      // JB_FLAG_SERIAL_FRAMING: every stream takes the serial walk (test hook)
     unsigned* tile_first;
     unsigned* fallback;
+    unsigned* big_list;
     unsigned* block_start;
     unsigned* tile_n;
     unsigned* tile_exit;
