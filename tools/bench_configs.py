@@ -103,6 +103,9 @@ def run(name, h, w, bs, d, transform, qname, qparam, n_images, steps=10, warmup=
 
 def main():
     out = []
+    if len(sys.argv) > 1 and sys.argv[1] == "config5":
+        run("5: 16384x16384 DFT qtable, single image", 16384, 16384, 4, 8, "DFT", "qtable", None, 1, steps=2, warmup=1)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "config3":
         run("3b: 3840x2160 bs5 d24 divide 1000, batch of 8", 2160, 3840, 5, 24, "DCT", "divide", 1000, 8, steps=2, warmup=1)
         return
