@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(JB_WALK_THREADS) jb_frame_walk_smem_kernel(JbF
 // CAP = tiles of one stream this instantiation handles in shared memory; longer streams are left to
 // the larger instantiation (or, beyond that, to the serial fallback).
 template <unsigned CAP, unsigned MIN_TILES>
-__global__ void __launch_bounds__(JB_FRAME_THREADS) jb_frame_reach_kernel(JbFrameArgs f) {
+__global__ void __launch_bounds__(1024) jb_frame_reach_kernel(JbFrameArgs f) {
     extern __shared__ __align__(16) unsigned char reach_smem[];
     uint16_t* J[2] = {(uint16_t*)reach_smem, (uint16_t*)reach_smem + CAP};
     uint8_t* R = (uint8_t*)(reach_smem + 4 * (size_t)CAP);
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(JB_FRAME_THREADS) jb_frame_reach_kernel(JbFram
     if (nt == 0) { if (tid == 0) f.fallback[s] = 1u; continue; }
     const uint32_t len = (uint32_t)f.plane_len[s];
     const unsigned T = f.tile_bytes;
-    for (unsigned t = tid; t < nt; t += JB_FRAME_THREADS) {
+    for (unsigned t = tid; t < nt; t += blockDim.x) {
         const uint32_t ex = f.tile_exit[t0 + t];
         uint16_t nx = 0xFFFFu;
         if (ex != JB_POS_INVALID && ex < len) { const unsigned k = ex / T; if (k > t && k < nt) nx = (uint16_t)k; }
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(JB_FRAME_THREADS) jb_frame_reach_kernel(JbFram
     __syncthreads();
     int cur = 0;
     for (unsigned span = 1; span < nt; span <<= 1) {
-        for (unsigned t = tid; t < nt; t += JB_FRAME_THREADS) {
+        for (unsigned t = tid; t < nt; t += blockDim.x) {
             const uint16_t j = J[cur][t];
             if (j != 0xFFFFu) {
                 if (R[t]) R[j] = 1;                          // marks only tiles that are on the chain
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(JB_FRAME_THREADS) jb_frame_reach_kernel(JbFram
     }
     // entries of the tiles on the chain, and the end of the chain
     int bad = 0, ends = 0;
-    for (unsigned t = tid; t < nt; t += JB_FRAME_THREADS) {
+    for (unsigned t = tid; t < nt; t += blockDim.x) {
         if (!R[t]) continue;
         const uint32_t ex = f.tile_exit[t0 + t];
         if (ex == len) ++ends;
@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(JB_FRAME_THREADS) jb_frame_link_kernel(JbFrame
 }
 
 // ---- F2b: per stream, ordinals of the tiles' first blocks -------------------------------------------
-__global__ void __launch_bounds__(JB_FRAME_THREADS) jb_frame_scan_kernel(JbFrameArgs f) {
+__global__ void __launch_bounds__(1024) jb_frame_scan_kernel(JbFrameArgs f) {
     __shared__ unsigned s_warp[33];
     const int s = blockIdx.x, tid = threadIdx.x;
     if (f.tile_first[f.n_planes] == 0) return;                // prep failed, error already set
@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(JB_FRAME_THREADS) jb_frame_scan_kernel(JbFrame
     const unsigned nt = f.tile_first[s + 1] - t0;
     const uint32_t len = (uint32_t)f.plane_len[s];
     unsigned carry = 0;
-    for (unsigned b = 0; b < nt; b += JB_FRAME_THREADS) {
+    for (unsigned b = 0; b < nt; b += blockDim.x) {
         const unsigned t = b + tid;
         const unsigned hops = t < nt ? f.tile_hops[t0 + t] : 0u;
         unsigned total;
@@ -526,10 +526,11 @@ cudaError_t jb_launch_framing(const JbFrameArgs& f, cudaStream_t s) {
         jb_frame_reach_kernel<JB_REACH_SMALL_CAP, 0><<<f.n_planes, JB_FRAME_THREADS, sm_small, s>>>(f);
         e = cudaFuncSetAttribute(jb_frame_reach_kernel<40000, JB_REACH_SMALL_CAP + 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_big);
         if (e != cudaSuccess) return e;
-        jb_frame_reach_kernel<40000, JB_REACH_SMALL_CAP + 1><<<f.n_planes < 32 ? f.n_planes : 32, JB_FRAME_THREADS, sm_big, s>>>(f);
+        jb_frame_reach_kernel<40000, JB_REACH_SMALL_CAP + 1><<<f.n_planes < 32 ? f.n_planes : 32, 1024, sm_big, s>>>(f);
     }
     jb_frame_link_kernel<<<grid, JB_FRAME_THREADS, 0, s>>>(f);
-    jb_frame_scan_kernel<<<f.n_planes, JB_FRAME_THREADS, 0, s>>>(f);
+    // a few long streams: wide CTAs; many short streams: narrow ones
+    jb_frame_scan_kernel<<<f.n_planes, (f.max_tiles / (unsigned)f.n_planes > 2048u) ? 1024 : JB_FRAME_THREADS, 0, s>>>(f);
     jb_frame_emit_kernel<<<grid, JB_FRAME_THREADS, 0, s>>>(f);
     jb_frame_serial_kernel<<<f.n_planes, 32, 0, s>>>(f);
     return cudaGetLastError();
