@@ -216,14 +216,13 @@ static int jb_inverse_common(int mode, const uint8_t* d_in, size_t in_bytes, con
         f.fallback = (unsigned*)(ws + L.fallback);
         f.big_list = (unsigned*)(ws + L.big_list);
         f.block_start = (unsigned*)(ws + L.block_start);
-        f.tile_n = (unsigned*)(ws + L.tile_n);
         f.tile_exit = (unsigned*)(ws + L.tile_exit);
         f.tile_entry = (unsigned*)(ws + L.tile_entry);
         f.tile_from = (unsigned*)(ws + L.tile_from);
         f.tile_npriv = (unsigned*)(ws + L.tile_npriv);
         f.tile_hops = (unsigned*)(ws + L.tile_hops);
         f.tile_base = (unsigned*)(ws + L.tile_base);
-        f.visited = (uint16_t*)(ws + L.visited);
+        f.vbits = (uint32_t*)(ws + L.vbits);
         f.status = (unsigned long long*)d_status;
         // a stream that fails framing leaves block_start unwritten: make it deterministic
         JB_CUDA_TRY(cudaMemsetAsync(f.block_start, 0xFF, (size_t)n_planes * g.nblocks * 4, s));

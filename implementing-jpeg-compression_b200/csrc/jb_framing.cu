@@ -7,9 +7,9 @@
 //
 //   * every block ends with a 0x00 byte (the EOB's eight zero bits reach the end of a byte and
 //     the padding is zero), so a block can only start at offset 0 or right after a 0x00 byte;
-//   * each stream is cut into tiles of T = 256 bytes.  WALK: one thread per tile starts at the first
-//     such offset in its tile and follows block extents to the tile end, recording every start it
-//     visits and where it leaves the tile (its exit; a long block may carry it over several tiles).
+//   * each stream is cut into tiles of T bytes (256 for typical content).  WALK: one thread per tile starts
+//     at the first such offset in its tile and follows block extents to the tile end, recording every start
+//     it visits (one bit per byte of the tile) and where it leaves the tile (its exit; a long block may carry it over several tiles).
 //     The walk of tile 0 starts at offset 0, which is a true block start; a walk that starts on a
 //     false offset re-synchronises with the true chain within a block or two (it lands after a 0x00
 //     byte, and nearly all of those are true ends);
@@ -167,19 +167,29 @@ __global__ void __launch_bounds__(1024) jb_frame_prep_kernel(JbFrameArgs f) {
 #define JB_WALK_THREADS 128
 #define JB_WALK_HALO 64           // bytes staged beyond the tile; longer blocks continue from global memory
 
-__device__ __forceinline__ void jb_walk_tile(JbWalker& w, const JbFrameArgs& f, unsigned tile, uint32_t tstart,
-                                             uint32_t tend) {
-    uint16_t* V = f.visited + (size_t)tile * f.tile_bytes;
+// any tile size: every thread reads its tile straight from global memory and keeps its bitmap there
+__global__ void __launch_bounds__(JB_WALK_THREADS) jb_frame_walk_kernel(JbFrameArgs f) {
+    const unsigned tile = blockIdx.x * JB_WALK_THREADS + threadIdx.x;
+    if (tile >= f.tile_first[f.n_planes]) return;
+    const int s = jb_stream_of_tile(f.tile_first, f.n_planes, tile);
+    const uint32_t len = (uint32_t)f.plane_len[s];
+    const uint32_t tstart = (tile - f.tile_first[s]) * f.tile_bytes;
+    const uint32_t tend = (uint32_t)jb_min((int)(tstart + f.tile_bytes), (int)len);
+    const unsigned wpt = f.tile_bytes >> 5;
+    uint32_t* B = f.vbits + (size_t)tile * wpt;
+    for (unsigned j = 0; j < wpt; ++j) B[j] = 0u;
+    JbWalker w;
+    w.init(f.in + f.plane_off[s], len);
     // first offset of the tile that can start a block: 0, or the byte after a 0x00
     uint32_t pos = tstart;
     if (tstart != 0) {
         while (pos < tend && w.byte_at(pos - 1) != 0) ++pos;
     }
-    unsigned n = 0;
     uint32_t exit_pos = pos;                     // == tend if the tile holds no candidate
     if (pos < tend) {
         w.seek(pos);
-        V[n++] = (uint16_t)(pos - tstart);
+        uint32_t last = pos;
+        B[(pos - tstart) >> 5] |= 1u << ((pos - tstart) & 31u);
         int count = 0;
         // one flat loop over codes (not one loop per block): the 32 lanes of a warp stay converged
         // although their blocks end at different codes
@@ -202,66 +212,85 @@ __device__ __forceinline__ void jb_walk_tile(JbWalker& w, const JbFrameArgs& f, 
             }
             if (bad) {
                 // the last recorded start was false (in a valid stream): resume at the next offset
-                // that follows a 0x00 byte; the list stays sorted, the true chain joins it later
-                uint32_t q = (uint32_t)V[n - 1] + tstart + 1u;
-                while (q < tend && w.byte_at(q - 1) != 0) ++q;
-                if (q >= tend) { exit_pos = JB_POS_INVALID; break; }
-                w.seek(q);
-                V[n++] = (uint16_t)(q - tstart);
-                count = 0;
-                continue;
-            }
-            if (eob) {
+                // that follows a 0x00 byte; the true chain joins the walk later
+                next = last + 1u;
+                while (next < tend && w.byte_at(next - 1) != 0) ++next;
+                if (next >= tend) { exit_pos = JB_POS_INVALID; break; }
+                w.seek(next);
+            } else if (eob) {
                 if (next >= tend) { exit_pos = next; break; }
-                V[n++] = (uint16_t)(next - tstart);
+            }
+            if (bad || eob) {
+                B[(next - tstart) >> 5] |= 1u << ((next - tstart) & 31u);
+                last = next;
                 count = 0;
             }
         }
     }
-    f.tile_n[tile] = n;
     f.tile_exit[tile] = exit_pos;
 }
 
-// any tile size: every thread reads its tile straight from global memory
-__global__ void __launch_bounds__(JB_WALK_THREADS) jb_frame_walk_kernel(JbFrameArgs f) {
-    const unsigned tile = blockIdx.x * JB_WALK_THREADS + threadIdx.x;
-    if (tile >= f.tile_first[f.n_planes]) return;
-    const int s = jb_stream_of_tile(f.tile_first, f.n_planes, tile);
-    const uint32_t len = (uint32_t)f.plane_len[s];
-    const uint32_t tstart = (tile - f.tile_first[s]) * f.tile_bytes;
-    const uint32_t tend = (uint32_t)jb_min((int)(tstart + f.tile_bytes), (int)len);
+// A block that runs past the staged window of its walk: parse it from global memory.
+// Returns the stream offset after the block, or JB_POS_INVALID.
+__device__ __noinline__ uint32_t jb_walk_block_global(const uint8_t* stream, uint32_t len, uint32_t start, int n,
+                                                      int maxblk) {
     JbWalker w;
-    w.init(f.in + f.plane_off[s], len);
-    jb_walk_tile(w, f, tile, tstart, tend);
+    w.init(stream, len);
+    w.seek(start);
+    return w.block(n, (uint32_t)maxblk * 8u) ? (w.bp >> 3) : JB_POS_INVALID;
 }
 
-// small tiles: the warp first copies each lane's window (one byte before the tile, the tile, and
-// JB_WALK_HALO bytes beyond it) into that lane's slice of shared memory with coalesced loads
-__global__ void __launch_bounds__(JB_WALK_THREADS) jb_frame_walk_smem_kernel(JbFrameArgs f, unsigned stride_words) {
+// Smallest q in [from, end) such that byte q-1 of the slice (big-endian-assembled words) is 0x00; `end` if none.
+__device__ __forceinline__ uint32_t jb_next_candidate(const uint32_t* sl, uint32_t from, uint32_t end) {
+    const uint32_t b = from - 1u;
+    uint32_t wi = b >> 2;
+    uint32_t v = sl[wi] | ~(0xFFFFFFFFu >> ((b & 3u) * 8u));        // bytes before b: made non-zero
+    for (;;) {
+        uint32_t t = (v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+        t = ~(t | v | 0x7F7F7F7Fu);                                 // 0x80 in every zero byte
+        if (t) {
+            const uint32_t q = wi * 4u + ((uint32_t)__clz((int)t) >> 3) + 1u;
+            return q < end ? q : end;
+        }
+        ++wi;
+        if (wi * 4u + 1u >= end) return end;
+        v = sl[wi];
+    }
+}
+
+// Small tiles.  Each lane owns a slice of shared memory: `data_words` words of stream (the byte before
+// the tile, the tile, JB_WALK_HALO bytes beyond it, zero fill; filled by the warp with coalesced loads,
+// byte-swapped so that a funnel shift extracts any code head) and the tile's bitmap of block starts.
+// Positions inside the walk are slice-relative: slice byte 0 is the 4-byte aligned address at or below
+// the byte before the tile.
+__global__ void __launch_bounds__(JB_WALK_THREADS) jb_frame_walk_smem_kernel(JbFrameArgs f, unsigned data_words,
+                                                                             unsigned slice_words) {
     extern __shared__ uint32_t s_words[];
     const int lane = threadIdx.x & 31;
+    const unsigned wpt = f.tile_bytes >> 5;
     const unsigned total_tiles = f.tile_first[f.n_planes];
     const unsigned tile = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = tile < total_tiles;
-    uint32_t len = 0, tstart = 0, tend = 0, first = 0, mis = 0, nw = 0, gnw = 0;
+    uint32_t len = 0, tstart = 0, tend = 0, first = 0, mis = 0, nw = 0;
     unsigned long long abase = 0;                   // aligned global address of the window
+    const uint8_t* stream = nullptr;
     if (live) {
         const int s = jb_stream_of_tile(f.tile_first, f.n_planes, tile);
         len = (uint32_t)f.plane_len[s];
+        stream = f.in + f.plane_off[s];
         tstart = (tile - f.tile_first[s]) * f.tile_bytes;
         tend = (uint32_t)jb_min((int)(tstart + f.tile_bytes), (int)len);
         first = tstart ? tstart - 1 : 0;
         const uint32_t last = (uint32_t)jb_min((int)(tstart + f.tile_bytes + JB_WALK_HALO), (int)len);
-        const unsigned long long a0 = (unsigned long long)(uintptr_t)(f.in + f.plane_off[s] + first);
+        const unsigned long long a0 = (unsigned long long)(uintptr_t)(stream + first);
         mis = (uint32_t)(a0 & 3ull);
         abase = a0 - mis;
         nw = (last - first + mis + 3u) >> 2;
-        if (nw > stride_words) nw = stride_words;
-        gnw = (len - first + mis + 3u) >> 2;
+        if (nw > data_words - 2u) nw = data_words - 2u;
     }
-    uint32_t* mine = s_words + (size_t)threadIdx.x * stride_words;
-    // four tiles at a time, up to sixteen loads in flight per lane
-    const int iters = (int)((stride_words + 31u) / 32u);
+    uint32_t* mine = s_words + (size_t)threadIdx.x * slice_words;
+    // four slices at a time, up to sixteen loads in flight per lane; the rest of a slice becomes zero
+    const int iters = (int)((slice_words + 31u) / 32u);
     for (int k0 = 0; k0 < 32; k0 += 4) {
         const uint32_t* g[4];
         uint32_t cnt[4];
@@ -270,7 +299,7 @@ __global__ void __launch_bounds__(JB_WALK_THREADS) jb_frame_walk_smem_kernel(JbF
         for (int q = 0; q < 4; ++q) {
             g[q] = (const uint32_t*)(uintptr_t)__shfl_sync(0xffffffffu, abase, k0 + q);
             cnt[q] = __shfl_sync(0xffffffffu, nw, k0 + q);
-            dst[q] = s_words + (size_t)((threadIdx.x & ~31) + k0 + q) * stride_words;
+            dst[q] = s_words + (size_t)((threadIdx.x & ~31) + k0 + q) * slice_words;
         }
         for (int ib = 0; ib < iters; ib += 4) {
             uint32_t v[4][4];
@@ -279,43 +308,102 @@ __global__ void __launch_bounds__(JB_WALK_THREADS) jb_frame_walk_smem_kernel(JbF
                 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const uint32_t idx = (uint32_t)(ib + j) * 32u + (uint32_t)lane;
-                    v[q][j] = idx < cnt[q] ? __ldg(g[q] + idx) : 0u;
+                    v[q][j] = idx < cnt[q] ? jb_bswap32(__ldg(g[q] + idx)) : 0u;
                 }
             #pragma unroll
             for (int q = 0; q < 4; ++q)
                 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const uint32_t idx = (uint32_t)(ib + j) * 32u + (uint32_t)lane;
-                    if (idx < cnt[q]) dst[q][idx] = v[q][j];
+                    if (idx < slice_words) dst[q][idx] = v[q][j];
                 }
         }
     }
     __syncwarp();
-    if (!live) return;
-    JbWalker w;
-    w.init_window(mine, nw, (const uint32_t*)(uintptr_t)abase, gnw, first, mis, len);
-    jb_walk_tile(w, f, tile, tstart, tend);
+    if (live) {
+        const uint32_t to_stream = first - mis;             // slice byte q is stream byte q + to_stream (mod 2^32)
+        const uint32_t tstart_s = tstart - to_stream, tend_s = tend - to_stream, len_s = len - to_stream;
+        const uint32_t staged_bits = nw * 32u;
+        uint32_t* bm = mine + data_words;
+        // first offset of the tile that can start a block: 0, or the byte after a 0x00
+        uint32_t q = tstart ? jb_next_candidate(mine, tstart_s, tend_s) : tstart_s;
+        uint32_t exit_pos = tend;                            // the tile holds no candidate
+        if (q < tend_s) {
+            uint32_t last = q;
+            bm[(q - tstart_s) >> 5] |= 1u << ((q - tstart_s) & 31u);
+            const uint32_t bm_addr = (uint32_t)__cvta_generic_to_shared(bm);
+            uint32_t p = q * 8u;                             // bit position inside the slice
+            int count = 0;
+            // One flat loop over codes, not one loop per block, and the end-of-block bookkeeping is
+            // predicated: the 32 lanes of a warp stay converged although their blocks end at different
+            // codes.  Only false starts, blocks that leave the staged window and the end of the tile branch.
+            int n;
+            asm volatile("mov.s32 %0, %1;" : "=r"(n) : "r"(f.n));      // keep it in a register, not a constant-bank load per code
+            // a block that ends at or beyond this bit leaves the tile (the staged window reaches further)
+            const uint32_t lim_bits = tend_s * 8u - 8u;
+            for (;;) {
+                const uint32_t idx = p >> 5;
+                const uint32_t x = __funnelshift_l(mine[idx + 1], mine[idx], p);
+                const uint32_t head = x >> 24, size = head & 15u;
+                p += 8u + size;
+                count += (int)(x >> 28) + (size != 0u ? 1 : 0);
+                uint32_t eob = x < 0x01000000u ? 1u : 0u;
+                const bool bad = ((head & 14u) == 0u && head != 0xF0u && x >= 0x01000000u) || count > n;
+                q = (p + 7u) >> 3;
+                if (bad || (x < 0x01000000u && p > lim_bits)) {
+                    bool false_start = bad;
+                    if (p > staged_bits) {
+                        // zero fill was parsed: repeat this block from global memory
+                        const uint32_t nx = jb_walk_block_global(stream, len, last + to_stream, n, f.maxblk);
+                        false_start = nx == JB_POS_INVALID;
+                        q = nx - to_stream;
+                    } else if (q > len_s) {
+                        false_start = true;
+                    }
+                    if (false_start) {
+                        // the last recorded start was false (in a valid stream): resume at the next offset
+                        // that follows a 0x00 byte; the true chain joins the walk later
+                        q = jb_next_candidate(mine, last + 1u, tend_s);
+                        if (q >= tend_s) { exit_pos = JB_POS_INVALID; break; }
+                    } else if (q >= tend_s) {
+                        exit_pos = q + to_stream;
+                        break;
+                    }
+                    eob = 1u;                                 // q is the next start to record
+                }
+                // (an OR with zero when no block ended here; it may then fall a few words past the bitmap)
+                const uint32_t rel = q - tstart_s;
+                asm volatile("red.shared.or.b32 [%0], %1;"
+                             :: "r"(bm_addr + ((rel >> 5) << 2)), "r"(eob << (rel & 31u)) : "memory");
+                last = eob ? q : last;
+                p = eob ? q * 8u : p;
+                count = eob ? 0 : count;
+            }
+        }
+        f.tile_exit[tile] = exit_pos;
+    }
+    __syncwarp();
+    // the warp's 32 bitmaps are consecutive in global memory
+    {
+        const unsigned warp_thread0 = threadIdx.x & ~31u;
+        const unsigned warp_tile0 = blockIdx.x * blockDim.x + warp_thread0;
+        const unsigned shift = 31u - (unsigned)__clz((int)wpt);          // wpt is a power of two
+        for (unsigned i = lane; i < 32u * wpt; i += 32u) {
+            const unsigned k = i >> shift, j = i & (wpt - 1u);
+            if (warp_tile0 + k < total_tiles)
+                f.vbits[(size_t)warp_tile0 * wpt + i] = s_words[(size_t)(warp_thread0 + k) * slice_words + data_words + j];
+        }
+    }
 }
 
 // ---- F2: chain of tiles per stream (pointer doubling over "tile of my exit") -----------------------
-// CAP = tiles of one stream this instantiation handles in shared memory; longer streams are left to
-// the larger instantiation (or, beyond that, to the serial fallback).
-template <unsigned CAP, unsigned MIN_TILES>
-__global__ void __launch_bounds__(1024) jb_frame_reach_kernel(JbFrameArgs f) {
-    extern __shared__ __align__(16) unsigned char reach_smem[];
-    uint16_t* J[2] = {(uint16_t*)reach_smem, (uint16_t*)reach_smem + CAP};
-    uint8_t* R = (uint8_t*)(reach_smem + 4 * (size_t)CAP);
+// CTA-wide.  J0/J1: uint16 [cap], R: uint8 [cap] in shared memory; nt <= cap.  Marks the stream for the
+// serial walk if the chain does not end exactly at the end of the stream.
+__device__ __forceinline__ void jb_reach_stream(const JbFrameArgs& f, int s, uint16_t* J0, uint16_t* J1, uint8_t* R) {
+    uint16_t* J[2] = {J0, J1};
     const int tid = threadIdx.x;
-    if (f.tile_first[f.n_planes] == 0) return;
-    // small instantiation: one CTA per stream; large one: a few CTAs share the list of long streams
-    const unsigned n_work = MIN_TILES ? f.big_list[0] : (unsigned)f.n_planes;
-    for (unsigned wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
-    const int s = MIN_TILES ? (int)f.big_list[1 + wi] : (int)wi;
     const unsigned t0 = f.tile_first[s];
     const unsigned nt = f.tile_first[s + 1] - t0;
-    if (nt < MIN_TILES) continue;                            // the smaller instantiation took it
-    if (nt > CAP) { if (CAP >= 40000u && tid == 0) f.fallback[s] = 1u; continue; }
-    if (nt == 0) { if (tid == 0) f.fallback[s] = 1u; continue; }
     const uint32_t len = (uint32_t)f.plane_len[s];
     const unsigned T = f.tile_bytes;
     for (unsigned t = tid; t < nt; t += blockDim.x) {
@@ -354,69 +442,86 @@ __global__ void __launch_bounds__(1024) jb_frame_reach_kernel(JbFrameArgs f) {
     const int total_ends = __syncthreads_count(ends);
     if (tid == 0 && (bad || total_ends != 1)) f.fallback[s] = 1u;
     __syncthreads();
+}
+
+// CAP = tiles of one stream this instantiation handles in shared memory; longer streams are left to
+// the larger instantiation (or, beyond that, to the serial fallback).
+template <unsigned CAP, unsigned MIN_TILES>
+__global__ void __launch_bounds__(1024) jb_frame_reach_kernel(JbFrameArgs f) {
+    extern __shared__ __align__(16) unsigned char reach_smem[];
+    const int tid = threadIdx.x;
+    if (f.tile_first[f.n_planes] == 0) return;
+    // small instantiation: one CTA per stream; large one: a few CTAs share the list of long streams
+    const unsigned n_work = MIN_TILES ? f.big_list[0] : (unsigned)f.n_planes;
+    for (unsigned wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+        const int s = MIN_TILES ? (int)f.big_list[1 + wi] : (int)wi;
+        const unsigned nt = f.tile_first[s + 1] - f.tile_first[s];
+        if (nt < MIN_TILES) continue;                            // the smaller instantiation took it
+        if (nt > CAP) { if (CAP >= 40000u && tid == 0) f.fallback[s] = 1u; continue; }
+        if (nt == 0) { if (tid == 0) f.fallback[s] = 1u; continue; }
+        jb_reach_stream(f, s, (uint16_t*)reach_smem, (uint16_t*)reach_smem + CAP, (uint8_t*)(reach_smem + 4 * (size_t)CAP));
     }
 }
 
-// ---- F2a: link each tile on the chain to its entry -----------------------------------------
-__global__ void __launch_bounds__(JB_FRAME_THREADS) jb_frame_link_kernel(JbFrameArgs f) {
-    const unsigned tile = blockIdx.x * JB_FRAME_THREADS + threadIdx.x;
-    if (tile >= f.tile_first[f.n_planes]) return;
-    const int s = jb_stream_of_tile(f.tile_first, f.n_planes, tile);
+// ---- F2a: link a tile on the chain to its entry ----------------------------------------------------
+__device__ __forceinline__ void jb_link_tile(const JbFrameArgs& f, int s, unsigned tile) {
     const uint32_t len = (uint32_t)f.plane_len[s];
     const unsigned t = tile - f.tile_first[s];
     const uint32_t tstart = t * f.tile_bytes;
     const uint32_t tend = (uint32_t)jb_min((int)(tstart + f.tile_bytes), (int)len);
-    const uint16_t* V = f.visited + (size_t)tile * f.tile_bytes;
-    const unsigned n = f.tile_n[tile];
+    const unsigned wpt = f.tile_bytes >> 5;
+    const uint32_t* B = f.vbits + (size_t)tile * wpt;
     const uint32_t my_exit = f.tile_exit[tile];
 
     const uint32_t E = f.tile_entry[tile];                  // JB_POS_INVALID: no true block starts here
-    unsigned from = n, npriv = 0, hops = 0;
-    (void)t;
+    unsigned from = f.tile_bytes, npriv = 0, hops = 0;      // from: byte of the tile where the chain joins the walk
     bool ok = true;
     if (E == JB_POS_INVALID) {
         // not on the chain of tiles: a block that started earlier covers this tile
     } else if (E < tstart || E >= tend || my_exit == JB_POS_INVALID) {
         ok = false;
-    } else if (ok) {
+    } else {
         const uint32_t rel = E - tstart;
-        unsigned lo = 0, hi = n;
-        while (lo < hi) { unsigned mid = (lo + hi) >> 1; if (V[mid] < rel) lo = mid + 1; else hi = mid; }
-        if (lo < n && V[lo] == rel) {
-            from = lo;
+        if ((B[rel >> 5] >> (rel & 31u)) & 1u) {
+            from = rel;
         } else {
             // follow the chain from E until it meets the walk (or leaves the tile at the walk's exit)
             JbWalker w;
             w.init(f.in + f.plane_off[s], len);
             w.seek(E);
             const uint32_t maxblk_bits = (uint32_t)f.maxblk * 8u;
-            uint32_t pos = E;
-            unsigned j = lo;
             for (;;) {
                 if (!w.block(f.n, maxblk_bits)) { ok = false; break; }
                 ++npriv;
-                pos = w.bp >> 3;
-                if (pos >= tend) { ok = (pos == my_exit); from = n; break; }
-                while (j < n && (uint32_t)V[j] + tstart < pos) ++j;
-                if (j < n && (uint32_t)V[j] + tstart == pos) { from = j; break; }
+                const uint32_t pos = w.bp >> 3;
+                if (pos >= tend) { ok = (pos == my_exit); break; }
+                const uint32_t r = pos - tstart;
+                if ((B[r >> 5] >> (r & 31u)) & 1u) { from = r; break; }
             }
         }
-        hops = npriv + (n - from);
+        hops = npriv;
+        if (from < f.tile_bytes) {
+            hops += (unsigned)__popc(B[from >> 5] >> (from & 31u));
+            for (unsigned j = (from >> 5) + 1u; j < wpt; ++j) hops += (unsigned)__popc(B[j]);
+        }
     }
-    if (!ok) { f.fallback[s] = 1u; hops = 0; from = n; npriv = 0; }
+    if (!ok) { f.fallback[s] = 1u; hops = 0; from = f.tile_bytes; npriv = 0; }
     f.tile_from[tile] = from;
     f.tile_npriv[tile] = npriv;
     f.tile_hops[tile] = hops;
 }
 
-// ---- F2b: per stream, ordinals of the tiles' first blocks -------------------------------------------
-__global__ void __launch_bounds__(1024) jb_frame_scan_kernel(JbFrameArgs f) {
-    __shared__ unsigned s_warp[33];
-    const int s = blockIdx.x, tid = threadIdx.x;
-    if (f.tile_first[f.n_planes] == 0) return;                // prep failed, error already set
+__global__ void __launch_bounds__(JB_FRAME_THREADS) jb_frame_link_kernel(JbFrameArgs f) {
+    const unsigned tile = blockIdx.x * JB_FRAME_THREADS + threadIdx.x;
+    if (tile >= f.tile_first[f.n_planes]) return;
+    jb_link_tile(f, jb_stream_of_tile(f.tile_first, f.n_planes, tile), tile);
+}
+
+// ---- F2b: per stream, ordinals of the tiles' first blocks (CTA-wide) -----------------------------------
+__device__ __forceinline__ void jb_scan_stream(const JbFrameArgs& f, int s, unsigned* s_warp) {
+    const int tid = threadIdx.x;
     const unsigned t0 = f.tile_first[s];
     const unsigned nt = f.tile_first[s + 1] - t0;
-    const uint32_t len = (uint32_t)f.plane_len[s];
     unsigned carry = 0;
     for (unsigned b = 0; b < nt; b += blockDim.x) {
         const unsigned t = b + tid;
@@ -427,7 +532,7 @@ __global__ void __launch_bounds__(1024) jb_frame_scan_kernel(JbFrameArgs f) {
         carry += total;
     }
     if (tid == 0) {
-        // (that the chain of tiles ends exactly at the stream end was checked by jb_frame_reach_kernel)
+        // (that the chain of tiles ends exactly at the stream end was checked by jb_reach_stream)
         const bool good = nt > 0 && f.fallback[s] == 0u && carry == (unsigned)f.nblocks;
         if (!good) {
             f.fallback[s] = 1u;
@@ -436,16 +541,19 @@ __global__ void __launch_bounds__(1024) jb_frame_scan_kernel(JbFrameArgs f) {
     }
 }
 
-// ---- F3: emit block offsets --------------------------------------------------------------------------
-__global__ void __launch_bounds__(JB_FRAME_THREADS) jb_frame_emit_kernel(JbFrameArgs f) {
-    const unsigned tile = blockIdx.x * JB_FRAME_THREADS + threadIdx.x;
-    if (tile >= f.tile_first[f.n_planes]) return;
-    const int s = jb_stream_of_tile(f.tile_first, f.n_planes, tile);
-    if (f.fallback[s]) return;
+__global__ void __launch_bounds__(1024) jb_frame_scan_kernel(JbFrameArgs f) {
+    __shared__ unsigned s_warp[33];
+    if (f.tile_first[f.n_planes] == 0) return;                // prep failed, error already set
+    jb_scan_stream(f, blockIdx.x, s_warp);
+}
+
+// ---- F3: emit the block offsets of a tile -------------------------------------------------------------
+__device__ __forceinline__ void jb_emit_tile(const JbFrameArgs& f, int s, unsigned tile) {
     const uint32_t len = (uint32_t)f.plane_len[s];
     const uint32_t tstart = (tile - f.tile_first[s]) * f.tile_bytes;
-    const uint16_t* V = f.visited + (size_t)tile * f.tile_bytes;
-    const unsigned n = f.tile_n[tile], from = f.tile_from[tile], npriv = f.tile_npriv[tile];
+    const unsigned wpt = f.tile_bytes >> 5;
+    const uint32_t* B = f.vbits + (size_t)tile * wpt;
+    const unsigned from = f.tile_from[tile], npriv = f.tile_npriv[tile];
     unsigned idx = f.tile_base[tile];
     unsigned* out = f.block_start + (size_t)s * f.nblocks;
     if (npriv) {
@@ -458,16 +566,31 @@ __global__ void __launch_bounds__(JB_FRAME_THREADS) jb_frame_emit_kernel(JbFrame
             w.block(f.n, maxblk_bits);
         }
     }
-    for (unsigned j = from; j < n && idx < (unsigned)f.nblocks; ++j) out[idx++] = tstart + V[j];
+    if (from < f.tile_bytes) {
+        uint32_t word = B[from >> 5] & (0xFFFFFFFFu << (from & 31u));
+        for (unsigned j = from >> 5;;) {
+            while (word && idx < (unsigned)f.nblocks) {
+                out[idx++] = tstart + j * 32u + (unsigned)__ffs((int)word) - 1u;
+                word &= word - 1u;
+            }
+            if (++j >= wpt) break;
+            word = B[j];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(JB_FRAME_THREADS) jb_frame_emit_kernel(JbFrameArgs f) {
+    const unsigned tile = blockIdx.x * JB_FRAME_THREADS + threadIdx.x;
+    if (tile >= f.tile_first[f.n_planes]) return;
+    const int s = jb_stream_of_tile(f.tile_first, f.n_planes, tile);
+    if (f.fallback[s]) return;
+    jb_emit_tile(f, s, tile);
 }
 
 // ---- F4: serial fallback, one warp per marked stream ------------------------------------------------------
 // The warp stages the stream through shared memory 4 KB at a time (coalesced); lane 0 walks it.
 #define JB_SERIAL_WORDS 1024
-__global__ void __launch_bounds__(32) jb_frame_serial_kernel(JbFrameArgs f) {
-    __shared__ uint32_t sw[JB_SERIAL_WORDS + 8];
-    const int s = blockIdx.x, lane = threadIdx.x;
-    if (f.fallback[s] == 0u) return;
+__device__ __forceinline__ void jb_serial_stream(const JbFrameArgs& f, int s, uint32_t* sw, int lane) {
     const uint32_t len = (uint32_t)f.plane_len[s];
     const uint8_t* stream = f.in + f.plane_off[s];
     unsigned* out = f.block_start + (size_t)s * f.nblocks;
@@ -503,23 +626,78 @@ __global__ void __launch_bounds__(32) jb_frame_serial_kernel(JbFrameArgs f) {
     if (lane == 0 && (!ok || k != (unsigned)f.nblocks)) jb_set_error(f.status, JB_ERR_BAD_STREAM);
 }
 
-cudaError_t jb_launch_framing(const JbFrameArgs& f, cudaStream_t s) {
+__global__ void __launch_bounds__(32) jb_frame_serial_kernel(JbFrameArgs f) {
+    __shared__ uint32_t sw[JB_SERIAL_WORDS + 8];
+    if (f.fallback[blockIdx.x] == 0u) return;
+    jb_serial_stream(f, blockIdx.x, sw, threadIdx.x);
+}
+
+// ---- F2..F4 in one launch, for batches of short streams: one CTA per stream ---------------------------------
+// (the per-tile arrays written by one phase and read by the next stay in L2; __syncthreads orders them)
+#define JB_STITCH_CAP 4096u
+#define JB_STITCH_THREADS 256
+__global__ void __launch_bounds__(JB_STITCH_THREADS) jb_frame_stitch_kernel(JbFrameArgs f) {
+    extern __shared__ __align__(16) unsigned char stitch_smem[];       // max(5 * cap, serial window)
+    __shared__ unsigned s_warp[33];
+    const int s = blockIdx.x, tid = threadIdx.x;
+    if (f.tile_first[f.n_planes] == 0) return;                // prep failed, error already set
+    const unsigned t0 = f.tile_first[s];
+    const unsigned nt = f.tile_first[s + 1] - t0;
+    const unsigned cap = f.stitch_cap;
+    if (nt == 0 || nt > cap) {
+        if (tid == 0) f.fallback[s] = 1u;                     // empty (invalid) or far longer than its peers
+        __syncthreads();
+    } else {
+        jb_reach_stream(f, s, (uint16_t*)stitch_smem, (uint16_t*)stitch_smem + cap, (uint8_t*)(stitch_smem + 4 * (size_t)cap));
+        for (unsigned t = tid; t < nt; t += blockDim.x) jb_link_tile(f, s, t0 + t);
+        __syncthreads();
+    }
+    jb_scan_stream(f, s, s_warp);
+    __syncthreads();
+    if (f.fallback[s] == 0u) {
+        for (unsigned t = tid; t < nt; t += blockDim.x) jb_emit_tile(f, s, t0 + t);
+    } else if (tid < 32) {
+        jb_serial_stream(f, s, (uint32_t*)stitch_smem, tid);
+    }
+}
+
+cudaError_t jb_launch_framing(const JbFrameArgs& f_in, cudaStream_t s) {
     cudaError_t e;
+    JbFrameArgs f = f_in;
     const unsigned grid = (f.max_tiles + JB_FRAME_THREADS - 1) / JB_FRAME_THREADS;
     jb_frame_prep_kernel<<<1, 1024, 0, s>>>(f);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    // staged window of one walk: 1 byte before the tile + tile + JB_WALK_HALO + slack, in words, odd stride;
-    // as many threads per block (a multiple of 32, at most JB_WALK_THREADS) as fit ~56 KB of shared memory
-    const unsigned stride_words = (((unsigned)f.tile_bytes + JB_WALK_HALO + 16u) / 4u) | 1u;
-    unsigned wthreads = (56u * 1024u / (stride_words * 4u)) / 32u * 32u;
-    if (wthreads > JB_WALK_THREADS) wthreads = JB_WALK_THREADS;
-    if (wthreads >= 32) {
-        const size_t smem = (size_t)wthreads * stride_words * 4;
+    // slice of one walk: stream words (1 byte before the tile + misalignment + tile + JB_WALK_HALO, two words of
+    // zero slack) and the bitmap, odd length; the block size that puts most warps on an SM
+    const unsigned data_words = (unsigned)f.tile_bytes / 4u + JB_WALK_HALO / 4u + 4u;
+    const unsigned slice_words = (data_words + (unsigned)f.tile_bytes / 32u) | 1u;
+    unsigned wthreads = 0, best_warps = 0;
+    for (unsigned wt = JB_WALK_THREADS; wt >= 32u; wt -= 32u) {
+        const size_t per_block = (size_t)wt * slice_words * 4u + 32u + 1024u;
+        unsigned blocks = (unsigned)((size_t)227 * 1024 / per_block);
+        if (blocks > 32u) blocks = 32u;
+        const unsigned warps = blocks * wt / 32u;
+        if (warps > best_warps && warps >= 8u) { best_warps = warps; wthreads = wt; }
+    }
+    if (wthreads) {
+        const size_t smem = (size_t)wthreads * slice_words * 4 + 32;       // + overhang of the last slice's bitmap
         e = cudaFuncSetAttribute(jb_frame_walk_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        jb_frame_walk_smem_kernel<<<(f.max_tiles + wthreads - 1) / wthreads, wthreads, smem, s>>>(f, stride_words);
+        jb_frame_walk_smem_kernel<<<(f.max_tiles + wthreads - 1) / wthreads, wthreads, smem, s>>>(f, data_words, slice_words);
     } else {
         jb_frame_walk_kernel<<<(f.max_tiles + JB_WALK_THREADS - 1) / JB_WALK_THREADS, JB_WALK_THREADS, 0, s>>>(f);
+    }
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if ((size_t)f.max_tiles <= (size_t)f.n_planes * (JB_STITCH_CAP / 4u)) {
+        // many short streams (a batch of images): the rest of the framing in one launch, one CTA per stream;
+        // a stream of more than `cap` tiles (far longer than its peers) takes the serial walk
+        unsigned cap = f.max_tiles < JB_STITCH_CAP ? f.max_tiles : JB_STITCH_CAP;
+        cap = (cap + 7u) & ~7u;
+        size_t smem = 5 * (size_t)cap;
+        if (smem < (JB_SERIAL_WORDS + 8) * 4) smem = (JB_SERIAL_WORDS + 8) * 4;
+        f.stitch_cap = cap;
+        jb_frame_stitch_kernel<<<f.n_planes, JB_STITCH_THREADS, smem, s>>>(f);
+        return cudaGetLastError();
     }
     {   // chain of tiles: streams of up to 4096 tiles (1 MB) in 20 KB of shared memory, longer ones in 200 KB
         const size_t sm_small = 5 * 4096, sm_big = 5 * 40000;

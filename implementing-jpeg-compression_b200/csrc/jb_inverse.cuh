@@ -23,14 +23,13 @@ struct JbDecLayout {
     size_t fallback;     // uint32 [n_planes]       stream needs the serial walk
     size_t big_list;     // uint32 [n_planes + 1]   [0] = count, then the streams with more than 4096 tiles
     size_t block_start;  // uint32 [n_planes * nblocks]  byte offset of every block inside its stream
-    size_t tile_n;       // uint32 [max_tiles]  starts recorded by the tile's walk
     size_t tile_exit;    // uint32 [max_tiles]  offset where the walk leaves the tile (or invalid)
     size_t tile_entry;   // uint32 [max_tiles]  offset of the first true block start of the tile
-    size_t tile_from;    // uint32 [max_tiles]  index into the walk's list where the true chain joins it
+    size_t tile_from;    // uint32 [max_tiles]  byte of the tile where the true chain joins the walk (tile_bytes: nowhere)
     size_t tile_npriv;   // uint32 [max_tiles]  true blocks before that point
     size_t tile_hops;    // uint32 [max_tiles]  true blocks that start inside the tile
     size_t tile_base;    // uint32 [max_tiles]  ordinal (within the stream) of the tile's first true block
-    size_t visited;      // uint16 [max_tiles * tile_bytes]
+    size_t vbits;        // uint32 [max_tiles * tile_bytes / 32]  bit b of a tile: its walk saw a block start at byte b
     size_t total;
     unsigned max_tiles;
     unsigned tile_bytes;
@@ -47,14 +46,13 @@ static inline JbDecLayout jb_dec_layout(int d, int n_planes, long long nblocks_p
     L.fallback = o;    o += jb_align_up((size_t)n_planes * 4, 256);
     L.big_list = o;    o += jb_align_up(((size_t)n_planes + 1) * 4, 256);
     L.block_start = o; o += jb_align_up((size_t)n_planes * (size_t)nblocks_per_plane * 4, 256);
-    L.tile_n = o;      o += jb_align_up((size_t)L.max_tiles * 4, 256);
     L.tile_exit = o;   o += jb_align_up((size_t)L.max_tiles * 4, 256);
     L.tile_entry = o;  o += jb_align_up((size_t)L.max_tiles * 4, 256);
     L.tile_from = o;   o += jb_align_up((size_t)L.max_tiles * 4, 256);
     L.tile_npriv = o;  o += jb_align_up((size_t)L.max_tiles * 4, 256);
     L.tile_hops = o;   o += jb_align_up((size_t)L.max_tiles * 4, 256);
     L.tile_base = o;   o += jb_align_up((size_t)L.max_tiles * 4, 256);
-    L.visited = o;     o += jb_align_up((size_t)L.max_tiles * L.tile_bytes * 2, 256);
+    L.vbits = o;       o += jb_align_up((size_t)L.max_tiles * (L.tile_bytes / 8), 256);
     L.total = o;
     return L;
 }
@@ -69,18 +67,18 @@ struct JbFrameArgs {
     int maxblk;
     unsigned max_tiles, tile_bytes;
     int force_serial;      // JB_FLAG_SERIAL_FRAMING: every stream takes the serial walk (test hook)
+    unsigned stitch_cap;   // set by jb_launch_framing: tiles per stream the one-launch path handles
     unsigned* tile_first;
     unsigned* fallback;
     unsigned* big_list;
     unsigned* block_start;
-    unsigned* tile_n;
     unsigned* tile_exit;
     unsigned* tile_entry;
     unsigned* tile_from;
     unsigned* tile_npriv;
     unsigned* tile_hops;
     unsigned* tile_base;
-    uint16_t* visited;
+    uint32_t* vbits;
     unsigned long long* status;
 };
 

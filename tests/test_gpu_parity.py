@@ -153,6 +153,28 @@ def test_serial_framing_fallback_matches(jb):
         jb.decompress_bands([streams[0], streams[1][:-2], streams[2]], cfg, flags=8)
 
 
+def test_one_long_stream_among_short_ones(jb):
+    """A batch of short streams takes the one-launch framing path (one CTA per stream); a stream far
+    longer than its peers (more tiles than that path holds) is walked serially and still decodes."""
+    import torch
+    h = w = 1536
+    cfg, ocfg = _cfgs(jb, (h, w, 1, 8, "DCT", "none", None))
+    rng = np.random.default_rng(5)
+    n_zero = 60
+    noisy = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    planes = torch.zeros((n_zero + 1, h, w), dtype=torch.uint8, device="cuda")
+    planes[17] = torch.from_numpy(noisy).cuda()
+    comp = jb.compress_planes(planes, cfg)
+    off = comp.host_offsets()
+    lens = np.diff(off)
+    assert lens[17] > 4096 * 256 and lens.sum() / (n_zero + 1) < 1024 * 256
+    out, status = jb.decompress_planes(comp.data, comp.offsets[:-1], comp.offsets[1:] - comp.offsets[:-1], cfg,
+                                       n_zero + 1, in_bytes=int(lens.sum()))
+    jb.check_status(status)
+    assert int(status.cpu()[2].item()) == 1                  # exactly the long stream took the serial walk
+    assert torch.equal(out, planes)                          # 'none' on 8-bit data with block_size 1 is lossless
+
+
 def test_framing_with_many_false_block_starts(jb):
     """Streams full of 0x00 bytes inside amplitude fields: most candidate offsets are false."""
     rng = np.random.default_rng(77)
