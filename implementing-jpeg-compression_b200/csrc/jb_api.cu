@@ -227,7 +227,7 @@ static int jb_inverse_common(int mode, const uint8_t* d_in, size_t in_bytes, con
         // a stream that fails framing leaves block_start unwritten: make it deterministic
         JB_CUDA_TRY(cudaMemsetAsync(f.block_start, 0xFF, (size_t)n_planes * g.nblocks * 4, s));
         JB_CUDA_TRY(jb_launch_framing(f, s));
-        a.in = d_in;
+        a.in = d_in; a.in_bytes = in_bytes;
         a.plane_off = f.plane_off; a.plane_len = f.plane_len;
         a.block_start = f.block_start;
     } else if (ws_bytes < table_bytes) {

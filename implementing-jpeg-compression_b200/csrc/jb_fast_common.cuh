@@ -29,6 +29,11 @@ __device__ __forceinline__ void ff_tma_load_3d(void* dst, const CUtensorMap* map
                  "[%0], [%1, {%2, %3, %4}], [%5];"
                  :: "r"(ff_smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(ff_smem_u32(bar)) : "memory");
 }
+// 1-D bulk copy global -> shared (16-byte aligned on both sides, size a multiple of 16), completion on an mbarrier
+__device__ __forceinline__ void ff_bulk_load_1d(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(ff_smem_u32(dst)), "l"(src), "r"(bytes), "r"(ff_smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void ff_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- 8-point transforms ---------------------------------------------------------------------
@@ -117,6 +122,6 @@ __device__ __forceinline__ void ff_bulk_commit() { asm volatile("cp.async.bulk.c
 template <int N>
 __device__ __forceinline__ void ff_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
 
-// 3-D uint8 tensor map over a batch of planes (x = byte in row, y = row, z = plane), box 128 x 32 x 1
+// 3-D uint8 tensor map over a batch of planes (x = byte in row, y = row, z = plane), box box_w x box_h x 1
 bool jb_make_plane_tensor_map(CUtensorMap* map, const void* base, int W, int H, int n_planes, size_t row_pitch,
-                              size_t plane_stride);
+                              size_t plane_stride, int box_w = 128, int box_h = 32);

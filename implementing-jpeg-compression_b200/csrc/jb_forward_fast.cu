@@ -467,14 +467,14 @@ static PFN_encodeTiled jb_get_encode_tiled() {
 
 // 3-D uint8 tensor (x = byte in row, y = row, z = plane), box 128 x 32 x 1
 bool jb_make_plane_tensor_map(CUtensorMap* map, const void* base, int W, int H, int n_planes, size_t row_pitch,
-                              size_t plane_stride) {
+                              size_t plane_stride, int box_w, int box_h) {
     PFN_encodeTiled enc = jb_get_encode_tiled();
     if (!enc) return false;
-    if (((uintptr_t)base & 15) || (row_pitch & 15) || (plane_stride & 15) || W < 128 || H < 32) return false;
+    if (((uintptr_t)base & 15) || (row_pitch & 15) || (plane_stride & 15) || W < box_w || H < box_h) return false;
     cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_planes};
     cuuint64_t strides[2] = {(cuuint64_t)row_pitch, (cuuint64_t)(n_planes > 1 ? plane_stride : row_pitch * (size_t)H)};
     if (strides[1] & 15) return false;
-    cuuint32_t box[3] = {128, 32, 1};
+    cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)base, dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

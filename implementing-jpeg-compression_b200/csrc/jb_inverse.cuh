@@ -86,6 +86,7 @@ struct JbInvArgs {
     JbGeom g;
     JbTables t;
     const uint8_t* in;
+    size_t in_bytes;            // bytes readable at `in`
     const unsigned long long* plane_off;
     const unsigned long long* plane_len;
     const unsigned* block_start;
