@@ -242,23 +242,57 @@ def run_ours(args, rank, world, local_rank):
             sampler = None
 
     # ---- device-resident timing ----
+    # The two library calls of a step are captured once into two CUDA graphs (same kernels, same buffers)
+    # and replayed: per rank and step ~20 small launches otherwise cost more CPU and launch gaps than the
+    # kernels themselves when the per-rank batch is small (8-GPU runs).  --no-graph launches them directly.
     K, Wm = args.steps, args.warmup
+    launch_mode = "direct"
+    state = {"comp": comp}
+    def direct_c():
+        state["comp"] = bc.compress_device()
+    def direct_d():
+        bc.decompress_device(state["comp"], total_bytes)
+    run_c, run_d = direct_c, direct_d
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                direct_c(); direct_d()                     # warm the allocator pools on the capture stream
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g_c, g_d = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_c):
+                comp_g = bc.compress_device()
+            with torch.cuda.graph(g_d, pool=g_c.pool()):
+                out_g, status_g = bc.decompress_device(comp_g, total_bytes)
+            g_c.replay(); g_d.replay()
+            torch.cuda.synchronize()
+            jb.check_status(comp_g.status); jb.check_status(status_g)
+            if comp_g.total_bytes() != total_bytes or not torch.equal(out_g[:3], out[:3]):
+                raise RuntimeError("graph replay differs from the direct calls")
+            state["comp"] = comp_g
+            run_c, run_d = g_c.replay, g_d.replay
+            launch_mode = "cuda graphs (one per library call)"
+        except Exception as exc:                          # noqa: BLE001 -- report and fall back to direct launches
+            launch_mode = "direct (graph capture failed: %s)" % str(exc).splitlines()[0][:120]
+            run_c, run_d = direct_c, direct_d
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
     for step in range(Wm):
-        comp = bc.compress_device()
-        bc.decompress_device(comp, total_bytes)
+        run_c(); run_d()
     barrier()
     for step in range(K):
         ev[step][0].record()
-        comp = bc.compress_device()
+        run_c()
         ev[step][1].record()
-        bc.decompress_device(comp, total_bytes)
+        run_d()
         ev[step][2].record()
     barrier()
     t_c = sum(e[0].elapsed_time(e[1]) for e in ev) / K           # ms per step, compress part
     t_d = sum(e[1].elapsed_time(e[2]) for e in ev) / K
     t_all = ev[0][0].elapsed_time(ev[-1][2]) / K
     t_c, t_d, t_all = max_over_ranks(t_c), max_over_ranks(t_d), max_over_ranks(t_all)
+    comp = state["comp"]
     jb.check_status(comp.status)
 
     # ---- end to end through host buffers ----
@@ -267,11 +301,13 @@ def run_ours(args, rank, world, local_rank):
         h_planes = torch.empty((n_planes, H, W), dtype=torch.uint8, pin_memory=True)
         h_planes.copy_(bc.d_planes)
         torch.cuda.synchronize()
+        n_sub = max(1, min(args.e2e_sub, n_img // 8))
         for step in range(min(Wm, 2)):
             hs, offs = bc.compress_host(h_planes)
             bc.decompress_host(hs, offs)
+            bc.roundtrip_host(h_planes, n_sub)
+        # (a) the two calls one after the other: host -> device traffic, then device -> host traffic
         barrier()
-        t0 = time.perf_counter()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
         for step in range(K):
@@ -279,14 +315,29 @@ def run_ours(args, rank, world, local_rank):
             dec = bc.decompress_host(hs, offs)
         e1.record()
         barrier()
+        t_seq = max_over_ranks(e0.elapsed_time(e1) / K)
+        seq_ok = bool(torch.equal(dec[:3], bc.d_decoded[:3].cpu()))
+        # (b) the same work as a two-stage pipeline over sub-batches: both directions of the link busy
+        barrier()
+        t0 = time.perf_counter()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for step in range(K):
+            dec, parts = bc.roundtrip_host(h_planes, n_sub)
+        e1.record()
+        barrier()
         t_e2e = max_over_ranks(e0.elapsed_time(e1) / K)
         wall_e2e = max_over_ranks((time.perf_counter() - t0) / K * 1e3)
         e2e = {"value": mp_total / (t_e2e * 1e-3), "unit": "MP/s",
-               "h2d_bytes_per_step": n_planes * H * W + total_bytes + 8 * (n_planes + 1),
-               "d2h_bytes_per_step": total_bytes + 8 * (n_planes + 1) + 64 + n_planes * H * W,
+               "h2d_bytes_per_step": n_planes * H * W + total_bytes + 8 * (n_planes + n_sub),
+               "d2h_bytes_per_step": total_bytes + 8 * (n_planes + n_sub) + 64 * n_sub + n_planes * H * W,
                "ms_per_step": t_e2e, "wall_ms_per_step": wall_e2e,
-               "api": "BatchCodec.compress_host + decompress_host (pinned host buffers), per rank",
-               "matches_device_path": bool(torch.equal(dec[:3], bc.d_decoded[:3].cpu()))}
+               "api": "BatchCodec.roundtrip_host (pinned host buffers in and out, streams pass through host memory; "
+                      "%d sub-batches pipelined on two CUDA streams so that both link directions are busy), per rank" % n_sub,
+               "sequential_ms_per_step": t_seq, "sequential_value": mp_total / (t_seq * 1e-3),
+               "sequential_api": "BatchCodec.compress_host then decompress_host",
+               "matches_device_path": bool(torch.equal(dec[:3], bc.d_decoded[:3].cpu())) and seq_ok
+                                      and bool(torch.equal(dec[-3:], bc.d_decoded[-3:].cpu()))}
 
     clocks = sampler.stop() if sampler is not None else {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
 
@@ -315,7 +366,7 @@ def run_ours(args, rank, world, local_rank):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
             "compress_mps": mp_total / (t_c * 1e-3), "decompress_mps": mp_total / (t_d * 1e-3),
             "ms_compress": t_c, "ms_decompress": t_d, "stream_bytes": stream_total,
-            "decoder_serial_fallback_streams_rank0": serial_streams,
+            "decoder_serial_fallback_streams_rank0": serial_streams, "launch": launch_mode,
             "bytes_per_pixel": stream_total / (N_IMAGES * H * W),
             "roofline": {"bound": "hbm", "kernel": "jb_fwd_fast_kernel (fused compress; timed with the table "
                          "builder and two memsets of the same call)", "achieved": ach_c, "peak": peak,
@@ -388,6 +439,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--images", type=int, default=N_IMAGES, help="batch size (profiling runs use a smaller one)")
+    ap.add_argument("--e2e-sub", type=int, default=32, help="sub-batches of the pipelined end-to-end round trip")
+    ap.add_argument("--no-graph", action="store_true", help="launch the kernels directly instead of replaying CUDA graphs")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
     args = ap.parse_args()

@@ -321,6 +321,93 @@ class BatchCodec:
         torch.cuda.current_stream().synchronize()
         return out, offsets
 
+    def roundtrip_host(self, h_planes, n_sub=8):
+        """compress_host followed by decompress_host, run as a two-stage pipeline over ``n_sub``
+        sub-batches of planes: while sub-batch i is decompressed and copied back (device -> host),
+        sub-batch i + 1 is copied in (host -> device) and compressed, so both directions of the
+        host link are busy.  The streams of every sub-batch are copied to the host and read back
+        from the host, exactly as in the two separate calls.
+
+        Returns ``(decoded, parts)``: the uint8 host tensor [n, H, W] and, per sub-batch,
+        ``(first_plane, host uint8 tensor with its streams, int64 numpy offsets)``."""
+        lib = _lib.load()
+        n_sub = max(1, min(int(n_sub), self.n_planes))
+        bounds = [self.n_planes * j // n_sub for j in range(n_sub + 1)]
+        p = self.config.c_params(self.flags)
+        caps = [int(lib.jb_max_stream_bytes(ctypes.byref(p), bounds[j + 1] - bounds[j])) for j in range(n_sub)]
+        cap0 = [0]
+        for c in caps:
+            cap0.append(cap0[-1] + ((c + 255) // 256) * 256)
+        with torch.cuda.device(self.device):
+            if getattr(self, "_rt", None) is None or self._rt["n_sub"] != n_sub:
+                self._rt = {
+                    "n_sub": n_sub, "sa": torch.cuda.Stream(), "sb": torch.cuda.Stream(),
+                    "d_work": torch.empty(cap0[-1], dtype=torch.uint8, device=self.device),
+                    "d_back": torch.empty(cap0[-1], dtype=torch.uint8, device=self.device),
+                    "h_off": [torch.empty(bounds[j + 1] - bounds[j] + 1, dtype=torch.int64, pin_memory=self.pinned)
+                              for j in range(n_sub)],
+                    "h_st": [torch.empty(2 * _lib.JB_STATUS_WORDS, dtype=torch.int64, pin_memory=self.pinned)
+                             for j in range(n_sub)],
+                    "h_streams": None,
+                }
+            rt = self._rt
+            if self.h_decoded is None:
+                self.h_decoded = torch.empty((self.n_planes, self.h, self.w), dtype=torch.uint8, pin_memory=self.pinned)
+            cur = torch.cuda.current_stream()
+            sa, sb = rt["sa"], rt["sb"]
+            sa.wait_stream(cur)
+            sb.wait_stream(cur)
+            nw = _lib.JB_STATUS_WORDS
+
+            def stage_in(j):
+                p0, p1 = bounds[j], bounds[j + 1]
+                with torch.cuda.stream(sa):
+                    self.d_planes[p0:p1].copy_(h_planes[p0:p1], non_blocking=True)
+                    comp = compress_planes(self.d_planes[p0:p1], self.config, flags=self.flags,
+                                           out=rt["d_work"][cap0[j]:cap0[j] + caps[j]])
+                    rt["h_off"][j].copy_(comp.offsets, non_blocking=True)
+                    rt["h_st"][j][:nw].copy_(comp.status, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(sa)
+                return ev
+
+            def stage_out(j, ev):
+                p0, p1 = bounds[j], bounds[j + 1]
+                ev.synchronize()
+                st = rt["h_st"][j]
+                if int(st[0].item()):
+                    _raise_for_code(-int(st[0].item()), int(st[1].item()) & 0xFFFFFFFFFFFFFFFF)
+                offsets = rt["h_off"][j].numpy().copy()
+                total = int(offsets[-1])
+                if rt["h_streams"] is None:
+                    rt["h_streams"] = torch.empty(cap0[-1], dtype=torch.uint8, pin_memory=self.pinned)
+                h_part = rt["h_streams"][cap0[j]:cap0[j] + total]
+                with torch.cuda.stream(sb):
+                    h_part.copy_(rt["d_work"][cap0[j]:cap0[j] + total], non_blocking=True)        # streams -> host
+                    d_in = rt["d_back"][cap0[j]:cap0[j] + caps[j]]
+                    d_in[:total].copy_(h_part, non_blocking=True)                                 # host -> device
+                    d_off = rt["h_off"][j].to(self.device, non_blocking=True)
+                    out, status = decompress_planes(d_in, d_off[:-1], d_off[1:] - d_off[:-1], self.config, p1 - p0,
+                                                    in_bytes=total, flags=self.flags, out=self.d_decoded[p0:p1])
+                    self.h_decoded[p0:p1].copy_(out, non_blocking=True)
+                    st[nw:].copy_(status, non_blocking=True)
+                return (p0, h_part, offsets)
+
+            parts = []
+            ev = stage_in(0)
+            for j in range(n_sub):
+                ev_next = stage_in(j + 1) if j + 1 < n_sub else None
+                parts.append(stage_out(j, ev))
+                ev = ev_next
+            cur.wait_stream(sa)
+            cur.wait_stream(sb)
+            cur.synchronize()
+            for j in range(n_sub):
+                st = rt["h_st"][j]
+                if int(st[nw].item()):
+                    _raise_for_code(-int(st[nw].item()), int(st[nw + 1].item()) & 0xFFFFFFFFFFFFFFFF)
+        return self.h_decoded, parts
+
     def decompress_host(self, h_streams, offsets):
         """Inverse of compress_host; returns a uint8 host tensor [n, H, W]."""
         total = int(offsets[-1])

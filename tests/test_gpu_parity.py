@@ -280,3 +280,22 @@ def test_batch_equals_per_plane_and_sharding_concatenates(jb):
         else:
             parts.append([])
     assert jb.sharding.concat_band_streams(parts)[0] == whole
+
+
+def test_pipelined_host_round_trip_equals_the_two_calls(jb):
+    """BatchCodec.roundtrip_host (sub-batches pipelined on two streams) returns what compress_host
+    followed by decompress_host returns, and its per-sub-batch streams concatenate to the same bytes."""
+    import torch
+    h, w, n = 136, 264, 10
+    cfg, _ = _cfgs(jb, (h, w, 4, 8, "DCT", "qtable", None))
+    planes = np.stack([synth_plane(h, w, 60 + i) for i in range(n)]).astype(np.uint8)
+    hp = torch.from_numpy(planes).pin_memory()
+    bc = jb.BatchCodec(cfg, n)
+    hs, offs = bc.compress_host(hp)
+    ref_streams = hs.numpy().tobytes()
+    ref_dec = bc.decompress_host(hs, offs).clone()
+    for n_sub in (1, 3, 10):
+        dec, parts = bc.roundtrip_host(hp, n_sub)
+        assert torch.equal(dec, ref_dec)
+        assert [p[0] for p in parts] == [n * j // n_sub for j in range(n_sub)]
+        assert b"".join(p[1].numpy().tobytes() for p in parts) == ref_streams
