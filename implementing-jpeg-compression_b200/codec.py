@@ -125,7 +125,7 @@ class _Workspace:
 _workspace = _Workspace()
 
 
-def compress_planes(planes, config, flags=0, out=None):
+def compress_planes(planes, config, flags=0, out=None, ws=None):
     """Compress a batch of equally sized planes that already live on the GPU.
 
     ``planes``: uint8 CUDA tensor [n, H, W] (or [H, W]); rows contiguous.  Returns a
@@ -154,7 +154,10 @@ def compress_planes(planes, config, flags=0, out=None):
         _raise_for_code(lib.jb_geometry_of(ctypes.byref(p), ctypes.byref(g)))
     ws_bytes = lib.jb_compress_workspace_bytes(ctypes.byref(p), n)
     with torch.cuda.device(dev):
-        ws = _workspace.get("fwd", ws_bytes, dev)
+        if ws is None:
+            ws = _workspace.get("fwd", ws_bytes, dev)
+        elif ws.numel() < ws_bytes:
+            raise ValueError("workspace too small: %d < %d bytes" % (ws.numel(), ws_bytes))
         if out is None:
             out = torch.empty(cap, dtype=torch.uint8, device=dev)
         offsets = torch.empty(n + 1, dtype=torch.int64, device=dev)
@@ -166,7 +169,7 @@ def compress_planes(planes, config, flags=0, out=None):
     return CompressedPlanes(out, offsets, status, n)
 
 
-def decompress_planes(data, offsets, lengths, config, n_planes, in_bytes=None, flags=0, out=None):
+def decompress_planes(data, offsets, lengths, config, n_planes, in_bytes=None, flags=0, out=None, ws=None):
     """Decompress ``n_planes`` streams held in the device buffer ``data``.
 
     ``offsets`` / ``lengths``: int64 CUDA tensors [n_planes].  ``in_bytes``: host-known upper
@@ -183,7 +186,10 @@ def decompress_planes(data, offsets, lengths, config, n_planes, in_bytes=None, f
         _raise_for_code(lib.jb_geometry_of(ctypes.byref(p), ctypes.byref(g)))
     h, w = int(config.height), int(config.width)
     with torch.cuda.device(dev):
-        ws = _workspace.get("inv", ws_bytes, dev)
+        if ws is None:
+            ws = _workspace.get("inv", ws_bytes, dev)
+        elif ws.numel() < ws_bytes:
+            raise ValueError("workspace too small: %d < %d bytes" % (ws.numel(), ws_bytes))
         if out is None:
             out = torch.empty((n_planes, h, w), dtype=torch.uint8, device=dev)
         status = torch.empty(_lib.JB_STATUS_WORDS, dtype=torch.int64, device=dev)
@@ -292,19 +298,42 @@ class BatchCodec:
             self.d_planes = torch.empty((self.n_planes, self.h, self.w), dtype=torch.uint8, device=self.device)
             self.d_streams = torch.empty(self.cap, dtype=torch.uint8, device=self.device)
             self.d_decoded = torch.empty((self.n_planes, self.h, self.w), dtype=torch.uint8, device=self.device)
+            # private workspaces: their table region is built by the first call of each direction and
+            # reused by the later ones (JB_FLAG_REUSE_TABLES); nothing else ever writes to them
+            self._ws_fwd = torch.empty(max(256, lib.jb_compress_workspace_bytes(ctypes.byref(p), self.n_planes)),
+                                       dtype=torch.uint8, device=self.device)
+            self._ws_inv = torch.empty(256, dtype=torch.uint8, device=self.device)      # sized by the first call
+        self._tables_fwd = self._tables_inv = False
         self.pinned = pinned
         self.h_streams = None
         self.h_decoded = None
 
+    def _compress(self, planes, out):
+        fl = self.flags | (_lib.JB_FLAG_REUSE_TABLES if self._tables_fwd else 0)
+        comp = compress_planes(planes, self.config, flags=fl, out=out, ws=self._ws_fwd)
+        self._tables_fwd = True
+        return comp
+
+    def _decompress(self, data, offsets, lengths, n_planes, in_bytes, out):
+        p = self.config.c_params(self.flags)
+        need = _lib.load().jb_decompress_workspace_bytes(ctypes.byref(p), int(n_planes), int(in_bytes))
+        if self._ws_inv.numel() < need:                    # the layout depends on the stream bytes: grow, rebuild tables
+            with torch.cuda.device(self.device):
+                self._ws_inv = torch.empty(int(need) + (int(need) >> 2), dtype=torch.uint8, device=self.device)
+            self._tables_inv = False
+        fl = self.flags | (_lib.JB_FLAG_REUSE_TABLES if self._tables_inv else 0)
+        res = decompress_planes(data, offsets, lengths, self.config, n_planes, in_bytes=in_bytes, flags=fl, out=out,
+                                ws=self._ws_inv)
+        self._tables_inv = True
+        return res
+
     # -- device-resident --------------------------------------------------------------------
     def compress_device(self, planes=None):
-        return compress_planes(self.d_planes if planes is None else planes, self.config, flags=self.flags,
-                               out=self.d_streams)
+        return self._compress(self.d_planes if planes is None else planes, self.d_streams)
 
     def decompress_device(self, comp, total_bytes):
         lengths = comp.offsets[1:] - comp.offsets[:-1]
-        return decompress_planes(comp.data, comp.offsets[:-1], lengths, self.config, self.n_planes,
-                                 in_bytes=int(total_bytes), flags=self.flags, out=self.d_decoded)
+        return self._decompress(comp.data, comp.offsets[:-1], lengths, self.n_planes, int(total_bytes), self.d_decoded)
 
     # -- host buffers in, host buffers out ------------------------------------------------------
     def compress_host(self, h_planes):
@@ -363,8 +392,7 @@ class BatchCodec:
                 p0, p1 = bounds[j], bounds[j + 1]
                 with torch.cuda.stream(sa):
                     self.d_planes[p0:p1].copy_(h_planes[p0:p1], non_blocking=True)
-                    comp = compress_planes(self.d_planes[p0:p1], self.config, flags=self.flags,
-                                           out=rt["d_work"][cap0[j]:cap0[j] + caps[j]])
+                    comp = self._compress(self.d_planes[p0:p1], rt["d_work"][cap0[j]:cap0[j] + caps[j]])
                     rt["h_off"][j].copy_(comp.offsets, non_blocking=True)
                     rt["h_st"][j][:nw].copy_(comp.status, non_blocking=True)
                     ev = torch.cuda.Event()
@@ -387,8 +415,8 @@ class BatchCodec:
                     d_in = rt["d_back"][cap0[j]:cap0[j] + caps[j]]
                     d_in[:total].copy_(h_part, non_blocking=True)                                 # host -> device
                     d_off = rt["h_off"][j].to(self.device, non_blocking=True)
-                    out, status = decompress_planes(d_in, d_off[:-1], d_off[1:] - d_off[:-1], self.config, p1 - p0,
-                                                    in_bytes=total, flags=self.flags, out=self.d_decoded[p0:p1])
+                    out, status = self._decompress(d_in, d_off[:-1], d_off[1:] - d_off[:-1], p1 - p0, total,
+                                                   self.d_decoded[p0:p1])
                     self.h_decoded[p0:p1].copy_(out, non_blocking=True)
                     st[nw:].copy_(status, non_blocking=True)
                 return (p0, h_part, offsets)
@@ -414,8 +442,7 @@ class BatchCodec:
         self.d_streams[:total].copy_(h_streams[:total], non_blocking=True)
         d_off = torch.from_numpy(np.ascontiguousarray(offsets, dtype=np.int64)).to(self.device, non_blocking=True)
         lengths = d_off[1:] - d_off[:-1]
-        out, status = decompress_planes(self.d_streams, d_off[:-1], lengths, self.config, self.n_planes,
-                                        in_bytes=total, flags=self.flags, out=self.d_decoded)
+        out, status = self._decompress(self.d_streams, d_off[:-1], lengths, self.n_planes, total, self.d_decoded)
         if self.h_decoded is None:
             self.h_decoded = torch.empty((self.n_planes, self.h, self.w), dtype=torch.uint8, pin_memory=self.pinned)
         self.h_decoded.copy_(out, non_blocking=True)

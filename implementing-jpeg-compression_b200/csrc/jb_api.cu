@@ -116,7 +116,7 @@ static int jb_forward_common(int mode, const uint8_t* d_planes, size_t plane_str
     a.tmp = (uint8_t*)(ws + w.tmp);
     a.chunk_cap = w.chunk_cap;
     a.coeffs_out = d_coeffs_out; a.coeffs_in = d_coeffs_in;
-    if (mode != 2) JB_CUDA_TRY(jb_launch_build_tables(g, a.t, s));
+    if (mode != 2 && !(g.flags & JB_FLAG_REUSE_TABLES)) JB_CUDA_TRY(jb_launch_build_tables(g, a.t, s));
     if (mode != 2 && !(g.flags & JB_FLAG_FORCE_GENERIC) && jb_fwd_fast_eligible(g))
         JB_CUDA_TRY(jb_launch_fwd_fast(a, mode, s));
     else if (mode != 2 && !(g.flags & JB_FLAG_FORCE_GENERIC) && jb_fwd_mid_eligible(g))
@@ -233,7 +233,7 @@ static int jb_inverse_common(int mode, const uint8_t* d_in, size_t in_bytes, con
     } else if (ws_bytes < table_bytes) {
         return JB_ERR_WORKSPACE;
     }
-    if (mode != 1) JB_CUDA_TRY(jb_launch_build_tables(g, a.t, s));
+    if (mode != 1 && !(g.flags & JB_FLAG_REUSE_TABLES)) JB_CUDA_TRY(jb_launch_build_tables(g, a.t, s));
     if (mode != 1 && !(g.flags & JB_FLAG_FORCE_GENERIC) && jb_inv_fast_eligible(g))
         JB_CUDA_TRY(jb_launch_inv_fast(a, mode, s));
     else if (mode != 1 && !(g.flags & JB_FLAG_FORCE_GENERIC) && jb_inv_mid_eligible(g))
