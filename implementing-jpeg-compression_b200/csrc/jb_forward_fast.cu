@@ -27,7 +27,7 @@
 #include "jb_fast_common.cuh"
 #include "jb_forward.cuh"
 
-#define FF_WARPS 14
+#define FF_WARPS 16
 #define FF_RING 2
 #define FF_STAGE_W 17       // words per packed-bytes row: 64 bytes + 1 word (odd stride)
 #define FF_STAGE_CAP 16     // words a block may occupy in its staging row; longer blocks take the slow path
@@ -35,10 +35,9 @@
 #define FF_COMPACT_BYTES (JB_CHUNK * FF_COEF_W * 4)   // the coefficient rows double as the compaction buffer
 
 struct __align__(128) FfWarpSmem {
-    uint8_t tile[FF_RING][FF_TILE_BYTES];
+    uint8_t tile[FF_RING][FF_TILE_BYTES];   // the slot just consumed doubles as the packed-bytes staging rows
     float scr[4 * FF_BLK_W];            // row-pass results [block][row][col]; on demand also the box sums
     uint32_t coef[JB_CHUNK * FF_COEF_W];
-    uint32_t stage[JB_CHUNK * FF_STAGE_W];
     unsigned long long bar[FF_RING];
     int big_blk[FF_BIG_CAP], big_pos[FF_BIG_CAP], big_amp[FF_BIG_CAP];
     int nbig;
@@ -386,10 +385,13 @@ jb_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfKernelArgs 
 
         if (MODE == 0 && cc.it + 1 == cc.nit) {
             // ---- A9 + A10: lane t packs block t into its (small) staging row ----
+            // (the chunk's last tile has been consumed: its ring slot holds the staging rows until the next
+            // TMA load is issued into it, behind a proxy fence)
+            uint32_t* stage = (uint32_t*)ws.tile[slot];
             unsigned len = 0;
             if (lane < cc.nvalid) {
                 JbBitWriter bw;
-                bw.init(ws.stage + lane * FF_STAGE_W, FF_STAGE_CAP);
+                bw.init(stage + lane * FF_STAGE_W, FF_STAGE_CAP);
                 int bad_pos, bad_run;
                 ff_pack_block(ws.coef + lane * FF_COEF_W, bw, bad_pos, bad_run);
                 len = bw.finish();
@@ -418,7 +420,7 @@ jb_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfKernelArgs 
                 // write the chunk with 128-bit stores; the slot is 16-byte aligned
                 __syncwarp();
                 uint8_t* cbuf = (uint8_t*)ws.coef;
-                const uint8_t* sb = (const uint8_t*)(ws.stage + lane * FF_STAGE_W);
+                const uint8_t* sb = (const uint8_t*)(stage + lane * FF_STAGE_W);
                 for (unsigned j = 0; j < len; ++j) cbuf[excl + j] = sb[j];
                 __syncwarp();
                 const uint4* c16 = (const uint4*)cbuf;
