@@ -20,7 +20,7 @@
 #include "jb_fast_common.cuh"
 #include "jb_inverse.cuh"
 
-#define FI_WARPS 14
+#define FI_WARPS 16
 #define FI_RING 2
 #define FI_STREAM_WORDS 400             // staged chunk bytes (1.6 KB; the average chunk is ~0.6 KB); denser
                                         // chunks are decoded straight from global memory
@@ -29,7 +29,6 @@ struct __align__(128) FiWarpSmem {
     uint8_t tile[FI_RING][FF_TILE_BYTES];
     float scr[4 * FF_BLK_W];
     uint32_t coef[JB_CHUNK * FF_COEF_W];
-    uint32_t sbytes[FI_STREAM_WORDS];
 };
 
 struct FiKernelArgs {
@@ -141,15 +140,20 @@ jb_inv_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FiKernelArgs 
             const uint32_t* wsrc = (const uint32_t*)(uintptr_t)(addr0 - mis);
             const unsigned nwords = ok ? (((c_end - c_start) + mis + 3u) >> 2) : 0u;
             const bool staged = nwords <= FI_STREAM_WORDS;
+            // the chunk's bytes are staged in the ring slot that the next tile will use: the store issued
+            // from it two tiles ago has to be done reading it
+            uint32_t* sbytes = (uint32_t*)ws.tile[store_seq % FI_RING];
+            if (lane == 0) ff_bulk_wait_read<FI_RING - 1>();
+            __syncwarp();
             if (ok && staged)
-                for (unsigned i = lane; i < nwords; i += 32) ws.sbytes[i] = __ldg(wsrc + i);
+                for (unsigned i = lane; i < nwords; i += 32) sbytes[i] = __ldg(wsrc + i);
             __syncwarp();
             int bad = ok ? 0 : 1;
             if (ok && lane < nvalid) {
                 int16_t* row = (int16_t*)(ws.coef + lane * FF_COEF_W);
                 const uint32_t bit0 = (my_start - c_start + mis) * 8u, bitl = (c_end - c_start + mis) * 8u;
                 if (my_start < c_start || my_start >= c_end) bad = 1;
-                else if (staged) bad = fi_decode_block<false>(ws.sbytes, nwords, bit0, bitl, row, s_izz);
+                else if (staged) bad = fi_decode_block<false>(sbytes, nwords, bit0, bitl, row, s_izz);
                 else bad = fi_decode_block<true>(wsrc, nwords, bit0, bitl, row, s_izz);
             }
             if (__any_sync(0xffffffffu, bad) && lane == 0) jb_set_error(a.status, JB_ERR_BAD_STREAM);
