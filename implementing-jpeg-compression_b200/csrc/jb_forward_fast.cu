@@ -157,8 +157,8 @@ __device__ __forceinline__ void ff_pack_block(const uint32_t* rowp, Writer& bw, 
         if (q4 < 4) lo |= m << (8 * q4); else hi |= m << (8 * (q4 - 4));
     }
     const int16_t* c16 = (const int16_t*)rowp;
-    int prev = -1;
-    bad_pos = -1; bad_run = 0;
+    int prev = -1, bad_prev = 0;
+    bad_pos = -1;
     #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
         uint32_t m = half ? hi : lo;
@@ -167,10 +167,20 @@ __device__ __forceinline__ void ff_pack_block(const uint32_t* rowp, Writer& bw, 
             m &= m - 1;
             const int amp = c16[p];
             const int run = p - prev - 1;
+            const uint32_t mag = (uint32_t)(amp < 0 ? -amp : amp);
+            if (mag > (uint32_t)JB_MAX_AMP) {                    // BadRleCodeError in the reference: nothing is emitted
+                if (bad_pos < 0) { bad_pos = p; bad_prev = prev; }
+                prev = p;
+                continue;
+            }
             prev = p;
-            if (!jb_put_coefficient(bw, run, amp) && bad_pos < 0) { bad_pos = p; bad_run = run % JB_MAX_RUN; }
+            int r = run;
+            while (r >= JB_MAX_RUN) { bw.put(0xF0u, 8); r -= JB_MAX_RUN; }
+            const int size = 33 - __clz((int)mag);               // bit length + 1 (mag >= 1)
+            bw.put(((((uint32_t)r << 4) | (uint32_t)size) << size) | ((amp > 0 ? 1u : 0u) << (size - 1)) | mag, 8 + size);
         }
     }
+    bad_run = bad_pos >= 0 ? (bad_pos - bad_prev - 1) % JB_MAX_RUN : 0;
     bw.put(0u, 8);
 }
 
