@@ -245,10 +245,13 @@ jb_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfKernelArgs 
         if (first >= a.n_chunks) return;
         ff_cursor_set(cc, first, g);
     }
+    // Generic-proxy writes into a ring slot (edge-tile fills, the staging rows of the pack stage) must be
+    // ordered before the TMA engine writes the slot again; tiles that were only read need no proxy fence.
+    bool dirty = true;
     auto issue = [&](FfCursor& c, int slot) {
         c.kind = ff_cursor_kind(c, g, aligned);
         if (use_tma && c.kind == 0 && lane == 0) {
-            ff_fence_proxy_async();
+            if (dirty) ff_fence_proxy_async();
             ff_mbar_expect_tx(&ws.bar[slot], FF_TILE_BYTES);
             ff_tma_load_3d(ws.tile[slot], &tmap, c.bx * 32, c.by * 32, c.plane, &ws.bar[slot]);
         }
@@ -272,24 +275,25 @@ jb_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfKernelArgs 
             if (have_next) ff_cursor_set(nx, c2, g);
         }
         if (have_next) issue(nx, slot ^ 1);
+        dirty = false;
 
         {
-            const uint8_t* plane_ptr = a.planes + (size_t)cc.plane * a.plane_stride;
             uint8_t* tile = ws.tile[slot];
             const int kind = cc.kind;
             if (kind == 0 && use_tma) {
                 const uint32_t par = (phasebits >> slot) & 1u;
-                int spins = 0;
-                while (!ff_mbar_try_wait(&ws.bar[slot], par)) {
-                    if (++spins > (1 << 24)) { if (lane == 0) jb_set_error(a.status, JB_ERR_CUDA); break; }
-                }
+                while (!ff_mbar_try_wait(&ws.bar[slot], par)) { }
                 phasebits ^= 1u << slot;
             } else if (kind <= 1) {
+                const uint8_t* plane_ptr = a.planes + (size_t)cc.plane * a.plane_stride;
                 ff_fill_rows(tile, plane_ptr, a.row_pitch, g, cc.by, cc.bx, lane);
+                dirty = true;
                 __syncwarp();
             } else {
+                const uint8_t* plane_ptr = a.planes + (size_t)cc.plane * a.plane_stride;
                 const FfEdgeGeom eg = {g.hb, g.H, g.W, g.H1, g.W1};
                 ff_fill_clamped(tile, plane_ptr, a.row_pitch, eg, cc.blk0 + 4 * cc.it, jb_min(4, cc.nvalid - 4 * cc.it), lane);
+                dirty = true;
                 __syncwarp();
             }
 
@@ -398,6 +402,7 @@ jb_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfKernelArgs 
             // (the chunk's last tile has been consumed: its ring slot holds the staging rows until the next
             // TMA load is issued into it, behind a proxy fence)
             uint32_t* stage = (uint32_t*)ws.tile[slot];
+            dirty = true;
             unsigned len = 0;
             if (lane < cc.nvalid) {
                 JbBitWriter bw;
