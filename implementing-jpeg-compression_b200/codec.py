@@ -259,6 +259,53 @@ def decompress_bands(streams, config, flags=0):
     return out.cpu().numpy()
 
 
+def rgb_to_ycbcr_planes(rgb, out=None):
+    """PIL's ``image.convert('YCbCr')`` on the device, bit-identical (compress.py:9).
+
+    ``rgb``: uint8 CUDA tensor [n, H, W, 3] or [H, W, 3], interleaved.  Returns uint8 planes
+    [3 n, H, W]: image i owns planes 3i (Y), 3i + 1 (Cb), 3i + 2 (Cr) -- the order
+    ``compress_planes`` expects for a batch of images.  Asynchronous on the current stream."""
+    lib = _lib.load()
+    if rgb.dim() == 3:
+        rgb = rgb.unsqueeze(0)
+    if rgb.dim() != 4 or rgb.shape[3] != 3:
+        raise BadArrayShapeError(tuple(rgb.shape))
+    if rgb.dtype != torch.uint8 or not rgb.is_cuda:
+        raise TypeError("rgb_to_ycbcr_planes expects a uint8 CUDA tensor")
+    rgb = rgb.contiguous()
+    n, h, w, _ = rgb.shape
+    if n == 0 or h == 0 or w == 0:
+        raise EmptyArrayError()
+    with torch.cuda.device(rgb.device):
+        if out is None:
+            out = torch.empty((3 * n, h, w), dtype=torch.uint8, device=rgb.device)
+        rc = lib.jb_rgb_to_ycbcr_planes(_ptr(rgb), rgb.stride(0), rgb.stride(1), n, h, w,
+                                        _ptr(out), out.stride(0), out.stride(1), _stream_ptr())
+    _raise_for_code(rc)
+    return out
+
+
+def ycbcr_planes_to_rgb(planes, out=None):
+    """PIL's ``image.convert('RGB')`` of a YCbCr image on the device, bit-identical (decompress.py:10).
+    ``planes``: uint8 CUDA tensor [3 n, H, W] as produced by ``decompress_planes``; returns [n, H, W, 3]."""
+    lib = _lib.load()
+    if planes.dim() != 3 or planes.shape[0] % 3 != 0:
+        raise BadArrayShapeError(tuple(planes.shape))
+    if planes.dtype != torch.uint8 or not planes.is_cuda:
+        raise TypeError("ycbcr_planes_to_rgb expects a uint8 CUDA tensor")
+    planes = planes.contiguous()
+    n3, h, w = planes.shape
+    if n3 == 0 or h == 0 or w == 0:
+        raise EmptyArrayError()
+    with torch.cuda.device(planes.device):
+        if out is None:
+            out = torch.empty((n3 // 3, h, w, 3), dtype=torch.uint8, device=planes.device)
+        rc = lib.jb_ycbcr_planes_to_rgb(_ptr(planes), planes.stride(0), planes.stride(1), n3 // 3, h, w,
+                                        _ptr(out), out.stride(0), out.stride(1), _stream_ptr())
+    _raise_for_code(rc)
+    return out
+
+
 class Jpeg:
     """pipeline.Jpeg (pipeline/__init__.py:98-124) on the CUDA path: the three bands of an
     image go through one batched launch each way; the container is the reference's."""
@@ -278,6 +325,30 @@ class Jpeg:
         planes = decompress_bands([data.y, data.cb, data.cr], config)
         # np.dstack(...).astype(np.uint8) -> Image.fromarray(mode='YCbCr'), :120-124
         return Image.merge("YCbCr", [Image.fromarray(np.ascontiguousarray(planes[i]), "L") for i in range(3)])
+
+    # The two CLI flows with the colour conversion on the device as well:
+    def compress_rgb(self, image):
+        """``Jpeg(config).compress(image.convert('YCbCr'))`` of compress.py:9-17, byte-identical; the RGB image
+        crosses to the GPU once, interleaved, and is converted there."""
+        rgb = torch.from_numpy(np.ascontiguousarray(np.asarray(image.convert("RGB"), dtype=np.uint8))).to(_require_cuda())
+        comp = compress_planes(rgb_to_ycbcr_planes(rgb), self.config)
+        y, cb, cr = comp.to_bytes_list()
+        return file_format.generate_data(self.config, file_format.CompressedData(y, cb, cr))
+
+    @staticmethod
+    def decompress_rgb(bytestream):
+        """``Jpeg.decompress(data).convert('RGB')`` of decompress.py:9-10, identical pixels."""
+        from PIL import Image
+        config, data = file_format.read_data(bytestream)
+        dev = _require_cuda()
+        streams = [data.y, data.cb, data.cr]
+        blob = torch.from_numpy(np.frombuffer(b"".join(streams), dtype=np.uint8).copy()).to(dev)
+        lens = torch.tensor([len(x) for x in streams], dtype=torch.int64)
+        offs = (torch.cumsum(lens, 0) - lens).to(dev)
+        planes, status = decompress_planes(blob, offs, lens.to(dev), config, 3, in_bytes=int(lens.sum()))
+        rgb = ycbcr_planes_to_rgb(planes)
+        check_status(status)
+        return Image.fromarray(rgb[0].cpu().numpy(), "RGB")
 
 
 class BatchCodec:

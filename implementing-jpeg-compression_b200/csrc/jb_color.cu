@@ -1,0 +1,207 @@
+// jb_color.cu -- RGB <-> YCbCr on the device, bit-identical to Pillow's Image.convert (the step on either side of
+// the codec path: compress.py:9 `convert('YCbCr')`, decompress.py:10 `convert('RGB')`, consumed by
+// pipeline/__init__.py:103-106 and produced by :120-124).  SURVEY.md section 8(f) row 1.
+//
+// Pillow converts with per-channel lookup tables in 6-bit fixed point; jb_color_tables.h holds tables that were fitted
+// against Pillow on all 2^24 inputs (tools/derive_pil_tables.py) and reproduce it exactly:
+//   y, cb, cr = (T[0][r] + T[1][g] + T[2][b]) >> 6
+//   r = clip(y + (R_CR[cr] >> 6)),  g = clip(y + ((G_CB[cb] + G_CR[cr]) >> 6)),  b = clip(y + (B_CB[cb] >> 6))
+// Both kernels are HBM-bound byte shuffles: interleaved pixels on one side (3 bytes per pixel, what PIL hands over),
+// three planes on the other (what jb_compress_planes reads / jb_decompress_planes writes).  A thread owns 16 pixels of
+// a row: three 128-bit accesses on the interleaved side, one per plane.  Forward, the three contributions of an input
+// byte are packed into one 64-bit shared-memory word (three 20-bit fields, biased by multiples of 64 to stay positive),
+// so a pixel costs three table reads and two 64-bit adds.
+#include "jb_common.cuh"
+#include "jb_color_tables.h"
+
+#define JC_THREADS 256
+#define JC_FIELD 20
+#define JC_BIAS (64 * 512)                  // per table and field: makes every packed contribution non-negative
+
+__constant__ int16_t c_fwd[3][768];          // [y|cb|cr][input channel * 256 + value]
+__constant__ int16_t c_inv[4][256];          // r_cr, g_cb, g_cr, b_cb
+
+static cudaError_t jc_upload_tables() {
+    static bool done = false;                // per process and device context; tables are constants
+    static int done_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (done && done_dev == dev) return cudaSuccess;
+    cudaError_t e;
+    if ((e = cudaMemcpyToSymbol(c_fwd, JB_RGB2YCC_Y, sizeof(JB_RGB2YCC_Y), 0)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(c_fwd, JB_RGB2YCC_CB, sizeof(JB_RGB2YCC_CB), sizeof(JB_RGB2YCC_Y))) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(c_fwd, JB_RGB2YCC_CR, sizeof(JB_RGB2YCC_CR), 2 * sizeof(JB_RGB2YCC_Y))) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(c_inv, JB_YCC2RGB_R_CR, 512, 0)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(c_inv, JB_YCC2RGB_G_CB, 512, 512)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(c_inv, JB_YCC2RGB_G_CR, 512, 1024)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(c_inv, JB_YCC2RGB_B_CB, 512, 1536)) != cudaSuccess) return e;
+    done = true; done_dev = dev;
+    return cudaSuccess;
+}
+
+struct JcArgs {
+    const uint8_t* src;
+    uint8_t* dst;
+    size_t image_stride, rgb_pitch;          // interleaved side
+    size_t plane_stride, plane_pitch;        // planar side: planes 3i, 3i+1, 3i+2 of image i
+    int n_images, H, W;
+    int vec_ok;                              // 16-byte alignment of every row on both sides
+};
+
+__device__ __forceinline__ uint32_t jc_byte(uint32_t w, int k) { return (w >> (8 * k)) & 0xFFu; }
+
+// ---- interleaved RGB -> planes Y, Cb, Cr ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(JC_THREADS) jb_rgb_to_ycc_kernel(JcArgs a) {
+    __shared__ unsigned long long s_t[3][256];           // per input channel: y | cb << 20 | cr << 40, biased
+    for (int i = threadIdx.x; i < 768; i += JC_THREADS) {
+        const int ch = i >> 8, v = i & 255;
+        const unsigned long long y = (unsigned long long)(c_fwd[0][ch * 256 + v] + JC_BIAS);
+        const unsigned long long cb = (unsigned long long)(c_fwd[1][ch * 256 + v] + JC_BIAS);
+        const unsigned long long cr = (unsigned long long)(c_fwd[2][ch * 256 + v] + JC_BIAS);
+        s_t[ch][v] = y | (cb << JC_FIELD) | (cr << (2 * JC_FIELD));
+    }
+    __syncthreads();
+    const int groups = (a.W + 15) >> 4;                  // 16-pixel groups per row
+    const long long total = (long long)a.n_images * a.H * groups;
+    const uint32_t unbias = 3u * JC_BIAS >> 6;
+    for (long long t = blockIdx.x * (long long)JC_THREADS + threadIdx.x; t < total; t += (long long)gridDim.x * JC_THREADS) {
+        const int gx = (int)(t % groups);
+        const long long ry = t / groups;
+        const int y = (int)(ry % a.H), img = (int)(ry / a.H);
+        const int x0 = gx * 16;
+        const uint8_t* in = a.src + (size_t)img * a.image_stride + (size_t)y * a.rgb_pitch + (size_t)x0 * 3;
+        uint8_t* out = a.dst + (size_t)(3 * img) * a.plane_stride + (size_t)y * a.plane_pitch + x0;
+        const int npx = min(16, a.W - x0);
+        if (!(a.vec_ok && npx == 16)) {
+            // ragged row end or unaligned buffers: pixel by pixel
+            for (int k = 0; k < npx; ++k) {
+                const unsigned long long s = s_t[0][in[3 * k]] + s_t[1][in[3 * k + 1]] + s_t[2][in[3 * k + 2]];
+                out[k] = (uint8_t)((((uint32_t)s & 0xFFFFFu) >> 6) - unbias);
+                out[a.plane_stride + k] = (uint8_t)((((uint32_t)(s >> JC_FIELD) & 0xFFFFFu) >> 6) - unbias);
+                out[2 * a.plane_stride + k] = (uint8_t)((((uint32_t)(s >> (2 * JC_FIELD)) & 0xFFFFFu) >> 6) - unbias);
+            }
+            continue;
+        }
+        const uint4* in16 = (const uint4*)in;
+        const uint4 q0 = __ldg(in16), q1 = __ldg(in16 + 1), q2 = __ldg(in16 + 2);
+        const uint32_t w[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+        uint32_t oy[4], ocb[4], ocr[4];
+        #pragma unroll
+        for (int g4 = 0; g4 < 4; ++g4) {                 // 4 pixels = 3 words
+            const uint32_t a0 = w[3 * g4], a1 = w[3 * g4 + 1], a2 = w[3 * g4 + 2];
+            const uint32_t r[4] = {jc_byte(a0, 0), jc_byte(a0, 3), jc_byte(a1, 2), jc_byte(a2, 1)};
+            const uint32_t g[4] = {jc_byte(a0, 1), jc_byte(a1, 0), jc_byte(a1, 3), jc_byte(a2, 2)};
+            const uint32_t b[4] = {jc_byte(a0, 2), jc_byte(a1, 1), jc_byte(a2, 0), jc_byte(a2, 3)};
+            uint32_t py = 0, pcb = 0, pcr = 0;
+            #pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const unsigned long long s = s_t[0][r[k]] + s_t[1][g[k]] + s_t[2][b[k]];
+                const uint32_t vy = ((uint32_t)s & 0xFFFFFu) >> 6;
+                const uint32_t vcb = ((uint32_t)(s >> JC_FIELD) & 0xFFFFFu) >> 6;
+                const uint32_t vcr = ((uint32_t)(s >> (2 * JC_FIELD)) & 0xFFFFFu) >> 6;
+                py |= ((vy - unbias) & 0xFFu) << (8 * k);
+                pcb |= ((vcb - unbias) & 0xFFu) << (8 * k);
+                pcr |= ((vcr - unbias) & 0xFFu) << (8 * k);
+            }
+            oy[g4] = py; ocb[g4] = pcb; ocr[g4] = pcr;
+        }
+        *(uint4*)out = make_uint4(oy[0], oy[1], oy[2], oy[3]);
+        *(uint4*)(out + a.plane_stride) = make_uint4(ocb[0], ocb[1], ocb[2], ocb[3]);
+        *(uint4*)(out + 2 * a.plane_stride) = make_uint4(ocr[0], ocr[1], ocr[2], ocr[3]);
+    }
+}
+
+// ---- planes Y, Cb, Cr -> interleaved RGB ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(JC_THREADS) jb_ycc_to_rgb_kernel(JcArgs a) {
+    __shared__ int s_cr[256], s_cb[256];                 // (R_CR >> 6) | G_CR << 16 ;  (B_CB >> 6) | G_CB << 16
+    for (int v = threadIdx.x; v < 256; v += JC_THREADS) {
+        s_cr[v] = ((c_inv[0][v] >> 6) & 0xFFFF) | ((int)c_inv[2][v] << 16);
+        s_cb[v] = ((c_inv[3][v] >> 6) & 0xFFFF) | ((int)c_inv[1][v] << 16);
+    }
+    __syncthreads();
+    const int groups = (a.W + 15) >> 4;
+    const long long total = (long long)a.n_images * a.H * groups;
+    for (long long t = blockIdx.x * (long long)JC_THREADS + threadIdx.x; t < total; t += (long long)gridDim.x * JC_THREADS) {
+        const int gx = (int)(t % groups);
+        const long long ry = t / groups;
+        const int y = (int)(ry % a.H), img = (int)(ry / a.H);
+        const int x0 = gx * 16;
+        const uint8_t* in = a.src + (size_t)(3 * img) * a.plane_stride + (size_t)y * a.plane_pitch + x0;
+        uint8_t* out = a.dst + (size_t)img * a.image_stride + (size_t)y * a.rgb_pitch + (size_t)x0 * 3;
+        const int npx = min(16, a.W - x0);
+        if (!(a.vec_ok && npx == 16)) {
+            for (int k = 0; k < npx; ++k) {
+                const int yy = in[k];
+                const int tcb = s_cb[in[a.plane_stride + k]], tcr = s_cr[in[2 * a.plane_stride + k]];
+                out[3 * k] = (uint8_t)max(0, min(255, yy + (int)(short)(tcr & 0xFFFF)));
+                out[3 * k + 1] = (uint8_t)max(0, min(255, yy + (((tcr >> 16) + (tcb >> 16)) >> 6)));
+                out[3 * k + 2] = (uint8_t)max(0, min(255, yy + (int)(short)(tcb & 0xFFFF)));
+            }
+            continue;
+        }
+        const uint4 q0 = __ldg((const uint4*)in), q1 = __ldg((const uint4*)(in + a.plane_stride)),
+                    q2 = __ldg((const uint4*)(in + 2 * a.plane_stride));
+        const uint32_t wy[4] = {q0.x, q0.y, q0.z, q0.w}, wcb[4] = {q1.x, q1.y, q1.z, q1.w}, wcr[4] = {q2.x, q2.y, q2.z, q2.w};
+        uint32_t o[12];
+        #pragma unroll
+        for (int g4 = 0; g4 < 4; ++g4) {
+            uint32_t px[4];                              // r | g << 8 | b << 16 per pixel
+            #pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int yy = (int)jc_byte(wy[g4], k);
+                const int tcr = s_cr[jc_byte(wcr[g4], k)], tcb = s_cb[jc_byte(wcb[g4], k)];
+                const int r = yy + (int)(short)(tcr & 0xFFFF);
+                const int b = yy + (int)(short)(tcb & 0xFFFF);
+                const int g = yy + (((tcr >> 16) + (tcb >> 16)) >> 6);
+                px[k] = (uint32_t)max(0, min(255, r)) | ((uint32_t)max(0, min(255, g)) << 8) | ((uint32_t)max(0, min(255, b)) << 16);
+            }
+            o[3 * g4] = px[0] | (px[1] << 24);
+            o[3 * g4 + 1] = (px[1] >> 8) | (px[2] << 16);
+            o[3 * g4 + 2] = (px[2] >> 16) | (px[3] << 8);
+        }
+        uint4* o16 = (uint4*)out;
+        o16[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        o16[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        o16[2] = make_uint4(o[8], o[9], o[10], o[11]);
+    }
+}
+
+static int jc_launch(bool forward, const uint8_t* src, uint8_t* dst, size_t image_stride, size_t rgb_pitch,
+                     size_t plane_stride, size_t plane_pitch, int n_images, int H, int W, void* stream) {
+    if (n_images <= 0 || H <= 0 || W <= 0) return JB_ERR_EMPTY_ARRAY;
+    if (!src || !dst || rgb_pitch < (size_t)3 * W || plane_pitch < (size_t)W) return JB_ERR_BAD_PARAM;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return JB_ERR_NO_DEVICE;
+    if (jc_upload_tables() != cudaSuccess) return JB_ERR_CUDA;
+    JcArgs a;
+    a.src = src; a.dst = dst;
+    a.image_stride = image_stride; a.rgb_pitch = rgb_pitch; a.plane_stride = plane_stride; a.plane_pitch = plane_pitch;
+    a.n_images = n_images; a.H = H; a.W = W;
+    const uint8_t* rgb = forward ? src : dst;
+    const uint8_t* pl = forward ? dst : src;
+    a.vec_ok = (((uintptr_t)rgb & 15) == 0 && (image_stride & 15) == 0 && (rgb_pitch & 15) == 0 &&
+                ((uintptr_t)pl & 15) == 0 && (plane_stride & 15) == 0 && (plane_pitch & 15) == 0) ? 1 : 0;
+    const long long total = (long long)n_images * H * ((W + 15) >> 4);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long long want = (total + JC_THREADS - 1) / JC_THREADS;
+    const long long cap = (long long)sms * 8 * 4;        // grid-stride beyond a few waves
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (forward) jb_rgb_to_ycc_kernel<<<grid, JC_THREADS, 0, s>>>(a);
+    else jb_ycc_to_rgb_kernel<<<grid, JC_THREADS, 0, s>>>(a);
+    return cudaGetLastError() == cudaSuccess ? JB_OK : JB_ERR_CUDA;
+}
+
+extern "C" int jb_rgb_to_ycbcr_planes(const uint8_t* d_rgb, size_t image_stride, size_t rgb_pitch, int n_images,
+                                      int height, int width, uint8_t* d_planes, size_t plane_stride, size_t plane_pitch,
+                                      void* stream) {
+    return jc_launch(true, d_rgb, d_planes, image_stride, rgb_pitch, plane_stride, plane_pitch, n_images, height, width, stream);
+}
+
+extern "C" int jb_ycbcr_planes_to_rgb(const uint8_t* d_planes, size_t plane_stride, size_t plane_pitch, int n_images,
+                                      int height, int width, uint8_t* d_rgb, size_t image_stride, size_t rgb_pitch,
+                                      void* stream) {
+    return jc_launch(false, d_planes, d_rgb, image_stride, rgb_pitch, plane_stride, plane_pitch, n_images, height, width, stream);
+}

@@ -177,6 +177,20 @@ int jb_stage_inverse_coeffs(const int16_t* d_coeffs, int n_planes, const jb_para
                             uint8_t* d_planes_out, size_t plane_stride, size_t row_pitch,
                             uint64_t* d_status, void* d_ws, size_t ws_bytes, void* stream);
 
+/* ---- colour conversion on either side of the path -------------------------
+ * Replaces PIL's im.convert('YCbCr') before Jpeg.compress reads the bands (compress.py:9,
+ * pipeline/__init__.py:103-106) and im.convert('RGB') after Jpeg.decompress stacks them (decompress.py:10,
+ * pipeline/__init__.py:120-124).  Bit-identical to Pillow on all 2^24 inputs (tables fitted against Pillow,
+ * tools/derive_pil_tables.py).  d_rgb: interleaved uint8 [n_images][height][width][3] (rgb_pitch bytes per
+ * row, image_stride bytes per image); d_planes: uint8 planes, image i owns planes 3i (Y), 3i+1 (Cb), 3i+2 (Cr)
+ * -- exactly the plane order jb_compress_planes / jb_decompress_planes use for a batch of images. */
+int jb_rgb_to_ycbcr_planes(const uint8_t* d_rgb, size_t image_stride, size_t rgb_pitch, int n_images,
+                           int height, int width, uint8_t* d_planes, size_t plane_stride, size_t plane_pitch,
+                           void* stream);
+int jb_ycbcr_planes_to_rgb(const uint8_t* d_planes, size_t plane_stride, size_t plane_pitch, int n_images,
+                           int height, int width, uint8_t* d_rgb, size_t image_stride, size_t rgb_pitch,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -299,3 +299,50 @@ def test_pipelined_host_round_trip_equals_the_two_calls(jb):
         assert torch.equal(dec, ref_dec)
         assert [p[0] for p in parts] == [n * j // n_sub for j in range(n_sub)]
         assert b"".join(p[1].numpy().tobytes() for p in parts) == ref_streams
+
+
+def test_colour_conversion_matches_pillow_on_every_colour(jb):
+    """jb_rgb_to_ycbcr_planes / jb_ycbcr_planes_to_rgb against the golden hashes of Pillow's conversion of all
+    2^24 inputs (tests/golden/color_tables.json, made by tools/derive_pil_tables.py), and against live Pillow
+    on ragged, unaligned shapes where it is importable."""
+    import hashlib
+    import json
+    import os
+    import torch
+    from test_color_tables import all_colours
+    with open(os.path.join(os.path.dirname(__file__), "golden", "color_tables.json")) as fh:
+        golden = json.load(fh)
+    src = torch.from_numpy(all_colours()).cuda()
+    planes = jb.rgb_to_ycbcr_planes(src)                              # [3, 4096, 4096]
+    ycc = torch.stack([planes[0], planes[1], planes[2]], dim=-1).cpu().numpy()
+    assert hashlib.sha256(ycc.tobytes()).hexdigest() == golden["sha256_rgb_to_ycbcr_all_2^24"]
+    as_planes = src.permute(2, 0, 1).contiguous()                     # the same triples read as (y, cb, cr)
+    rgb = jb.ycbcr_planes_to_rgb(as_planes)[0].cpu().numpy()
+    assert hashlib.sha256(rgb.tobytes()).hexdigest() == golden["sha256_ycbcr_to_rgb_all_2^24"]
+    try:
+        from PIL import Image
+    except ImportError:
+        return
+    rng = np.random.default_rng(11)
+    for n, h, w in ((1, 37, 53), (3, 16, 16), (2, 5, 130)):
+        img = rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)
+        want = np.stack([np.asarray(Image.fromarray(img[i], "RGB").convert("YCbCr")) for i in range(n)])
+        got = jb.rgb_to_ycbcr_planes(torch.from_numpy(img).cuda()).cpu().numpy().reshape(n, 3, h, w)
+        assert np.array_equal(got, want.transpose(0, 3, 1, 2))
+        back = jb.ycbcr_planes_to_rgb(torch.from_numpy(np.ascontiguousarray(img.transpose(0, 3, 1, 2)).reshape(3 * n, h, w)).cuda())
+        want_rgb = np.stack([np.asarray(Image.fromarray(img[i], "YCbCr").convert("RGB")) for i in range(n)])
+        assert np.array_equal(back.cpu().numpy(), want_rgb)
+
+
+def test_rgb_front_ends_equal_the_pillow_flow(jb):
+    """Jpeg.compress_rgb / decompress_rgb == the compress.py / decompress.py flows with PIL's conversions."""
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(21)
+    h, w = 72, 104
+    base = np.stack([synth_plane(h, w, 90 + i) for i in range(3)], axis=-1).astype(np.uint8)
+    img = Image.fromarray(base, "RGB")
+    cfg, _ = _cfgs(jb, (h, w, 4, 8, "DCT", "qtable", None))
+    blob = jb.Jpeg(cfg).compress_rgb(img)
+    assert blob == jb.Jpeg(cfg).compress(img.convert("YCbCr"))
+    out = jb.Jpeg.decompress_rgb(blob)
+    assert np.array_equal(np.asarray(out), np.asarray(jb.Jpeg.decompress(blob).convert("RGB")))

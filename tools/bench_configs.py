@@ -101,8 +101,53 @@ def run(name, h, w, bs, d, transform, qname, qparam, n_images, steps=10, warmup=
     return res
 
 
+def measured_peak():
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return float(json.load(open(pk))["hbm_gbs"]) if os.path.exists(pk) else 6550.1
+
+
+def run_colour(n_img=512, h=1080, w=1920, steps=10, warmup=3, content="synthetic"):
+    """RGB <-> YCbCr kernels: algorithmic bytes = 3 bytes per pixel read + 3 written."""
+    import jpeg_b200 as jb
+    if content == "random":                  # uniform random bytes: worst case for the table lookups (bank conflicts)
+        gen = torch.Generator(device="cuda").manual_seed(5)
+        rgb = torch.randint(0, 256, (n_img, h, w, 3), dtype=torch.uint8, device="cuda", generator=gen)
+    else:                                    # the benchmark's smooth + noise planes, three per image, read as R, G, B
+        import bench
+        bench.H, bench.W = h, w
+        rgb = bench.synth_planes_device(n_img, torch.device("cuda"), 0).view(n_img, 3, h, w).permute(0, 2, 3, 1).contiguous()
+    planes = torch.empty((3 * n_img, h, w), dtype=torch.uint8, device="cuda")
+    back = torch.empty_like(rgb)
+    for _ in range(warmup):
+        jb.rgb_to_ycbcr_planes(rgb, out=planes); jb.ycbcr_planes_to_rgb(planes, out=back)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    torch.cuda.synchronize()
+    ev[0].record()
+    for _ in range(steps):
+        jb.rgb_to_ycbcr_planes(rgb, out=planes)
+    ev[1].record()
+    for _ in range(steps):
+        jb.ycbcr_planes_to_rgb(planes, out=back)
+    ev[2].record()
+    torch.cuda.synchronize()
+    t_f, t_i = ev[0].elapsed_time(ev[1]) / steps, ev[1].elapsed_time(ev[2]) / steps
+    peak = measured_peak()
+    a = 6.0 * n_img * h * w
+    res = {"config": "colour: %d x %dx%d RGB <-> YCbCr planes, %s content" % (n_img, w, h, content), "ms_rgb_to_ycbcr": t_f, "ms_ycbcr_to_rgb": t_i,
+           "rgb_to_ycbcr_GBps": a / (t_f * 1e-3) / 1e9, "ycbcr_to_rgb_GBps": a / (t_i * 1e-3) / 1e9,
+           "rgb_to_ycbcr_frac_of_measured_hbm": a / (t_f * 1e-3) / 1e9 / peak,
+           "ycbcr_to_rgb_frac_of_measured_hbm": a / (t_i * 1e-3) / 1e9 / peak,
+           "MPps_rgb_to_ycbcr": n_img * h * w / 1e6 / (t_f * 1e-3), "MPps_ycbcr_to_rgb": n_img * h * w / 1e6 / (t_i * 1e-3)}
+    print(json.dumps(res), flush=True)
+    return res
+
+
 def main():
     out = []
+    if len(sys.argv) > 1 and sys.argv[1] == "colour":
+        run_colour()
+        run_colour(content="random")
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "config5":
         run("5: 16384x16384 DFT qtable, single image", 16384, 16384, 4, 8, "DFT", "qtable", None, 1, steps=2, warmup=1)
         return
