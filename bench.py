@@ -105,7 +105,7 @@ def run_reference(args, rank):
         "e2e": {"value": v, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_json_line(line)
 
 
 def workload_config(n_gpus):
@@ -200,7 +200,8 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")       # keep NCCL's version banner off stdout
+        # stdout carries exactly one JSON line: NCCL's version banner / debug lines go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
 
     i0, i1 = jb.sharding.image_slice(N_IMAGES, rank, world)
@@ -388,7 +389,7 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": K * 8,
             "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit_json_line(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -431,8 +432,28 @@ def cpu_baseline_with_parity(bc, comp, n_img):
                               "max_pixel_error": maxerr}}
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout must carry exactly one JSON line: keep the real stdout for it and point file descriptor 1 at stderr,
+    so that banners printed by libraries (NCCL's version line, for one) cannot end up in front of it."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit_json_line(line):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     global N_IMAGES
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
