@@ -384,9 +384,9 @@ def run_ours(args, rank, world, local_rank):
                                     "algorithmic_bytes_per_launch": a_d},
             "cpu_baseline": cpu,
             "e2e": e2e,
-# per step: compress = fused kernel, 2 scan kernels, gather (4); decompress = framing prep, walk, stitch
-            # and the fused kernel (4); the table builders run once per codec object, outside the timed region
-            "gpu_launches": K * 8,
+# per step: compress = init, fused kernel, 2 scan kernels, gather (5); decompress = framing prep, walk,
+            # stitch and the fused kernel (4); the table builders run once per codec object, outside the timed region
+            "gpu_launches": K * 9,
             "clocks": clocks,
         }
         emit_json_line(line)

@@ -80,9 +80,17 @@ extern "C" size_t jb_stage_pack_workspace_bytes(int n_planes, int blocks_per_pla
     return jb_fwd_ws(dct_size, (size_t)n_planes * cpp).total;
 }
 
-static int jb_reset_status(uint64_t* d_status, cudaStream_t s) {
-    JB_CUDA_TRY(cudaMemsetAsync(d_status, 0, JB_STATUS_WORDS * sizeof(uint64_t), s));
-    JB_CUDA_TRY(cudaMemsetAsync(d_status + 1, 0xFF, sizeof(uint64_t), s));
+// One small launch instead of three memset nodes: the status block (word 1 = "no bad code yet" = all ones) and,
+// for the compress direction, the chunk ticket.
+__global__ void jb_init_kernel(unsigned long long* status, unsigned* ticket) {
+    const int t = threadIdx.x;
+    if (t < JB_STATUS_WORDS) status[t] = t == 1 ? ~0ull : 0ull;
+    if (ticket && t < 64) ticket[t] = 0u;
+}
+
+static int jb_reset_status(uint64_t* d_status, unsigned* d_ticket, cudaStream_t s) {
+    jb_init_kernel<<<1, 64, 0, s>>>((unsigned long long*)d_status, d_ticket);
+    JB_CUDA_TRY(cudaGetLastError());
     return JB_OK;
 }
 
@@ -96,9 +104,8 @@ static int jb_forward_common(int mode, const uint8_t* d_planes, size_t plane_str
     if (!d_ws || ws_bytes < w.total) return JB_ERR_WORKSPACE;
     if (((uintptr_t)d_ws & 255) != 0) return JB_ERR_BAD_PARAM;
     char* ws = (char*)d_ws;
-    int rc = jb_reset_status(d_status, s);
+    int rc = jb_reset_status(d_status, (unsigned*)(ws + w.ticket), s);
     if (rc != JB_OK) return rc;
-    JB_CUDA_TRY(cudaMemsetAsync(ws + w.ticket, 0, 256, s));
 
     JbFwdArgs a;
     memset(&a, 0, sizeof(a));
@@ -189,8 +196,10 @@ static int jb_inverse_common(int mode, const uint8_t* d_in, size_t in_bytes, con
     const size_t table_bytes = jb_table_layout(g.d).total;
     if (!d_ws || ((uintptr_t)d_ws & 255) != 0) return JB_ERR_WORKSPACE;
     char* ws = (char*)d_ws;
-    int rc = jb_reset_status(d_status, s);
-    if (rc != JB_OK) return rc;
+    if (mode == 2) {                                  // (with framing, jb_frame_prep_kernel resets the status block)
+        int rc = jb_reset_status(d_status, nullptr, s);
+        if (rc != JB_OK) return rc;
+    }
 
     JbInvArgs a;
     memset(&a, 0, sizeof(a));
@@ -224,8 +233,8 @@ static int jb_inverse_common(int mode, const uint8_t* d_in, size_t in_bytes, con
         f.tile_base = (unsigned*)(ws + L.tile_base);
         f.vbits = (uint32_t*)(ws + L.vbits);
         f.status = (unsigned long long*)d_status;
-        // a stream that fails framing leaves block_start unwritten: make it deterministic
-        JB_CUDA_TRY(cudaMemsetAsync(f.block_start, 0xFF, (size_t)n_planes * g.nblocks * 4, s));
+        // (a stream that fails framing leaves its part of block_start unwritten; the call then reports
+        // JB_ERR_BAD_STREAM and the transform kernels check every offset they read against the stream bounds)
         JB_CUDA_TRY(jb_launch_framing(f, s));
         a.in = d_in; a.in_bytes = in_bytes;
         a.plane_off = f.plane_off; a.plane_len = f.plane_len;

@@ -137,6 +137,8 @@ __global__ void __launch_bounds__(1024) jb_frame_prep_kernel(JbFrameArgs f) {
     unsigned carry = 0;
     bool bad = false;
     if (threadIdx.x == 0) f.big_list[0] = 0u;
+    // first kernel of the decompress call: reset the status block (word 1 = "no bad code yet")
+    if (threadIdx.x < JB_STATUS_WORDS) f.status[threadIdx.x] = threadIdx.x == 1 ? ~0ull : 0ull;
     __syncthreads();
     for (int base = 0; base < f.n_planes; base += 1024) {
         int s = base + threadIdx.x;
