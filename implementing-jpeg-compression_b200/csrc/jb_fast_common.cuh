@@ -114,9 +114,14 @@ __device__ __forceinline__ void ff_dft_column_stage(const float (&col)[8], int c
     }
 }
 
+// The output planes are written once and not read again by this call: evict-first keeps the 126 MB L2 from holding
+// them back (measured: about -0.02 ms on the 1024-image decompress, evict-last +0.03 ms; the same hint on the
+// compress kernel's tile loads made no difference).
 __device__ __forceinline__ void ff_tma_store_3d(const CUtensorMap* map, int x, int y, int z, const void* src) {
-    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
-                 :: "l"(map), "r"(x), "r"(y), "r"(z), "r"(ff_smem_u32(src)) : "memory");
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%1, %2, %3}], [%4], %5;"
+                 :: "l"(map), "r"(x), "r"(y), "r"(z), "r"(ff_smem_u32(src)), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void ff_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
