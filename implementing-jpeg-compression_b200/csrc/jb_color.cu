@@ -9,35 +9,20 @@
 // Both kernels are HBM-bound byte shuffles: interleaved pixels on one side (3 bytes per pixel, what PIL hands over),
 // three planes on the other (what jb_compress_planes reads / jb_decompress_planes writes).  A thread owns 16 pixels of
 // a row: three 128-bit accesses on the interleaved side, one per plane.  Forward, the three contributions of an input
-// byte are packed into one 64-bit shared-memory word (three 20-bit fields, biased by multiples of 64 to stay positive),
-// so a pixel costs three table reads and two 64-bit adds.
+// byte are packed into one 64-bit shared-memory word: y at bit 0, cb at bit 26, cr at bit 42.  The negative tables are
+// biased by 8192 each -- 16384 per component in total, which vanishes when the sum is shifted by 6 and cut to a byte --
+// so a pixel costs three table reads and one 64-bit three-way add, and the cb / cr results land byte-aligned in the high
+// word (bits 32..39 and 48..55).
 #include "jb_common.cuh"
-#include "jb_color_tables.h"
+#define JB_COLOR_TABLE_QUAL __constant__
+#include "jb_color_tables.h"                // the tables live in constant memory, initialised when the module loads
 
 #define JC_THREADS 256
-#define JC_FIELD 20
-#define JC_BIAS (64 * 512)                  // per table and field: makes every packed contribution non-negative
-
-__constant__ int16_t c_fwd[3][768];          // [y|cb|cr][input channel * 256 + value]
-__constant__ int16_t c_inv[4][256];          // r_cr, g_cb, g_cr, b_cb
-
-static cudaError_t jc_upload_tables() {
-    static bool done = false;                // per process and device context; tables are constants
-    static int done_dev = -1;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (done && done_dev == dev) return cudaSuccess;
-    cudaError_t e;
-    if ((e = cudaMemcpyToSymbol(c_fwd, JB_RGB2YCC_Y, sizeof(JB_RGB2YCC_Y), 0)) != cudaSuccess) return e;
-    if ((e = cudaMemcpyToSymbol(c_fwd, JB_RGB2YCC_CB, sizeof(JB_RGB2YCC_CB), sizeof(JB_RGB2YCC_Y))) != cudaSuccess) return e;
-    if ((e = cudaMemcpyToSymbol(c_fwd, JB_RGB2YCC_CR, sizeof(JB_RGB2YCC_CR), 2 * sizeof(JB_RGB2YCC_Y))) != cudaSuccess) return e;
-    if ((e = cudaMemcpyToSymbol(c_inv, JB_YCC2RGB_R_CR, 512, 0)) != cudaSuccess) return e;
-    if ((e = cudaMemcpyToSymbol(c_inv, JB_YCC2RGB_G_CB, 512, 512)) != cudaSuccess) return e;
-    if ((e = cudaMemcpyToSymbol(c_inv, JB_YCC2RGB_G_CR, 512, 1024)) != cudaSuccess) return e;
-    if ((e = cudaMemcpyToSymbol(c_inv, JB_YCC2RGB_B_CB, 512, 1536)) != cudaSuccess) return e;
-    done = true; done_dev = dev;
-    return cudaSuccess;
-}
+#define JC_FWD_THREADS 512
+#define JC_FWD_SMEM (3 * 256 * 16 * 8)     // replicated tables of the forward kernel
+#define JC_CB_SHIFT 26                       // field offsets inside the packed table word
+#define JC_CR_SHIFT 42
+#define JC_BIAS 8192                        // added to every table with negative entries (two per chroma component)
 
 struct JcArgs {
     const uint8_t* src;
@@ -51,20 +36,24 @@ struct JcArgs {
 __device__ __forceinline__ uint32_t jc_byte(uint32_t w, int k) { return (w >> (8 * k)) & 0xFFu; }
 
 // ---- interleaved RGB -> planes Y, Cb, Cr ----------------------------------------------------------------------------
-__global__ void __launch_bounds__(JC_THREADS) jb_rgb_to_ycc_kernel(JcArgs a) {
-    __shared__ unsigned long long s_t[3][256];           // per input channel: y | cb << 20 | cr << 40, biased
-    for (int i = threadIdx.x; i < 768; i += JC_THREADS) {
+__global__ void __launch_bounds__(JC_FWD_THREADS) jb_rgb_to_ycc_kernel(JcArgs a) {
+    // per input channel and value: y | cb << 26 | cr << 42, in 16 copies -- lane l of a half-warp reads copy l, which
+    // sits in its own pair of banks, so the (data dependent) table reads never conflict
+    extern __shared__ unsigned long long s_rep[];
+    const int cp = threadIdx.x & 15;
+    for (int i = threadIdx.x >> 4; i < 768; i += JC_FWD_THREADS >> 4) {
         const int ch = i >> 8, v = i & 255;
-        const unsigned long long y = (unsigned long long)(c_fwd[0][ch * 256 + v] + JC_BIAS);
-        const unsigned long long cb = (unsigned long long)(c_fwd[1][ch * 256 + v] + JC_BIAS);
-        const unsigned long long cr = (unsigned long long)(c_fwd[2][ch * 256 + v] + JC_BIAS);
-        s_t[ch][v] = y | (cb << JC_FIELD) | (cr << (2 * JC_FIELD));
+        // cb: the R and G tables are negative, cr: the G and B tables (the +128 << 6 sits in the B tables)
+        const int y = JB_RGB2YCC_Y[ch * 256 + v];
+        const int cb = JB_RGB2YCC_CB[ch * 256 + v] + (ch != 2 ? JC_BIAS : 0);
+        const int cr = JB_RGB2YCC_CR[ch * 256 + v] + (ch != 0 ? JC_BIAS : 0);
+        s_rep[i * 16 + cp] = (unsigned long long)y | ((unsigned long long)cb << JC_CB_SHIFT) | ((unsigned long long)cr << JC_CR_SHIFT);
     }
     __syncthreads();
+    const unsigned long long* t_r = s_rep + cp, * t_g = s_rep + 256 * 16 + cp, * t_b = s_rep + 512 * 16 + cp;
     const int groups = (a.W + 15) >> 4;                  // 16-pixel groups per row
     const long long total = (long long)a.n_images * a.H * groups;
-    const uint32_t unbias = 3u * JC_BIAS >> 6;
-    for (long long t = blockIdx.x * (long long)JC_THREADS + threadIdx.x; t < total; t += (long long)gridDim.x * JC_THREADS) {
+    for (long long t = blockIdx.x * (long long)JC_FWD_THREADS + threadIdx.x; t < total; t += (long long)gridDim.x * JC_FWD_THREADS) {
         const int gx = (int)(t % groups);
         const long long ry = t / groups;
         const int y = (int)(ry % a.H), img = (int)(ry / a.H);
@@ -75,10 +64,10 @@ __global__ void __launch_bounds__(JC_THREADS) jb_rgb_to_ycc_kernel(JcArgs a) {
         if (!(a.vec_ok && npx == 16)) {
             // ragged row end or unaligned buffers: pixel by pixel
             for (int k = 0; k < npx; ++k) {
-                const unsigned long long s = s_t[0][in[3 * k]] + s_t[1][in[3 * k + 1]] + s_t[2][in[3 * k + 2]];
-                out[k] = (uint8_t)((((uint32_t)s & 0xFFFFFu) >> 6) - unbias);
-                out[a.plane_stride + k] = (uint8_t)((((uint32_t)(s >> JC_FIELD) & 0xFFFFFu) >> 6) - unbias);
-                out[2 * a.plane_stride + k] = (uint8_t)((((uint32_t)(s >> (2 * JC_FIELD)) & 0xFFFFFu) >> 6) - unbias);
+                const unsigned long long s = t_r[in[3 * k] * 16] + t_g[in[3 * k + 1] * 16] + t_b[in[3 * k + 2] * 16];
+                out[k] = (uint8_t)((uint32_t)s >> 6);
+                out[a.plane_stride + k] = (uint8_t)(s >> 32);
+                out[2 * a.plane_stride + k] = (uint8_t)(s >> 48);
             }
             continue;
         }
@@ -92,18 +81,16 @@ __global__ void __launch_bounds__(JC_THREADS) jb_rgb_to_ycc_kernel(JcArgs a) {
             const uint32_t r[4] = {jc_byte(a0, 0), jc_byte(a0, 3), jc_byte(a1, 2), jc_byte(a2, 1)};
             const uint32_t g[4] = {jc_byte(a0, 1), jc_byte(a1, 0), jc_byte(a1, 3), jc_byte(a2, 2)};
             const uint32_t b[4] = {jc_byte(a0, 2), jc_byte(a1, 1), jc_byte(a2, 0), jc_byte(a2, 3)};
-            uint32_t py = 0, pcb = 0, pcr = 0;
+            uint32_t lo[4], hi[4];
             #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const unsigned long long s = s_t[0][r[k]] + s_t[1][g[k]] + s_t[2][b[k]];
-                const uint32_t vy = ((uint32_t)s & 0xFFFFFu) >> 6;
-                const uint32_t vcb = ((uint32_t)(s >> JC_FIELD) & 0xFFFFFu) >> 6;
-                const uint32_t vcr = ((uint32_t)(s >> (2 * JC_FIELD)) & 0xFFFFFu) >> 6;
-                py |= ((vy - unbias) & 0xFFu) << (8 * k);
-                pcb |= ((vcb - unbias) & 0xFFu) << (8 * k);
-                pcr |= ((vcr - unbias) & 0xFFu) << (8 * k);
+                const unsigned long long s = t_r[r[k] * 16] + t_g[g[k] * 16] + t_b[b[k] * 16];
+                lo[k] = (uint32_t)s >> 6;                // y in the low byte
+                hi[k] = (uint32_t)(s >> 32);             // cb in byte 0, cr in byte 2
             }
-            oy[g4] = py; ocb[g4] = pcb; ocr[g4] = pcr;
+            oy[g4] = __byte_perm(__byte_perm(lo[0], lo[1], 0x0040), __byte_perm(lo[2], lo[3], 0x0040), 0x5410);
+            ocb[g4] = __byte_perm(__byte_perm(hi[0], hi[1], 0x0040), __byte_perm(hi[2], hi[3], 0x0040), 0x5410);
+            ocr[g4] = __byte_perm(__byte_perm(hi[0], hi[1], 0x0062), __byte_perm(hi[2], hi[3], 0x0062), 0x5410);
         }
         *(uint4*)out = make_uint4(oy[0], oy[1], oy[2], oy[3]);
         *(uint4*)(out + a.plane_stride) = make_uint4(ocb[0], ocb[1], ocb[2], ocb[3]);
@@ -115,8 +102,8 @@ __global__ void __launch_bounds__(JC_THREADS) jb_rgb_to_ycc_kernel(JcArgs a) {
 __global__ void __launch_bounds__(JC_THREADS) jb_ycc_to_rgb_kernel(JcArgs a) {
     __shared__ int s_cr[256], s_cb[256];                 // (R_CR >> 6) | G_CR << 16 ;  (B_CB >> 6) | G_CB << 16
     for (int v = threadIdx.x; v < 256; v += JC_THREADS) {
-        s_cr[v] = ((c_inv[0][v] >> 6) & 0xFFFF) | ((int)c_inv[2][v] << 16);
-        s_cb[v] = ((c_inv[3][v] >> 6) & 0xFFFF) | ((int)c_inv[1][v] << 16);
+        s_cr[v] = ((JB_YCC2RGB_R_CR[v] >> 6) & 0xFFFF) | ((int)JB_YCC2RGB_G_CR[v] << 16);
+        s_cb[v] = ((JB_YCC2RGB_B_CB[v] >> 6) & 0xFFFF) | ((int)JB_YCC2RGB_G_CB[v] << 16);
     }
     __syncthreads();
     const int groups = (a.W + 15) >> 4;
@@ -172,7 +159,6 @@ static int jc_launch(bool forward, const uint8_t* src, uint8_t* dst, size_t imag
     if (!src || !dst || rgb_pitch < (size_t)3 * W || plane_pitch < (size_t)W) return JB_ERR_BAD_PARAM;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return JB_ERR_NO_DEVICE;
-    if (jc_upload_tables() != cudaSuccess) return JB_ERR_CUDA;
     JcArgs a;
     a.src = src; a.dst = dst;
     a.image_stride = image_stride; a.rgb_pitch = rgb_pitch; a.plane_stride = plane_stride; a.plane_pitch = plane_pitch;
@@ -185,12 +171,19 @@ static int jc_launch(bool forward, const uint8_t* src, uint8_t* dst, size_t imag
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    long long want = (total + JC_THREADS - 1) / JC_THREADS;
-    const long long cap = (long long)sms * 8 * 4;        // grid-stride beyond a few waves
-    const unsigned grid = (unsigned)(want < cap ? want : cap);
     cudaStream_t s = (cudaStream_t)stream;
-    if (forward) jb_rgb_to_ycc_kernel<<<grid, JC_THREADS, 0, s>>>(a);
-    else jb_ycc_to_rgb_kernel<<<grid, JC_THREADS, 0, s>>>(a);
+    if (forward) {
+        // persistent CTAs (two per SM: 96 KB of tables each), grid-stride over the 16-pixel groups
+        if (cudaFuncSetAttribute(jb_rgb_to_ycc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, JC_FWD_SMEM) != cudaSuccess)
+            return JB_ERR_CUDA;
+        const long long want = (total + JC_FWD_THREADS - 1) / JC_FWD_THREADS;
+        const long long cap = (long long)sms * 2;
+        jb_rgb_to_ycc_kernel<<<(unsigned)(want < cap ? want : cap), JC_FWD_THREADS, JC_FWD_SMEM, s>>>(a);
+    } else {
+        const long long want = (total + JC_THREADS - 1) / JC_THREADS;
+        const long long cap = (long long)sms * 8 * 4;    // grid-stride beyond a few waves
+        jb_ycc_to_rgb_kernel<<<(unsigned)(want < cap ? want : cap), JC_THREADS, 0, s>>>(a);
+    }
     return cudaGetLastError() == cudaSuccess ? JB_OK : JB_ERR_CUDA;
 }
 

@@ -21,7 +21,7 @@ def _golden():
 def _header_tables():
     text = open(HEADER).read()
     out = {}
-    for name, body in re.findall(r"static const int16_t (\w+)\[\d+\] = \{([^}]*)\}", text):
+    for name, body in re.findall(r"JB_COLOR_TABLE_QUAL int16_t (\w+)\[\d+\] = \{([^}]*)\}", text):
         out[name] = [int(v) for v in body.replace("\n", " ").split(",") if v.strip()]
     return out
 

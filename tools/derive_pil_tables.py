@@ -127,9 +127,10 @@ def main():
                  "// Integer tables that reproduce Pillow %s's RGB <-> YCbCr conversion on all 2^24 inputs:\n"
                  "//   y/cb/cr = (T[0][r] + T[1][g] + T[2][b]) >> 6      (the +128 of cb, cr is folded into T[2])\n"
                  "//   r = clip(y + (R_CR[cr] >> 6)), g = clip(y + ((G_CB[cb] + G_CR[cr]) >> 6)), b = clip(y + (B_CB[cb] >> 6))\n"
-                 "#pragma once\n#include <stdint.h>\n\n" % PIL.__version__)
+                 "// JB_COLOR_TABLE_QUAL: storage of the tables (the CUDA file sets it to __constant__).\n"
+                 "#pragma once\n#include <stdint.h>\n#ifndef JB_COLOR_TABLE_QUAL\n#define JB_COLOR_TABLE_QUAL static const\n#endif\n\n" % PIL.__version__)
         def emit(name, rows):
-            fh.write("static const int16_t %s[%d] = {\n" % (name, len(rows)))
+            fh.write("JB_COLOR_TABLE_QUAL int16_t %s[%d] = {\n" % (name, len(rows)))
             for i in range(0, len(rows), 16):
                 fh.write("    " + ", ".join(str(int(v)) for v in rows[i:i + 16]) + ",\n")
             fh.write("};\n\n")
