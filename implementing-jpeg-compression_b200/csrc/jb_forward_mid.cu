@@ -4,8 +4,8 @@
 // after another:
 //   1. the (d*bs) x (d*bs) source tile is copied to shared memory with 8-byte coalesced loads
 //      (edge / misaligned tiles: clamped byte loads -- padding.py:8-12, dct_padding.py:8-9);
-//   2. separable box sums: horizontal sums of bs bytes per (row, column), then vertical sums of bs
-//      rows -> exact integer sums X (subsampling.py:9-11 without the division);
+//   2. separable box sums: vertical sums of bs rows (32-bit loads, two 16-bit partial sums per register),
+//      then horizontal sums of bs columns -> exact integer sums X (subsampling.py:9-11 without the division);
 //   3. C.X.C^T as two register-tiled contractions out of shared memory (transforms.py:46-58):
 //      each thread owns 4 outputs and streams X and 4-wide slices of C^T -- 2 shared loads per 4 FFMA.
 //      fp32 on exact integers; coefficients within the fp32 error bound of a rounding tie are
@@ -48,7 +48,7 @@ __host__ __device__ inline FmLayout fm_layout(int d, int bs, bool dft) {
     L.qt = o;    o += (size_t)n * 4;
     L.zz = o;    o += jb_align_up((size_t)n * 2, 16);
     L.tile = o;  o += 2 * jb_align_up((size_t)L.side * L.pitch, 16);      // double buffered
-    L.hsum = o;  o += jb_align_up((size_t)L.side * d * 2, 16);
+    L.hsum = o;  o += jb_align_up((size_t)L.pitch * d * 2, 16);      // vertical sums V[i][x], uint16
     L.x = o;     o += (size_t)n * 4;
     L.t = o;     o += (size_t)n * 4;
     L.t2 = o;    o += dft ? (size_t)n * 4 : 0;
@@ -190,23 +190,32 @@ jb_fwd_mid_kernel(const JbFwdArgs a) {
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();                       // tile gi complete; everyone is done with block gi - 1
         if (gi + 1 < nvalid) stage_tile(gi + 1, sTile + (size_t)((gi + 1) & 1) * tile_bytes);
-        // ---- 2a. horizontal sums: lane = column j, warps stride over the tile rows ----
-        if (lane < d) {
-            for (int r = warp; r < side; r += FM_THREADS / 32) {
-                const uint8_t* p = tile + r * pitch + lane * bs;
-                int s = 0;
-                for (int k = 0; k < bs; ++k) s += p[k];
-                sH[r * d + lane] = (uint16_t)s;
+        // ---- 2a. vertical sums of bs rows, four byte columns per thread (two 16-bit lanes per register) ----
+        {
+            const int nwc = pitch >> 2;                                   // words per tile row
+            const uint32_t* t32 = (const uint32_t*)tile;
+            uint32_t* v32 = (uint32_t*)sH;                                // V[i][x] as uint16, row length = pitch
+            for (int t = tid; t < d * nwc; t += FM_THREADS) {
+                const int i = t / nwc, wc = t - i * nwc;
+                const uint32_t* p = t32 + (size_t)i * bs * nwc + wc;
+                uint32_t even = 0, odd = 0;                               // bytes 0,2 and bytes 1,3 (sums <= 255 bs < 2^16)
+                for (int k = 0; k < bs; ++k) {
+                    const uint32_t w = p[k * nwc];
+                    even += w & 0x00FF00FFu;
+                    odd += (w >> 8) & 0x00FF00FFu;
+                }
+                v32[i * (nwc * 2) + 2 * wc] = (even & 0xFFFFu) | (odd << 16);
+                v32[i * (nwc * 2) + 2 * wc + 1] = (even >> 16) | (odd & 0xFFFF0000u);
             }
         }
         __syncthreads();
-        // ---- 2b. vertical sums -> X (exact integers, as float) ----
-        if (lane < d) {
-            for (int i = warp; i < d; i += FM_THREADS / 32) {
-                int s = 0;
-                for (int k = 0; k < bs; ++k) s += sH[(i * bs + k) * d + lane];
-                sX[i * d + lane] = (float)s;
-            }
+        // ---- 2b. horizontal sums of bs columns -> X (exact integers, as float) ----
+        for (int t = tid; t < n; t += FM_THREADS) {
+            const int i = t / d, j = t - i * d;
+            const uint16_t* p = sH + i * pitch + j * bs;
+            int sum = 0;
+            for (int k = 0; k < bs; ++k) sum += p[k];
+            sX[t] = (float)sum;
         }
         __syncthreads();
         // ---- 3a. T[i][v] = sum_j X[i][j] A[v][j]: thread (i, group of 4 v) ----
