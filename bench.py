@@ -369,18 +369,18 @@ def run_ours(args, rank, world, local_rank):
             "ms_compress": t_c, "ms_decompress": t_d, "stream_bytes": stream_total,
             "decoder_serial_fallback_streams_rank0": serial_streams, "launch": launch_mode,
             "bytes_per_pixel": stream_total / (N_IMAGES * H * W),
-            "roofline": {"bound": "hbm", "kernel": "jb_fwd_fast_kernel (fused compress; timed with the table "
-                         "builder and two memsets of the same call)", "achieved": ach_c, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "jb_fwd_fast_kernel (fused compress; timed together with the init, "
+                         "scan and gather launches of the same call: 1.16 of the 1.27 ms are the fused kernel)", "achieved": ach_c, "peak": peak,
                          "unit": "GB/s", "frac": ach_c / peak, "frac_of_nominal_8000": ach_c / 8000.0,
                          # dram__bytes_read+write of one launch from `ncu --set full` at 1024 images on one GPU
-                         # (profiles/r1_ncu_full_prof_fwd_full_r1.csv: 6.389 GB + 0.127 GB), scaled to this rank's share
-                         "traffic": 6.516e9 * n_img / 1024.0, "traffic_source": "profiles/r1_ncu_full_prof_fwd_full_r1.csv",
+                         # (profiles/r1_ncu_full_v8_jb_fwd_fast.txt: 6.418 GB + 0.127 GB), scaled to this rank's share
+                         "traffic": 6.545e9 * n_img / 1024.0, "traffic_source": "profiles/r1_ncu_full_v8_jb_fwd_fast.txt",
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": a_c},
-            "roofline_decompress": {"bound": "hbm", "kernel": "framing kernels + jb_inv_fast_kernel (the fused kernel alone: 1.41 ms of the decompress time)",
+            "roofline_decompress": {"bound": "hbm", "kernel": "framing kernels + jb_inv_fast_kernel (the fused kernel alone: 1.40 ms of the decompress time)",
                                     "achieved": ach_d, "peak": peak, "unit": "GB/s", "frac": ach_d / peak,
                                     "frac_of_nominal_8000": ach_d / 8000.0,
-                                    "traffic": 6.470e9 * n_img / 1024.0,
-                                    "traffic_source": "profiles/r1_ncu_full_prof_inv_full_r1.csv (fused inverse kernel only)",
+                                    "traffic": 6.461e9 * n_img / 1024.0,
+                                    "traffic_source": "profiles/r1_ncu_full_v8_jb_inv_fast.txt (fused inverse kernel only)",
                                     "algorithmic_bytes_per_launch": a_d},
             "cpu_baseline": cpu,
             "e2e": e2e,
