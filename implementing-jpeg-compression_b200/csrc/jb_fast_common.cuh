@@ -17,6 +17,9 @@ __device__ __forceinline__ void ff_mbar_init(unsigned long long* bar, uint32_t c
 __device__ __forceinline__ void ff_mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(ff_smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void ff_mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(ff_smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool ff_mbar_try_wait(unsigned long long* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
@@ -122,6 +125,13 @@ __device__ __forceinline__ void ff_tma_store_3d(const CUtensorMap* map, int x, i
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%1, %2, %3}], [%4], %5;"
                  :: "l"(map), "r"(x), "r"(y), "r"(z), "r"(ff_smem_u32(src)), "l"(pol) : "memory");
+}
+// 1-D bulk copy shared -> global (16-byte aligned on both sides, size a multiple of 16), bulk-group completion
+__device__ __forceinline__ void ff_bulk_store_1d(void* dst, const void* src, uint32_t bytes) {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                 :: "l"(dst), "r"(ff_smem_u32(src)), "r"(bytes), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void ff_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>

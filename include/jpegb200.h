@@ -80,6 +80,8 @@ typedef struct jb_params {
 #define JB_FLAG_NO_TMA        2  /* specialised kernels stage tiles with plain loads/stores */
 #define JB_FLAG_NO_REFINE     4  /* skip the float64 re-evaluation of near-tie coefficients */
 #define JB_FLAG_SERIAL_FRAMING 8 /* decoder: find block boundaries with the serial fallback walk only */
+#define JB_FLAG_STRIP_DECODER 32 /* decoder: use the CTA-wide strip kernel where it applies (dense planes, width a
+                                   whole number of 48..64-block segments); experimental, measured slower */
 #define JB_FLAG_REUSE_TABLES  16 /* the caller promises that this workspace was last used by a call of the same
                                    direction with identical transform / size / quantiser parameters and has not
                                    been written since: the table builder launch is skipped */
