@@ -335,28 +335,27 @@ __global__ void __launch_bounds__(JB_WALK_THREADS) jb_frame_walk_smem_kernel(JbF
             bm[(q - tstart_s) >> 5] |= 1u << ((q - tstart_s) & 31u);
             const uint32_t bm_addr = (uint32_t)__cvta_generic_to_shared(bm);
             uint32_t p = q * 8u;                             // bit position inside the slice
-            int count = 0;
             // One flat loop over codes, not one loop per block, and the end-of-block bookkeeping is
             // predicated: the 32 lanes of a warp stay converged although their blocks end at different
             // codes.  Only false starts, blocks that leave the staged window and the end of the tile branch.
-            int n;
-            asm volatile("mov.s32 %0, %1;" : "=r"(n) : "r"(f.n));      // keep it in a register, not a constant-bank load per code
+            // (No coefficient count here: a parse that started on a false offset runs into an impossible
+            // code within a few codes, or into the zero fill behind the window; a parse that started on a
+            // true offset of a valid stream never exceeds the count.  The transform kernel checks it.)
             // a block that ends at or beyond this bit leaves the tile (the staged window reaches further)
             const uint32_t lim_bits = tend_s * 8u - 8u;
             for (;;) {
                 const uint32_t idx = p >> 5;
                 const uint32_t x = __funnelshift_l(mine[idx + 1], mine[idx], p);
-                const uint32_t head = x >> 24, size = head & 15u;
-                p += 8u + size;
-                count += (int)(x >> 28) + (size != 0u ? 1 : 0);
+                const uint32_t head = x >> 24;
+                p += 8u + (head & 15u);
                 uint32_t eob = x < 0x01000000u ? 1u : 0u;
-                const bool bad = ((head & 14u) == 0u && head != 0xF0u && x >= 0x01000000u) || count > n;
+                const bool bad = (head & 14u) == 0u && head != 0xF0u && x >= 0x01000000u;
                 q = (p + 7u) >> 3;
                 if (bad || (x < 0x01000000u && p > lim_bits)) {
                     bool false_start = bad;
                     if (p > staged_bits) {
                         // zero fill was parsed: repeat this block from global memory
-                        const uint32_t nx = jb_walk_block_global(stream, len, last + to_stream, n, f.maxblk);
+                        const uint32_t nx = jb_walk_block_global(stream, len, last + to_stream, f.n, f.maxblk);
                         false_start = nx == JB_POS_INVALID;
                         q = nx - to_stream;
                     } else if (q > len_s) {
@@ -379,7 +378,6 @@ __global__ void __launch_bounds__(JB_WALK_THREADS) jb_frame_walk_smem_kernel(JbF
                              :: "r"(bm_addr + ((rel >> 5) << 2)), "r"(eob << (rel & 31u)) : "memory");
                 last = eob ? q : last;
                 p = eob ? q * 8u : p;
-                count = eob ? 0 : count;
             }
         }
         f.tile_exit[tile] = exit_pos;
