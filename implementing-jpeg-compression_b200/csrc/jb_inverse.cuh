@@ -12,8 +12,14 @@
 static inline unsigned jb_frame_tile_bytes(size_t in_bytes, int n_planes, long long nblocks_per_plane) {
     const double blocks = (double)n_planes * (double)nblocks_per_plane;
     const double avg = blocks > 0 ? (double)in_bytes / blocks : 16.0;
-    unsigned t = 256;
-    while (t < 4096 && (double)t < 12.0 * avg) t <<= 1;
+#ifndef JB_MIN_TILE
+#define JB_MIN_TILE 256
+#endif
+#ifndef JB_TILE_BLOCKS
+#define JB_TILE_BLOCKS 12.0
+#endif
+    unsigned t = JB_MIN_TILE;
+    while (t < 4096 && (double)t < JB_TILE_BLOCKS * avg) t <<= 1;
     return t;
 }
 
