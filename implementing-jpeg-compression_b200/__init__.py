@@ -14,11 +14,12 @@ from . import file_format  # noqa: F401
 from .file_format import CompressedData  # noqa: F401
 from .codec import (Jpeg, CompressedPlanes, BatchCodec, compress_band, decompress_band, compress_bands,  # noqa: F401
                     decompress_bands, compress_planes, decompress_planes, check_status, geometry,
-                    rgb_to_ycbcr_planes, ycbcr_planes_to_rgb)
+                    rgb_to_ycbcr_planes, ycbcr_planes_to_rgb, pack_containers, containers_to_bytes,
+                    compress_images_rgb)
 from . import stages, sharding  # noqa: F401
 
 __all__ = ["Configuration", "QuantizationMethod", "Jpeg", "CompressedData", "CompressedPlanes", "BatchCodec",
            "compress_band", "decompress_band", "compress_bands", "decompress_bands", "compress_planes",
-           "decompress_planes", "check_status", "geometry", "rgb_to_ycbcr_planes", "ycbcr_planes_to_rgb", "file_format", "stages", "sharding",
+           "decompress_planes", "check_status", "geometry", "rgb_to_ycbcr_planes", "ycbcr_planes_to_rgb", "pack_containers", "containers_to_bytes", "compress_images_rgb", "file_format", "stages", "sharding",
            "BadArrayShapeError", "BadQuantizationError", "BadRleCodeError", "BadStreamError",
            "EmptyArrayError", "NativeLibraryError"]

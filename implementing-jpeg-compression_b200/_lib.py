@@ -60,6 +60,8 @@ SYMBOLS = {
     "jb_stage_inverse_coeffs": (_I, [_P, _I, _PP, _P, _SZ, _SZ, _P, _P, _SZ, _P]),
     "jb_rgb_to_ycbcr_planes": (_I, [_P, _SZ, _SZ, _I, _I, _I, _P, _SZ, _SZ, _P]),
     "jb_ycbcr_planes_to_rgb": (_I, [_P, _SZ, _SZ, _I, _I, _I, _P, _SZ, _SZ, _P]),
+    "jb_containers_max_bytes": (_SZ, [_I, _I, _SZ]),
+    "jb_pack_containers": (_I, [_P, _P, _I, ctypes.c_char_p, _I, _P, _SZ, _P, _P, _P]),
 }
 
 _lib = None

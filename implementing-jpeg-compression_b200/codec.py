@@ -306,6 +306,62 @@ def ycbcr_planes_to_rgb(planes, out=None):
     return out
 
 
+def pack_containers(comp, config):
+    """file_format.generate_data for a whole batch on the device (file_format.py:86-93).
+
+    ``comp``: the ``CompressedPlanes`` of 3 n planes (image i = planes 3i, 3i+1, 3i+2).  Returns
+    ``(uint8 CUDA tensor with the n containers back to back, int64 CUDA tensor [n + 1] of offsets, status)``;
+    asynchronous.  ``containers_to_bytes`` turns the pair into one ``bytes`` per image."""
+    lib = _lib.load()
+    if comp.n_planes % 3:
+        raise BadArrayShapeError((comp.n_planes,))
+    n = comp.n_planes // 3
+    header = file_format.create_header(config)
+    dev = comp.data.device
+    cap = lib.jb_containers_max_bytes(n, len(header), comp.data.numel())
+    with torch.cuda.device(dev):
+        out = torch.empty(cap, dtype=torch.uint8, device=dev)
+        offs = torch.empty(n + 1, dtype=torch.int64, device=dev)
+        status = torch.zeros(_lib.JB_STATUS_WORDS, dtype=torch.int64, device=dev)
+        rc = lib.jb_pack_containers(_ptr(comp.data), _ptr(comp.offsets), n, header, len(header), _ptr(out), out.numel(),
+                                    _ptr(offs), _ptr(status), _stream_ptr())
+    _raise_for_code(rc)
+    return out, offs, status
+
+
+def containers_to_bytes(out, offs, status=None):
+    """One ``bytes`` per image from ``pack_containers``' result (one device -> host copy for the batch)."""
+    if status is not None:
+        check_status(status)
+    o = offs.cpu().numpy()
+    host = out[:int(o[-1])].cpu().numpy().tobytes()
+    return [host[int(o[i]):int(o[i + 1])] for i in range(len(o) - 1)]
+
+
+def compress_images_rgb(images, config):
+    """``[Jpeg(config).compress(im.convert('YCbCr')) for im in images]`` (compress.py:9-17), byte-identical, as one
+    batch: the RGB images cross to the GPU once through a pinned buffer (``np.asarray`` views, no Python lists --
+    compare util.py:110-112), colour conversion, compression and container assembly happen on the device, and one
+    copy brings every container back."""
+    n = len(images)
+    if n == 0:
+        return []
+    h, w = int(config.height), int(config.width)
+    dev = _require_cuda()
+    staging = torch.empty((n, h, w, 3), dtype=torch.uint8, pin_memory=True)
+    view = staging.numpy()
+    for i, im in enumerate(images):
+        a = np.asarray(im if im.mode == "RGB" else im.convert("RGB"))
+        if a.shape != (h, w, 3):
+            raise ValueError("image %d is %s but config says %dx%d" % (i, a.shape, h, w))
+        view[i] = a
+    rgb = staging.to(dev, non_blocking=True)
+    comp = compress_planes(rgb_to_ycbcr_planes(rgb), config)
+    out, offs, status = pack_containers(comp, config)
+    comp.check()
+    return containers_to_bytes(out, offs, status)
+
+
 class Jpeg:
     """pipeline.Jpeg (pipeline/__init__.py:98-124) on the CUDA path: the three bands of an
     image go through one batched launch each way; the container is the reference's."""
@@ -330,7 +386,7 @@ class Jpeg:
     def compress_rgb(self, image):
         """``Jpeg(config).compress(image.convert('YCbCr'))`` of compress.py:9-17, byte-identical; the RGB image
         crosses to the GPU once, interleaved, and is converted there."""
-        rgb = torch.from_numpy(np.ascontiguousarray(np.asarray(image.convert("RGB"), dtype=np.uint8))).to(_require_cuda())
+        rgb = torch.from_numpy(np.array(image.convert("RGB"), dtype=np.uint8)).to(_require_cuda())
         comp = compress_planes(rgb_to_ycbcr_planes(rgb), self.config)
         y, cb, cr = comp.to_bytes_list()
         return file_format.generate_data(self.config, file_format.CompressedData(y, cb, cr))

@@ -198,3 +198,99 @@ extern "C" int jb_ycbcr_planes_to_rgb(const uint8_t* d_planes, size_t plane_stri
                                       void* stream) {
     return jc_launch(false, d_planes, d_rgb, image_stride, rgb_pitch, plane_stride, plane_pitch, n_images, height, width, stream);
 }
+
+// =====================================================================================================================
+// Container assembly for a batch of images: file_format.generate_data
+// (file_format.py:86-93) writes, per image, the header followed by a little-endian u32 length and the stream of each of
+// the three bands.  With the streams of image i stored back to back (planes 3i, 3i+1, 3i+2 of jb_compress_planes),
+// container i starts at  i * (header_len + 12) + plane_off[3i] - plane_off[0]  -- no scan needed -- and one device to host
+// copy then moves every container of the batch.
+// =====================================================================================================================
+struct JcPackArgs {
+    const uint8_t* streams;
+    const unsigned long long* plane_off;     // [3 n + 1]
+    uint8_t* out;
+    unsigned long long* image_off;           // [n + 1]
+    unsigned long long out_cap;
+    unsigned long long* status;              // [0]: error code (capacity)
+    int n_images, header_len;
+    uint8_t header[256];
+};
+
+__global__ void __launch_bounds__(256) jb_pack_containers_kernel(const JcPackArgs a) {
+    const int img = blockIdx.x, tid = threadIdx.x;
+    const unsigned long long o0 = a.plane_off[0];
+    const unsigned long long s0 = a.plane_off[3 * img], s1 = a.plane_off[3 * img + 1], s2 = a.plane_off[3 * img + 2],
+                             s3 = a.plane_off[3 * img + 3];
+    const unsigned long long per = (unsigned long long)a.header_len + 12ull;
+    const unsigned long long dst0 = (unsigned long long)img * per + (s0 - o0);
+    const unsigned long long end = dst0 + per + (s3 - s0);
+    if (tid == 0) {
+        a.image_off[img] = dst0;
+        if (img == a.n_images - 1) a.image_off[a.n_images] = end;
+    }
+    if (end > a.out_cap) {
+        if (tid == 0) atomicMax(a.status, (unsigned long long)(-JB_ERR_OUT_CAPACITY));
+        return;
+    }
+    uint8_t* d = a.out + dst0;
+    for (int i = tid; i < a.header_len; i += 256) d[i] = a.header[i];
+    d += a.header_len;
+    const unsigned long long st[4] = {s0, s1, s2, s3};
+    #pragma unroll
+    for (int b = 0; b < 3; ++b) {
+        const unsigned long long len = st[b + 1] - st[b];
+        if (tid < 4) d[tid] = (uint8_t)(len >> (8 * tid));                 // struct.pack('<L', len)
+        d += 4;
+        const uint8_t* src = a.streams + st[b];
+        // bytes up to a 16-byte boundary of the destination, then 128-bit stores assembled from unaligned loads
+        const unsigned head = (unsigned)((16u - (unsigned)((uintptr_t)d & 15u)) & 15u);
+        const unsigned long long h = len < head ? len : head;
+        if (tid < h) d[tid] = src[tid];
+        const uint8_t* s = src + h;
+        uint4* d16 = (uint4*)(d + h);
+        const unsigned mis = (unsigned)((uintptr_t)s & 3u);
+        // (an unaligned source reads one word past each 16 bytes: keep that word inside the stream)
+        const unsigned long long body = len - h, guard = mis ? 4ull : 0ull;
+        const unsigned long long nvec = body > guard ? (body - guard) >> 4 : 0ull;
+        const uint32_t* sw = (const uint32_t*)(s - mis);
+        for (unsigned long long v = tid; v < nvec; v += 256) {
+            const uint32_t w0 = __ldg(sw + 4 * v), w1 = __ldg(sw + 4 * v + 1), w2 = __ldg(sw + 4 * v + 2), w3 = __ldg(sw + 4 * v + 3);
+            uint4 o = make_uint4(w0, w1, w2, w3);
+            if (mis) {
+                const uint32_t w4 = __ldg(sw + 4 * v + 4);
+                const unsigned sh = mis * 8u;
+                o = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
+                               __funnelshift_r(w3, w4, sh));
+            }
+            d16[v] = o;
+        }
+        const unsigned long long done = h + (nvec << 4);
+        if (done + tid < len) d[done + tid] = src[done + tid];               // fewer than 16 bytes left
+        d += len;
+    }
+}
+
+extern "C" size_t jb_containers_max_bytes(int n_images, int header_len, size_t stream_bytes) {
+    if (n_images <= 0 || header_len < 0 || header_len > 256) return 0;
+    return (size_t)n_images * ((size_t)header_len + 12) + stream_bytes;
+}
+
+extern "C" int jb_pack_containers(const uint8_t* d_streams, const uint64_t* d_plane_off, int n_images, const uint8_t* header,
+                                  int header_len, uint8_t* d_out, size_t out_cap, uint64_t* d_image_off, uint64_t* d_status,
+                                  void* stream) {
+    if (n_images <= 0) return JB_ERR_EMPTY_ARRAY;
+    if (!d_streams || !d_plane_off || !header || !d_out || !d_image_off || !d_status || header_len <= 0 || header_len > 256)
+        return JB_ERR_BAD_PARAM;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return JB_ERR_NO_DEVICE;
+    JcPackArgs a;
+    a.streams = d_streams; a.plane_off = (const unsigned long long*)d_plane_off; a.out = d_out;
+    a.image_off = (unsigned long long*)d_image_off; a.out_cap = out_cap; a.status = (unsigned long long*)d_status;
+    a.n_images = n_images; a.header_len = header_len;
+    memcpy(a.header, header, (size_t)header_len);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (cudaMemsetAsync(d_status, 0, sizeof(uint64_t), s) != cudaSuccess) return JB_ERR_CUDA;
+    jb_pack_containers_kernel<<<n_images, 256, 0, s>>>(a);
+    return cudaGetLastError() == cudaSuccess ? JB_OK : JB_ERR_CUDA;
+}

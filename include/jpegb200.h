@@ -193,6 +193,16 @@ int jb_ycbcr_planes_to_rgb(const uint8_t* d_planes, size_t plane_stride, size_t 
                            int height, int width, uint8_t* d_rgb, size_t image_stride, size_t rgb_pitch,
                            void* stream);
 
+/* ---- containers of a batch of images -------------------------------------
+ * Replaces the host loop over file_format.generate_data (file_format.py:86-93): container i = header, then for
+ * Y, Cb, Cr a little-endian u32 length and the stream, taken from the output of jb_compress_planes on
+ * 3 n planes (d_streams, d_plane_off[3 n + 1]).  `header` is a HOST pointer to file_format.create_header's
+ * bytes (<= 256).  d_image_off receives n + 1 offsets into d_out; d_status[0] a positive error code. */
+size_t jb_containers_max_bytes(int n_images, int header_len, size_t stream_bytes);
+int jb_pack_containers(const uint8_t* d_streams, const uint64_t* d_plane_off, int n_images, const uint8_t* header,
+                       int header_len, uint8_t* d_out, size_t out_cap, uint64_t* d_image_off, uint64_t* d_status,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

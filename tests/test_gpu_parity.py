@@ -369,3 +369,28 @@ def test_strip_decoder_equals_tile_decoder(jb, h, w, n, tr):
     streams = comp.to_bytes_list()
     want = rp.decompress_band(streams[n - 1], ocfg)
     assert np.abs(outs[0][n - 1].astype(np.int64) - want).max() <= 1
+
+
+def test_batched_containers_equal_generate_data(jb):
+    """jb_pack_containers == file_format.generate_data per image (file_format.py:86-93), for stream lengths of
+    every alignment, and the batched RGB front end == the per-image Pillow flow."""
+    import torch
+    h, w, n = 40, 72, 7
+    cfg, _ = _cfgs(jb, (h, w, 4, 8, "DCT", "qtable", None))
+    planes = np.stack([synth_plane(h, w, 500 + i) for i in range(3 * n)]).astype(np.uint8)
+    planes[4] = 0                                       # very short streams too
+    comp = jb.compress_planes(torch.from_numpy(planes).cuda(), cfg)
+    streams = comp.to_bytes_list()
+    out, offs, status = jb.pack_containers(comp, cfg)
+    got = jb.containers_to_bytes(out, offs, status)
+    want = [jb.file_format.generate_data(cfg, jb.CompressedData(*streams[3 * i:3 * i + 3])) for i in range(n)]
+    assert got == want
+    try:
+        from PIL import Image
+    except ImportError:
+        return
+    rng = np.random.default_rng(8)
+    imgs = [Image.fromarray((planes[3 * i:3 * i + 3].transpose(1, 2, 0) ^ rng.integers(0, 8, (h, w, 3), dtype=np.uint8)), "RGB")
+            for i in range(n)]
+    batch = jb.compress_images_rgb(imgs, cfg)
+    assert batch == [jb.Jpeg(cfg).compress(im.convert("YCbCr")) for im in imgs]
