@@ -53,7 +53,7 @@ extern "C" size_t jb_max_stream_bytes(const jb_params* p, int n_planes) {
 }
 
 // ---- compress ----------------------------------------------------------------------------------
-struct JbFwdWs { size_t ticket, chunk_len, chunk_off, seg_total, tmp, total; unsigned chunk_cap; };
+struct JbFwdWs { size_t ticket, chunk_len, chunk_off, seg_total, tmp_small, tmp, total; unsigned chunk_cap; };
 static JbFwdWs jb_fwd_ws(int d, size_t n_chunks) {
     JbFwdWs w;
     size_t o = jb_align_up(jb_table_layout(d).total, 256);
@@ -63,6 +63,7 @@ static JbFwdWs jb_fwd_ws(int d, size_t n_chunks) {
     w.chunk_len = o; o += jb_align_up(n_chunks * 4, 256);
     w.chunk_off = o; o += jb_align_up(n_chunks * 4, 256);
     w.seg_total = o; o += jb_align_up(((n_chunks + JB_SCAN_SEG - 1) / JB_SCAN_SEG) * 8, 256);
+    w.tmp_small = o; o += jb_align_up(n_chunks * (size_t)JB_SLOT_STRIDE, 256);
     w.tmp = o;       o += jb_align_up(n_chunks * (size_t)w.chunk_cap, 256);
     w.total = o;
     return w;
@@ -121,6 +122,7 @@ static int jb_forward_common(int mode, const uint8_t* d_planes, size_t plane_str
     a.chunk_off = (unsigned*)(ws + w.chunk_off);
     a.seg_total = (unsigned long long*)(ws + w.seg_total);
     a.tmp = (uint8_t*)(ws + w.tmp);
+    a.tmp_small = (uint8_t*)(ws + w.tmp_small);
     a.chunk_cap = w.chunk_cap;
     a.coeffs_out = d_coeffs_out; a.coeffs_in = d_coeffs_in;
     if (mode != 2 && !(g.flags & JB_FLAG_REUSE_TABLES)) JB_CUDA_TRY(jb_launch_build_tables(g, a.t, s));

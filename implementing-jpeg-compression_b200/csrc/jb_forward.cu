@@ -230,7 +230,7 @@ jb_fwd_generic_kernel(const JbFwdArgs a) {
     __syncthreads();
     // compacted copy of the chunk into its slot of the temporary buffer; the scan + gather
     // kernels below move it to its final place in the stream
-    uint8_t* slot = a.tmp + (size_t)chunk * a.chunk_cap;
+    uint8_t* slot = jb_chunk_slot(a, chunk, s_boff[nvalid - 1] + s_blen[nvalid - 1]);
     for (int gi = 0; gi < nvalid; ++gi) {
         const uint8_t* sb = (const uint8_t*)(sStage + gi * L.stageW);
         uint8_t* dst = slot + s_boff[gi];
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(256) jb_gather_chunks_kernel(JbFwdArgs a) {
     const int lane = threadIdx.x & 31;
     const unsigned c = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (c >= a.n_chunks) return;
-    const uint8_t* src = a.tmp + (size_t)c * a.chunk_cap;        // 16-byte aligned, >= 1 KB + 32 B per slot
+    const uint8_t* src = a.tmp_small + (size_t)c * JB_SLOT_STRIDE;   // 16-byte aligned, 1 KB + 32 B per slot
     const uint4* s16 = (const uint4*)src;
     const uint32_t* s32 = (const uint32_t*)src;
     // the first kilobyte of the slot is fetched before its length is known: the two round trips
@@ -295,6 +295,16 @@ __global__ void __launch_bounds__(256) jb_gather_chunks_kernel(JbFwdArgs a) {
         pn[k] = __ldg(s32 + 4 * (lane + 32 * k) + 4);
     }
     const unsigned len = a.chunk_len[c];
+    if (len > JB_SLOT_SMALL) {                                 // a dense chunk: it went to the worst-case-sized slot
+        src = a.tmp + (size_t)c * a.chunk_cap;
+        s16 = (const uint4*)src;
+        s32 = (const uint32_t*)src;
+        #pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            pv[k] = __ldg(s16 + lane + 32 * k);
+            pn[k] = __ldg(s32 + 4 * (lane + 32 * k) + 4);
+        }
+    }
     const unsigned long long base = a.seg_total[c / JB_SCAN_SEG] + a.chunk_off[c];
     if (lane == 0 && c % (unsigned)a.g.cpp == 0) a.plane_off[c / (unsigned)a.g.cpp] = base;
     if (base + len > a.out_cap) return;                       // flagged by the segment scan

@@ -428,7 +428,7 @@ jb_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfKernelArgs 
             const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
             const unsigned excl = incl - len;
             if (lane == 0) a.chunk_len[cc.chunk] = total;
-            uint8_t* slot = a.tmp + (size_t)cc.chunk * a.chunk_cap;
+            uint8_t* slot = jb_chunk_slot(a, cc.chunk, total);
             const bool small = total <= FF_COMPACT_BYTES && !__any_sync(0xffffffffu, len > FF_STAGE_CAP * 4);
             if (small) {
                 // compact the 32 rows inside shared memory (the coefficient rows are dead now), then

@@ -321,7 +321,7 @@ jb_fwd_mid_kernel(const JbFwdArgs a) {
     }
     __syncthreads();
     // ---- 6. chunk bytes -> slot ----
-    uint8_t* slot = a.tmp + (size_t)chunk * a.chunk_cap;
+    uint8_t* slot = jb_chunk_slot(a, chunk, s_boff[JB_CHUNK - 1] + s_blen[JB_CHUNK - 1]);
     if (!s_slow) {
         for (int gi = 0; gi < nvalid; ++gi) {
             const uint8_t* sb = (const uint8_t*)(sStage + gi * L.stageW);
