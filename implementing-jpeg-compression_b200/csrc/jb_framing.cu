@@ -291,36 +291,22 @@ __global__ void __launch_bounds__(JB_WALK_THREADS) jb_frame_walk_smem_kernel(JbF
         if (nw > data_words - 2u) nw = data_words - 2u;
     }
     uint32_t* mine = s_words + (size_t)threadIdx.x * slice_words;
-    // four slices at a time, up to sixteen loads in flight per lane; the rest of a slice becomes zero
-    const int iters = (int)((slice_words + 31u) / 32u);
-    for (int k0 = 0; k0 < 32; k0 += 4) {
-        const uint32_t* g[4];
-        uint32_t cnt[4];
-        uint32_t* dst[4];
-        #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            g[q] = (const uint32_t*)(uintptr_t)__shfl_sync(0xffffffffu, abase, k0 + q);
-            cnt[q] = __shfl_sync(0xffffffffu, nw, k0 + q);
-            dst[q] = s_words + (size_t)((threadIdx.x & ~31) + k0 + q) * slice_words;
-        }
-        for (int ib = 0; ib < iters; ib += 4) {
-            uint32_t v[4][4];
-            #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint32_t idx = (uint32_t)(ib + j) * 32u + (uint32_t)lane;
-                    v[q][j] = idx < cnt[q] ? jb_bswap32(__ldg(g[q] + idx)) : 0u;
-                }
-            #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint32_t idx = (uint32_t)(ib + j) * 32u + (uint32_t)lane;
-                    if (idx < slice_words) dst[q][idx] = v[q][j];
-                }
+    // all 32 slices of the warp with asynchronous 4-byte copies (zero fill behind the window), every load of the
+    // warp in flight at once; then each lane byte-swaps its own slice in place
+    for (int k = 0; k < 32; ++k) {
+        const uint32_t* g = (const uint32_t*)(uintptr_t)__shfl_sync(0xffffffffu, abase, k);
+        const uint32_t cnt = __shfl_sync(0xffffffffu, nw, k);
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_words + (size_t)((threadIdx.x & ~31) + k) * slice_words);
+        for (uint32_t idx = lane; idx < slice_words; idx += 32) {
+            const bool in = idx < cnt;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;"
+                         :: "r"(dst + idx * 4u), "l"(in ? g + idx : (const uint32_t*)f.tile_first), "r"(in ? 4 : 0) : "memory");
         }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    for (uint32_t i = 0; i < data_words; ++i) mine[i] = jb_bswap32(mine[i]);
     __syncwarp();
     if (live) {
         const uint32_t to_stream = first - mis;             // slice byte q is stream byte q + to_stream (mod 2^32)
