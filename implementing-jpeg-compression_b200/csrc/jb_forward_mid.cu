@@ -338,6 +338,303 @@ jb_fwd_mid_kernel(const JbFwdArgs a) {
     }
 }
 
+// =====================================================================================================
+// Warp-per-block variant (DCT, dct_size 16 / 24 / 32, source tile rows of at most 128 bytes).
+//
+// The CTA-per-block kernel above spends its time at barriers: every block takes five CTA-wide phases with
+// at most 144 busy threads each (ncu, config 3: 39 % of the issue slots used, 16 % of the stall samples at
+// the barrier, the contractions themselves only 15 % of the instructions).  Here every warp takes a block of
+// the chunk through all stages on its own, so eight blocks per CTA are in flight and the CTA meets only
+// twice per chunk:
+//   * box sums straight from global memory: lane c loads word column c of the bs rows of a band (coalesced
+//     4-byte loads, several bands in flight), adds them as two 16-bit lanes per register, and bs neighbouring
+//     column sums are added through a 256-byte scratch row -> row i of X (exact integers, as float);
+//   * C.X.C^T with the operands in registers: lane v keeps row v of C and computes T[i][v] for all i from
+//     broadcast reads of X, then Y[u][v] for all u from broadcast reads of C -- T never leaves the registers.
+//     The summation order is the one of the kernel above (fp32 fmaf chains over ascending index), so both
+//     produce the same coefficients;
+//   * quantise, tie check (fp64 re-evaluation), zigzag, int16 row, non-zero bitmap by ballots;
+// then, as above, one lane per block run-length encodes and packs, and the CTA copies the chunk to its slot.
+// =====================================================================================================
+#define FW_WARPS 8
+#define FW_BANDS 4                      // bands whose loads are issued together (divides 16, 24, 32)
+
+struct FwLayout {
+    int coefW, maskW, stageW, vrowW;
+    size_t a, qm, qt, zz, x, vrow, coef, mask, stage, total;
+};
+
+__host__ __device__ inline FwLayout fw_layout(int d, int side) {
+    FwLayout L;
+    const int n = d * d;
+    L.coefW = ((n + 1) / 2) | 1;
+    L.maskW = (n + 31) / 32;
+    L.stageW = (FM_STAGE_BYTES / 4) | 1;
+    L.vrowW = (side + 7) / 8 * 4 + 4;                   // uint16 column sums of one band, in words (4 per 32-bit source word)
+    size_t o = 0;
+    L.a = o;     o += (size_t)n * 4;
+    L.qm = o;    o += (size_t)n * 4;
+    L.qt = o;    o += (size_t)n * 4;
+    L.zz = o;    o += jb_align_up((size_t)n * 2, 16);
+    L.x = o;     o += (size_t)FW_WARPS * n * 4;
+    L.vrow = o;  o += jb_align_up((size_t)FW_WARPS * 2 * L.vrowW * 4, 16);
+    L.coef = o;  o += (size_t)JB_CHUNK * L.coefW * 4;
+    L.mask = o;  o += (size_t)JB_CHUNK * L.maskW * 4;
+    L.stage = o; o += (size_t)JB_CHUNK * L.stageW * 4;
+    L.total = o;
+    return L;
+}
+
+static bool fw_eligible(const JbGeom& g) {
+    if (g.transform != JB_TRANSFORM_DCT) return false;
+    if (g.d != 16 && g.d != 24 && g.d != 32) return false;
+    const int side = g.d * g.bs;
+    return side <= 128 && fw_layout(g.d, side).total <= 110 * 1024;
+}
+
+template <int D, int MODE>
+__global__ void __launch_bounds__(FW_WARPS * 32, 2)
+jb_fwd_mid_warp_kernel(const JbFwdArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const JbGeom& g = a.g;
+    constexpr int n = D * D;
+    const int bs = g.bs, side = D * bs;
+    const FwLayout L = fw_layout(D, side);
+    float* sA = (float*)(smem + L.a);            // A[u][i], row-major
+    float* sQm = (float*)(smem + L.qm);
+    float* sQt = (float*)(smem + L.qt);
+    uint16_t* sZz = (uint16_t*)(smem + L.zz);
+    uint32_t* sCoef = (uint32_t*)(smem + L.coef);
+    uint32_t* sMask = (uint32_t*)(smem + L.mask);
+    uint32_t* sStage = (uint32_t*)(smem + L.stage);
+
+    __shared__ unsigned s_chunk;
+    __shared__ unsigned s_blen[JB_CHUNK], s_boff[JB_CHUNK];
+    __shared__ int s_big_blk[FM_BIG_CAP], s_big_pos[FM_BIG_CAP], s_big_amp[FM_BIG_CAP];
+    __shared__ int s_nbig, s_slow;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float* sX = (float*)(smem + L.x) + warp * n;
+    uint16_t* sV = (uint16_t*)(smem + L.vrow) + (size_t)warp * 2 * L.vrowW * 2;     // two band rows per warp
+    if (tid == 0) { s_chunk = atomicAdd(a.ticket, 1u); s_nbig = 0; s_slow = 0; }
+    for (int idx = tid; idx < n; idx += FW_WARPS * 32) {
+        sA[idx] = a.t.fA[idx];
+        sQm[idx] = a.t.qmult[idx];
+        sQt[idx] = a.t.qtol[idx];
+        sZz[idx] = a.t.zz[idx];
+    }
+    __syncthreads();
+    const unsigned chunk = s_chunk;
+    if (chunk >= a.n_chunks) return;
+    const int plane = chunk / g.cpp;
+    const int blk0 = (chunk % g.cpp) * JB_CHUNK;
+    const int nvalid = jb_min(JB_CHUNK, g.nblocks - blk0);
+    const uint8_t* src = a.planes + (size_t)plane * a.plane_stride;
+    const bool vec_ok = (side % 4 == 0) && (((uintptr_t)src & 3) == 0) && (a.row_pitch % 4 == 0);
+    const bool refine_on = !(g.flags & JB_FLAG_NO_REFINE);
+    const int nwc = side >> 2;                                  // 32-bit words per tile row (<= 32)
+    const int v = lane < D ? lane : D - 1;                      // frequency column of this lane (lanes >= D idle along)
+
+    for (int gi = warp; gi < nvalid; gi += FW_WARPS) {
+        const int blk = blk0 + gi;
+        const int by = blk / g.hb, bx = blk - by * g.hb;
+        const bool interior = (by + 1) * side <= g.H && (bx + 1) * side <= g.W;
+        // ---- box sums -> X ----
+        if (interior && vec_ok) {
+            const uint32_t* base = (const uint32_t*)(src + (size_t)by * side * a.row_pitch + (size_t)bx * side);
+            const size_t pw = a.row_pitch >> 2;
+            // FW_BANDS bands at a time, and the loads of the next group are issued before this group's sums go through
+            // the scratch rows: two groups (2 FW_BANDS bs loads per lane) are in flight
+            uint32_t even[FW_BANDS], odd[FW_BANDS], even_n[FW_BANDS], odd_n[FW_BANDS];
+            const size_t band = (size_t)bs * pw;
+            auto load_group = [&](int i0, uint32_t (&ev)[FW_BANDS], uint32_t (&od)[FW_BANDS]) {
+                #pragma unroll
+                for (int b = 0; b < FW_BANDS; ++b) ev[b] = od[b] = 0u;
+                if (lane < nwc && i0 < D) {
+                    const uint32_t* p[FW_BANDS];                    // one row pointer per band, stepped down the bs rows
+                    p[0] = base + (size_t)i0 * band + lane;
+                    #pragma unroll
+                    for (int b = 1; b < FW_BANDS; ++b) p[b] = p[b - 1] + band;
+                    #pragma unroll 5
+                    for (int k = 0; k < bs; ++k) {
+                        #pragma unroll
+                        for (int b = 0; b < FW_BANDS; ++b) {
+                            const uint32_t w = __ldg(p[b]);
+                            p[b] += pw;
+                            ev[b] += w & 0x00FF00FFu;               // bytes 0,2 and 1,3 of the word column (sums <= 255 bs < 2^16)
+                            od[b] += (w >> 8) & 0x00FF00FFu;
+                        }
+                    }
+                }
+            };
+            load_group(0, even, odd);
+            for (int i0 = 0; i0 < D; i0 += FW_BANDS) {
+                load_group(i0 + FW_BANDS, even_n, odd_n);
+                #pragma unroll
+                for (int b = 0; b < FW_BANDS; ++b) {
+                    uint16_t* vr = sV + (b & 1) * (L.vrowW * 2);
+                    if (lane < nwc)
+                        *(uint2*)(vr + 4 * lane) = make_uint2((even[b] & 0xFFFFu) | (odd[b] << 16), (even[b] >> 16) | (odd[b] & 0xFFFF0000u));
+                    __syncwarp();
+                    if (lane < D) {
+                        int sum = 0;
+                        for (int k = 0; k < bs; ++k) sum += vr[lane * bs + k];
+                        sX[(i0 + b) * D + lane] = (float)sum;
+                    }
+                    // (the other scratch row serves the next band; this one again two bands later, after two syncs)
+                }
+                #pragma unroll
+                for (int b = 0; b < FW_BANDS; ++b) { even[b] = even_n[b]; odd[b] = odd_n[b]; }
+            }
+        } else {
+            // edge block or unaligned plane: the reference's two-level edge replication, byte by byte
+            if (lane < D) {
+                const int sj = jb_min(bx * D + lane, g.W1 - 1);
+                for (int i = 0; i < D; ++i) {
+                    const int si = jb_min(by * D + i, g.H1 - 1);
+                    int sum = 0;
+                    for (int di = 0; di < bs; ++di) {
+                        const uint8_t* r = src + (size_t)jb_min(si * bs + di, g.H - 1) * a.row_pitch;
+                        for (int dj = 0; dj < bs; ++dj) sum += r[jb_min(sj * bs + dj, g.W - 1)];
+                    }
+                    sX[i * D + lane] = (float)sum;
+                }
+            }
+        }
+        __syncwarp();
+        // ---- T[i][v] = sum_j X[i][j] A[v][j], all i, in registers ----
+        float arow[D];                                          // row v of the transform matrix (not live during the loads above)
+        #pragma unroll
+        for (int j = 0; j < D; ++j) arow[j] = sA[v * D + j];
+        float t[D];
+        #pragma unroll
+        for (int i = 0; i < D; ++i) {
+            float acc = 0.f;
+            #pragma unroll
+            for (int j = 0; j < D; j += 4) {
+                const float4 x4 = *(const float4*)(sX + i * D + j);     // same address in every lane: broadcast
+                acc = fmaf(x4.x, arow[j], acc); acc = fmaf(x4.y, arow[j + 1], acc);
+                acc = fmaf(x4.z, arow[j + 2], acc); acc = fmaf(x4.w, arow[j + 3], acc);
+            }
+            t[i] = acc;
+        }
+        // ---- Y[u][v] = sum_i A[u][i] T[i][v]; quantise, tie check, zigzag ----
+        int16_t* crow = (int16_t*)(sCoef + gi * L.coefW);
+        #pragma unroll 4
+        for (int u = 0; u < D; ++u) {
+            float y = 0.f;
+            #pragma unroll
+            for (int i = 0; i < D; i += 4) {
+                const float4 c4 = *(const float4*)(sA + u * D + i);     // broadcast
+                y = fmaf(c4.x, t[i], y); y = fmaf(c4.y, t[i + 1], y);
+                y = fmaf(c4.z, t[i + 2], y); y = fmaf(c4.w, t[i + 3], y);
+            }
+            if (lane < D) {
+                const int idx = u * D + v;
+                const float val = y * sQm[idx];
+                float r = rintf(val);
+                if (refine_on && fabsf(fabsf(val - r) - 0.5f) < sQt[idx] + 2.4e-7f * fabsf(val))
+                    r = (float)rint(fm_refine(sX, u, v, D, bs, g.transform, g.qmode, a.t.fA64, a.t.fB64, a.t.qrecip[idx]));
+                int q = (int)r;
+                const int zp = sZz[idx];
+                if (MODE == 1) {
+                    a.coeffs_out[((size_t)plane * g.nblocks + blk) * n + zp] = (int16_t)max(-32767, min(32767, q));
+                } else {
+                    if (q > JB_MAX_AMP || q < -JB_MAX_AMP) {
+                        const int kk = atomicAdd(&s_nbig, 1);
+                        if (kk < FM_BIG_CAP) { s_big_blk[kk] = gi; s_big_pos[kk] = zp; s_big_amp[kk] = q; }
+                        q = q > 0 ? 32767 : -32767;
+                    }
+                    crow[zp] = (int16_t)q;
+                }
+            }
+        }
+        __syncwarp();
+        // ---- non-zero bitmap of the block (zigzag order) ----
+        if (MODE != 1) {
+            for (int w0 = 0; w0 < L.maskW; ++w0) {
+                const int p = w0 * 32 + lane;
+                const unsigned m = __ballot_sync(0xffffffffu, p < n && crow[p] != 0);
+                if (lane == 0) sMask[gi * L.maskW + w0] = m;
+            }
+        }
+        __syncwarp();
+    }
+    if (MODE == 1) return;
+    // ---- run-length + bit packing of the warp's own blocks, one lane per block, non-zero coefficients only:
+    //      the eight warps pack side by side instead of queueing behind one packing warp at a barrier ----
+    __syncwarp();
+    {
+        const int my_gi = warp + lane * FW_WARPS;
+        if (lane < JB_CHUNK / FW_WARPS) {
+            unsigned len = 0;
+            if (my_gi < nvalid) {
+                const int16_t* c = (const int16_t*)(sCoef + my_gi * L.coefW);
+                JbBitWriter bw;
+                bw.init(sStage + my_gi * L.stageW, FM_STAGE_BYTES / 4);
+                int bad_pos, bad_run;
+                fm_pack_masked(c, sMask + my_gi * L.maskW, L.maskW, bw, bad_pos, bad_run);
+                len = bw.finish();
+                if (len > FM_STAGE_BYTES) s_slow = 1;
+                if (bad_pos >= 0) {
+                    long long amp = c[bad_pos];
+                    const int nb = jb_min(s_nbig, FM_BIG_CAP);
+                    for (int k = 0; k < nb; ++k)
+                        if (s_big_blk[k] == my_gi && s_big_pos[k] == bad_pos) amp = s_big_amp[k];
+                    jb_report_bad_code(a.status, (unsigned long long)plane * g.nblocks + blk0 + my_gi, bad_pos, bad_run, amp);
+                }
+            }
+            s_blen[my_gi] = len;
+        }
+    }
+    __syncthreads();
+    if (tid < JB_CHUNK) {
+        const unsigned len = s_blen[tid];
+        unsigned incl = len;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (tid >= o) incl += y;
+        }
+        s_boff[tid] = incl - len;
+        if (tid == 31) a.chunk_len[chunk] = incl;
+    }
+    __syncthreads();
+    uint8_t* slot = jb_chunk_slot(a, chunk, s_boff[JB_CHUNK - 1] + s_blen[JB_CHUNK - 1]);
+    if (!s_slow) {
+        for (int gi = 0; gi < nvalid; ++gi) {
+            const uint8_t* sb = (const uint8_t*)(sStage + gi * L.stageW);
+            uint8_t* dst = slot + s_boff[gi];
+            for (unsigned j = tid; j < s_blen[gi]; j += FW_WARPS * 32) dst[j] = sb[j];
+        }
+    } else if (tid < nvalid) {
+        const int16_t* c = (const int16_t*)(sCoef + tid * L.coefW);
+        JbByteWriter bw;
+        bw.init(slot + s_boff[tid]);
+        int bad_pos, bad_run;
+        fm_pack_masked(c, sMask + tid * L.maskW, L.maskW, bw, bad_pos, bad_run);
+        bw.finish();
+    }
+}
+
+template <int D, int MODE>
+static cudaError_t fw_launch_t(const JbFwdArgs& a, cudaStream_t s) {
+    const size_t smem = fw_layout(D, D * a.g.bs).total;
+    cudaError_t e = cudaFuncSetAttribute(jb_fwd_mid_warp_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    jb_fwd_mid_warp_kernel<D, MODE><<<a.n_chunks, FW_WARPS * 32, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+template <int MODE>
+static cudaError_t fw_launch_d(const JbFwdArgs& a, cudaStream_t s) {
+    switch (a.g.d) {
+    case 16: return fw_launch_t<16, MODE>(a, s);
+    case 24: return fw_launch_t<24, MODE>(a, s);
+    default: return fw_launch_t<32, MODE>(a, s);
+    }
+}
+
 template <bool DFT, int MODE>
 static cudaError_t fm_launch_t(const JbFwdArgs& a, cudaStream_t s) {
     const size_t smem = fm_layout(a.g.d, a.g.bs, DFT).total;
@@ -350,6 +647,14 @@ static cudaError_t fm_launch_t(const JbFwdArgs& a, cudaStream_t s) {
 cudaError_t jb_launch_fwd_mid(const JbFwdArgs& a, int mode, cudaStream_t s) {
     if (a.n_chunks == 0) return cudaSuccess;
     const bool dft = a.g.transform == JB_TRANSFORM_DFT;
+    if (fw_eligible(a.g) && !(a.g.flags & JB_FLAG_NO_TMA)) {       // (JB_FLAG_NO_TMA doubles as "plain variant" for the tests)
+        if (mode == 0) {
+            cudaError_t e = fw_launch_d<0>(a, s);
+            if (e != cudaSuccess) return e;
+            return jb_launch_scan_gather(a, s);
+        }
+        return fw_launch_d<1>(a, s);
+    }
     if (mode == 0) {
         cudaError_t e = dft ? fm_launch_t<true, 0>(a, s) : fm_launch_t<false, 0>(a, s);
         if (e != cudaSuccess) return e;
