@@ -238,61 +238,77 @@ jb_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfKernelArgs 
     };
 
     // The warp walks a stream of 4-block tiles (chunk after chunk) one tile ahead of itself: while tile
-    // `cc` is transformed, the TMA load of tile `nx` is in flight in the other ring slot.
-    FfCursor cc;
+    // (bx, by) of chunk `ck` is transformed, the TMA load of the next tile is in flight in the other ring
+    // slot -- the next tile of the same chunk, or the first tile of a freshly claimed chunk `nk`.
+    // Chunk-level state only moves at chunk boundaries; per tile only (bx, by, kind) do.
+    FfCursor ck, nk;
     {
         const unsigned first = claim();
         if (first >= a.n_chunks) return;
-        ff_cursor_set(cc, first, g);
+        ff_cursor_set(ck, first, g);
     }
+    const int hb = g.hb;
+    const int bx_lim = aligned ? jb_min(hb - 4, g.W / 32 - 4) : -1;      // beyond it: wrap / right edge / unaligned -> kind 2
+    const int by_lim = g.H / 32 - 1;                                     // beyond it: rows replicated -> kind 1
+    auto tile_kind = [&](const FfCursor& c, int it, int bx, int by) -> int {
+        if (bx > bx_lim || 4 * it + 4 > c.nvalid) return 2;
+        return by <= by_lim ? 0 : 1;
+    };
     // Generic-proxy writes into a ring slot (edge-tile fills, the staging rows of the pack stage) must be
     // ordered before the TMA engine writes the slot again; tiles that were only read need no proxy fence.
     bool dirty = true;
-    auto issue = [&](FfCursor& c, int slot) {
-        c.kind = ff_cursor_kind(c, g, aligned);
-        if (use_tma && c.kind == 0 && lane == 0) {
+    auto issue = [&](int plane, int bx, int by, int kind, int slot) {
+        if (use_tma && kind == 0 && lane == 0) {
             if (dirty) ff_fence_proxy_async();
             ff_mbar_expect_tx(&ws.bar[slot], FF_TILE_BYTES);
-            ff_tma_load_3d(ws.tile[slot], &tmap, c.bx * 32, c.by * 32, c.plane, &ws.bar[slot]);
+            ff_tma_load_3d(ws.tile[slot], &tmap, bx * 32, by * 32, plane, &ws.bar[slot]);
         }
     };
     int slot = 0;
     unsigned phasebits = 0;
-    issue(cc, 0);
+    int bx = ck.bx, by = ck.by;
+    int kind = tile_kind(ck, 0, bx, by);
+    issue(ck.plane, bx, by, kind, 0);
     bool have = true;
 
     while (have) {
+      bool have_next = true;
+      #pragma unroll 1
+      for (int it = 0; it < ck.nit; ++it) {
         // ---- the tile after this one: same chunk, or the first tile of a freshly claimed chunk ----
-        FfCursor nx = cc;
-        bool have_next = true;
-        if (cc.it + 1 < cc.nit) {
-            ++nx.it;
-            nx.bx += 4;
-            while (nx.bx >= g.hb) { nx.bx -= g.hb; ++nx.by; }
+        int nbx, nby, nkind, nplane = ck.plane;
+        if (it + 1 < ck.nit) {
+            nbx = bx + 4; nby = by;
+            while (nbx >= hb) { nbx -= hb; ++nby; }
+            nkind = tile_kind(ck, it + 1, nbx, nby);
         } else {
             const unsigned c2 = claim();
             have_next = c2 < a.n_chunks;
-            if (have_next) ff_cursor_set(nx, c2, g);
+            nbx = nby = 0; nkind = 2;
+            if (have_next) {
+                ff_cursor_set(nk, c2, g);
+                nbx = nk.bx; nby = nk.by; nplane = nk.plane;
+                nkind = tile_kind(nk, 0, nbx, nby);
+            }
         }
-        if (have_next) issue(nx, slot ^ 1);
+        if (have_next) issue(nplane, nbx, nby, nkind, slot ^ 1);
         dirty = false;
 
         {
             uint8_t* tile = ws.tile[slot];
-            const int kind = cc.kind;
             if (kind == 0 && use_tma) {
                 const uint32_t par = (phasebits >> slot) & 1u;
                 while (!ff_mbar_try_wait(&ws.bar[slot], par)) { }
                 phasebits ^= 1u << slot;
             } else if (kind <= 1) {
-                const uint8_t* plane_ptr = a.planes + (size_t)cc.plane * a.plane_stride;
-                ff_fill_rows(tile, plane_ptr, a.row_pitch, g, cc.by, cc.bx, lane);
+                const uint8_t* plane_ptr = a.planes + (size_t)ck.plane * a.plane_stride;
+                ff_fill_rows(tile, plane_ptr, a.row_pitch, g, by, bx, lane);
                 dirty = true;
                 __syncwarp();
             } else {
-                const uint8_t* plane_ptr = a.planes + (size_t)cc.plane * a.plane_stride;
+                const uint8_t* plane_ptr = a.planes + (size_t)ck.plane * a.plane_stride;
                 const FfEdgeGeom eg = {g.hb, g.H, g.W, g.H1, g.W1};
-                ff_fill_clamped(tile, plane_ptr, a.row_pitch, eg, cc.blk0 + 4 * cc.it, jb_min(4, cc.nvalid - 4 * cc.it), lane);
+                ff_fill_clamped(tile, plane_ptr, a.row_pitch, eg, ck.blk0 + 4 * it, jb_min(4, ck.nvalid - 4 * it), lane);
                 dirty = true;
                 __syncwarp();
             }
@@ -336,7 +352,7 @@ jb_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfKernelArgs 
             if (DFT) ff_dft_column_stage(col, li, y); else ff_dct8(col, y);
 
             // ---- quantise, tie check ----
-            const int gblk = 4 * cc.it + lb;                // block inside the chunk
+            const int gblk = 4 * it + lb;                // block inside the chunk
             int qi[8];
             unsigned nearmask = 0;
             float vmax = 0.f;
@@ -367,9 +383,9 @@ jb_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfKernelArgs 
                 __syncwarp();
             }
             // ---- zigzag store ----
-            if (gblk < cc.nvalid) {
+            if (gblk < ck.nvalid) {
                 if (MODE == 1) {
-                    int16_t* dst = a.coeffs_out + ((size_t)cc.plane * g.nblocks + cc.blk0 + gblk) * 64;
+                    int16_t* dst = a.coeffs_out + ((size_t)ck.plane * g.nblocks + ck.blk0 + gblk) * 64;
                     #pragma unroll
                     for (int u = 0; u < 8; ++u)
                         dst[((u < 4 ? zzlo : zzhi) >> (8 * (u & 3))) & 0xFFu] = (int16_t)max(-32767, min(32767, qi[u]));
@@ -397,14 +413,14 @@ jb_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfKernelArgs 
             __syncwarp();          // tile and scr are free again
         }
 
-        if (MODE == 0 && cc.it + 1 == cc.nit) {
+        if (MODE == 0 && it + 1 == ck.nit) {
             // ---- A9 + A10: lane t packs block t into its (small) staging row ----
             // (the chunk's last tile has been consumed: its ring slot holds the staging rows until the next
             // TMA load is issued into it, behind a proxy fence)
             uint32_t* stage = (uint32_t*)ws.tile[slot];
             dirty = true;
             unsigned len = 0;
-            if (lane < cc.nvalid) {
+            if (lane < ck.nvalid) {
                 JbBitWriter bw;
                 bw.init(stage + lane * FF_STAGE_W, FF_STAGE_CAP);
                 int bad_pos, bad_run;
@@ -415,7 +431,7 @@ jb_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfKernelArgs 
                     const int nb = jb_min(ws.nbig, FF_BIG_CAP);
                     for (int k = 0; k < nb; ++k)
                         if (ws.big_blk[k] == lane && ws.big_pos[k] == bad_pos) amp = ws.big_amp[k];
-                    jb_report_bad_code(a.status, (unsigned long long)cc.plane * g.nblocks + cc.blk0 + lane,
+                    jb_report_bad_code(a.status, (unsigned long long)ck.plane * g.nblocks + ck.blk0 + lane,
                                        bad_pos, bad_run, amp);
                 }
             }
@@ -427,8 +443,8 @@ jb_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfKernelArgs 
             }
             const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
             const unsigned excl = incl - len;
-            if (lane == 0) a.chunk_len[cc.chunk] = total;
-            uint8_t* slot = jb_chunk_slot(a, cc.chunk, total);
+            if (lane == 0) a.chunk_len[ck.chunk] = total;
+            uint8_t* slot = jb_chunk_slot(a, ck.chunk, total);
             const bool small = total <= FF_COMPACT_BYTES && !__any_sync(0xffffffffu, len > FF_STAGE_CAP * 4);
             if (small) {
                 // compact the 32 rows inside shared memory (the coefficient rows are dead now), then
@@ -443,7 +459,7 @@ jb_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfKernelArgs 
             } else {
                 // a block longer than its staging row (or a very dense chunk): pack again, bytes straight
                 // to the slot
-                if (lane < cc.nvalid) {
+                if (lane < ck.nvalid) {
                     JbByteWriter bw;
                     bw.init(slot + excl);
                     int bad_pos, bad_run;
@@ -455,9 +471,11 @@ jb_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfKernelArgs 
             __syncwarp();
         }
 
-        cc = nx;
-        have = have_next;
+        bx = nbx; by = nby; kind = nkind;
         slot ^= 1;
+      }
+      have = have_next;
+      ck = nk;
     }
 }
 
