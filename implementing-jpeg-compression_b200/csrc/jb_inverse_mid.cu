@@ -220,6 +220,182 @@ jb_inv_mid_kernel(const JbInvArgs a) {
     }
 }
 
+// =====================================================================================================
+// Warp-per-block variant (DCT, dct_size 16 / 24 / 32), the mirror of jb_fwd_mid_warp_kernel: the kernel
+// above meets at three CTA-wide barriers per block and lets one warp decode while seven wait (ncu, config 3:
+// 30 % of the stall samples at the barrier).  Here four lanes of every warp decode the warp's own blocks, and
+// the warp then takes each of them through dequantisation, X = B.Y.B^T with the operands in registers (lane c
+// keeps row c of B and column c of P; Y and B arrive by broadcast reads) and the bs x bs replication, with
+// warp-level synchronisation only.  Same fp32 summation order as above, hence the same pixels.
+// =====================================================================================================
+#define IW_WARPS 8
+
+struct IwLayout {
+    int side, coefW;
+    size_t a, dq, izz, lut, y, pix, coef, total;
+};
+
+__host__ __device__ inline IwLayout iw_layout(int d, int bs) {
+    IwLayout L;
+    const int n = d * d;
+    L.side = d * bs;
+    L.coefW = ((n + 1) / 2) | 1;
+    size_t o = 0;
+    L.a = o;    o += (size_t)n * 4;
+    L.dq = o;   o += (size_t)n * 4;
+    L.izz = o;  o += jb_align_up((size_t)n * 2, 16);
+    L.lut = o;  o += jb_align_up((size_t)L.side + 8, 16);
+    L.y = o;    o += (size_t)IW_WARPS * n * 4;
+    L.pix = o;  o += (size_t)IW_WARPS * jb_align_up((size_t)n, 16);
+    L.coef = o; o += (size_t)JB_CHUNK * L.coefW * 4;
+    L.total = o;
+    return L;
+}
+
+static bool iw_eligible(const JbGeom& g) {
+    if (g.transform != JB_TRANSFORM_DCT) return false;
+    if (g.d != 16 && g.d != 24 && g.d != 32) return false;
+    return iw_layout(g.d, g.bs).total <= 110 * 1024;
+}
+
+template <int D, int MODE>
+__global__ void __launch_bounds__(IW_WARPS * 32, 2)
+jb_inv_mid_warp_kernel(const JbInvArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const JbGeom& g = a.g;
+    constexpr int n = D * D;
+    const int bs = g.bs;
+    const IwLayout L = iw_layout(D, bs);
+    float* sA = (float*)(smem + L.a);              // iA[r][u], row-major
+    float* sDq = (float*)(smem + L.dq);
+    uint16_t* sIzz = (uint16_t*)(smem + L.izz);
+    uint8_t* sLut = smem + L.lut;                  // sLut[x] = x / bs: sample column of tile byte column x
+    uint32_t* sCoef = (uint32_t*)(smem + L.coef);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float* sY = (float*)(smem + L.y) + warp * n;
+    uint8_t* sPix = smem + L.pix + (size_t)warp * jb_align_up((size_t)n, 16);
+    const unsigned chunk = blockIdx.x;
+    if (chunk >= a.n_chunks) return;
+    const int plane = chunk / g.cpp;
+    const int blk0 = (chunk % g.cpp) * JB_CHUNK;
+    const int nvalid = jb_min(JB_CHUNK, g.nblocks - blk0);
+
+    for (int idx = tid; idx < n; idx += IW_WARPS * 32) {
+        sA[idx] = a.t.iA[idx];
+        sDq[idx] = a.t.dqmult[idx];
+        sIzz[idx] = a.t.izz[idx];
+    }
+    for (int i = tid; i < JB_CHUNK * L.coefW; i += IW_WARPS * 32) sCoef[i] = 0u;
+    for (int x = tid; x < L.side + 8; x += IW_WARPS * 32) sLut[x] = (uint8_t)jb_min(x / bs, D - 1);
+    __syncthreads();
+
+    // ---- coefficients: four lanes of every warp decode the warp's own blocks ----
+    if (MODE == 2) {
+        for (int gi = warp; gi < nvalid; gi += IW_WARPS)
+            for (int zp = lane; zp < n; zp += 32)
+                ((int16_t*)(sCoef + gi * L.coefW))[sIzz[zp]] = a.coeffs_in[((size_t)plane * g.nblocks + blk0 + gi) * n + zp];
+    } else if (lane < JB_CHUNK / IW_WARPS) {
+        const int gi = warp + lane * IW_WARPS;
+        if (gi < nvalid) {
+            const unsigned long long len = a.plane_len[plane];
+            const unsigned start = a.block_start[(size_t)plane * g.nblocks + blk0 + gi];
+            int rc = 1;
+            if (len <= 0xFFFFFFFFull && start < (unsigned)len)
+                rc = im_decode_block(a.in + a.plane_off[plane], start, (unsigned)len, n,
+                                     (int16_t*)(sCoef + gi * L.coefW), sIzz);
+            if (rc) jb_set_error(a.status, JB_ERR_BAD_STREAM);
+        }
+    }
+    __syncwarp();
+
+    uint8_t* dst = a.planes_out + (size_t)plane * a.plane_stride;
+    const int side = L.side;
+    const bool vec_ok = (side % 8 == 0) && (((uintptr_t)dst & 7) == 0) && (a.row_pitch % 8 == 0);
+    const int c = lane < D ? lane : D - 1;                     // sample column of this lane (lanes >= D idle along)
+    const int w8 = side >> 3;
+
+    for (int gi = warp; gi < nvalid; gi += IW_WARPS) {
+        const int blk = blk0 + gi;
+        const int by = blk / g.hb, bx = blk - by * g.hb;
+        // dequantise: integer coefficient * quantiser step (exact in fp32)
+        {
+            const int16_t* row = (const int16_t*)(sCoef + gi * L.coefW);
+            for (int idx = lane; idx < n; idx += 32) sY[idx] = (float)row[idx] * sDq[idx];
+        }
+        __syncwarp();
+        // P[u][c] = sum_v Y[u][v] iA[c][v], all u, in registers
+        float brow[D], pcol[D];
+        #pragma unroll
+        for (int v = 0; v < D; ++v) brow[v] = sA[c * D + v];
+        #pragma unroll
+        for (int u = 0; u < D; ++u) {
+            float acc = 0.f;
+            #pragma unroll
+            for (int v = 0; v < D; v += 4) {
+                const float4 y4 = *(const float4*)(sY + u * D + v);       // broadcast
+                acc = fmaf(y4.x, brow[v], acc); acc = fmaf(y4.y, brow[v + 1], acc);
+                acc = fmaf(y4.z, brow[v + 2], acc); acc = fmaf(y4.w, brow[v + 3], acc);
+            }
+            pcol[u] = acc;
+        }
+        // X[r][c] = sum_u iA[r][u] P[u][c] -> np.round, clamp -> sample (r, c)
+        #pragma unroll 4
+        for (int r = 0; r < D; ++r) {
+            float x = 0.f;
+            #pragma unroll
+            for (int u = 0; u < D; u += 4) {
+                const float4 b4 = *(const float4*)(sA + r * D + u);       // broadcast
+                x = fmaf(b4.x, pcol[u], x); x = fmaf(b4.y, pcol[u + 1], x);
+                x = fmaf(b4.z, pcol[u + 2], x); x = fmaf(b4.w, pcol[u + 3], x);
+            }
+            if (lane < D) sPix[r * D + c] = (uint8_t)fminf(fmaxf(rintf(x), 0.f), 255.f);
+        }
+        __syncwarp();
+        // bs x bs replication straight to the plane (util.inflate), cropped to the subsampled extent and to the plane
+        const int y0 = by * side, x0 = bx * side;
+        const int rows = jb_min(side, jb_min(g.H, g.H1 * bs) - y0), cols = jb_min(side, jb_min(g.W, g.W1 * bs) - x0);
+        if (rows == side && cols == side && vec_ok) {
+            uint8_t* base = dst + (size_t)y0 * a.row_pitch + x0;
+            for (int t = lane; t < D * w8; t += 32) {                   // (sample row, 8-byte word)
+                const int i = t / w8, c8 = t - i * w8;
+                const uint8_t* prow = sPix + i * D;
+                const uint2 l = *(const uint2*)(sLut + 8 * c8);
+                const uint32_t lo = (uint32_t)prow[l.x & 255u] | ((uint32_t)prow[(l.x >> 8) & 255u] << 8) |
+                                    ((uint32_t)prow[(l.x >> 16) & 255u] << 16) | ((uint32_t)prow[l.x >> 24] << 24);
+                const uint32_t hi = (uint32_t)prow[l.y & 255u] | ((uint32_t)prow[(l.y >> 8) & 255u] << 8) |
+                                    ((uint32_t)prow[(l.y >> 16) & 255u] << 16) | ((uint32_t)prow[l.y >> 24] << 24);
+                uint8_t* o = base + (size_t)i * bs * a.row_pitch + 8 * c8;
+                for (int di = 0; di < bs; ++di) *(uint2*)(o + (size_t)di * a.row_pitch) = make_uint2(lo, hi);
+            }
+        } else if (rows > 0 && cols > 0) {
+            for (int idx = lane; idx < rows * cols; idx += 32) {
+                const int r = idx / cols, cc = idx - r * cols;
+                dst[(size_t)(y0 + r) * a.row_pitch + x0 + cc] = sPix[(r / bs) * D + cc / bs];
+            }
+        }
+        __syncwarp();                                            // sPix and sY are rewritten by the next block
+    }
+}
+
+template <int D, int MODE>
+static cudaError_t iw_launch_t(const JbInvArgs& a, cudaStream_t s) {
+    const size_t smem = iw_layout(D, a.g.bs).total;
+    cudaError_t e = cudaFuncSetAttribute(jb_inv_mid_warp_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    jb_inv_mid_warp_kernel<D, MODE><<<a.n_chunks, IW_WARPS * 32, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+template <int MODE>
+static cudaError_t iw_launch_d(const JbInvArgs& a, cudaStream_t s) {
+    switch (a.g.d) {
+    case 16: return iw_launch_t<16, MODE>(a, s);
+    case 24: return iw_launch_t<24, MODE>(a, s);
+    default: return iw_launch_t<32, MODE>(a, s);
+    }
+}
+
 template <bool DFT, int MODE>
 static cudaError_t im_launch_t(const JbInvArgs& a, cudaStream_t s) {
     const size_t smem = im_layout(a.g.d, a.g.bs, DFT).total;
@@ -232,6 +408,8 @@ static cudaError_t im_launch_t(const JbInvArgs& a, cudaStream_t s) {
 cudaError_t jb_launch_inv_mid(const JbInvArgs& a, int mode, cudaStream_t s) {
     if (a.n_chunks == 0) return cudaSuccess;
     const bool dft = a.g.transform == JB_TRANSFORM_DFT;
+    if (iw_eligible(a.g) && !(a.g.flags & JB_FLAG_NO_TMA))         // (JB_FLAG_NO_TMA doubles as "plain variant" for the tests)
+        return mode == 0 ? iw_launch_d<0>(a, s) : iw_launch_d<2>(a, s);
     if (mode == 0) return dft ? im_launch_t<true, 0>(a, s) : im_launch_t<false, 0>(a, s);
     return dft ? im_launch_t<true, 2>(a, s) : im_launch_t<false, 2>(a, s);
 }
