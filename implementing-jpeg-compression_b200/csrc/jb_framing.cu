@@ -329,15 +329,28 @@ __global__ void __launch_bounds__(JB_WALK_THREADS) jb_frame_walk_smem_kernel(JbF
             // true offset of a valid stream never exceeds the count.  The transform kernel checks it.)
             // a block that ends at or beyond this bit leaves the tile (the staged window reaches further)
             const uint32_t lim_bits = tend_s * 8u - 8u;
+            const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(mine);
             for (;;) {
-                const uint32_t idx = p >> 5;
-                const uint32_t x = __funnelshift_l(mine[idx + 1], mine[idx], p);
-                const uint32_t head = x >> 24;
-                p += 8u + (head & 15u);
-                uint32_t eob = x < 0x01000000u ? 1u : 0u;
-                const bool bad = (head & 14u) == 0u && head != 0xF0u && x >= 0x01000000u;
+                // Two codes per pass from one 32-bit window: a code is at most 8 + 15 bits long, so the head of
+                // the code behind it lies inside the window too.  The second code counts only if the first one
+                // neither ends the block (the next block starts on a byte boundary) nor is impossible.
+                const uint32_t wa = s_base + ((p >> 3) & ~3u);
+                uint32_t w0, w1;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(wa));
+                asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(wa));
+                const uint32_t x1 = __funnelshift_l(w1, w0, p);
+                // "stop": the code ends the block (EOB) or is impossible ((r, 0) with 0 < r < 15, or size 1)
+                const uint32_t a1 = 8u + ((x1 >> 24) & 15u);
+                const bool stop1 = (x1 & 0x0E000000u) == 0u && (x1 & 0xFF000000u) != 0xF0000000u;
+                const uint32_t x2 = x1 << a1;
+                const uint32_t xs = stop1 ? x1 : x2;                 // the code that decides this pass
+                const uint32_t a2 = stop1 ? 0u : 8u + ((x2 >> 24) & 15u);
+                p += a1 + a2;
+                const bool stop = (xs & 0x0E000000u) == 0u && (xs & 0xFF000000u) != 0xF0000000u;
+                const bool bad = stop && xs >= 0x01000000u;
+                uint32_t eob = stop ? 1u : 0u;                        // (a stop that is not an EOB takes the branch below)
                 q = (p + 7u) >> 3;
-                if (bad || (x < 0x01000000u && p > lim_bits)) {
+                if (stop && (xs >= 0x01000000u || p > lim_bits)) {
                     bool false_start = bad;
                     if (p > staged_bits) {
                         // zero fill was parsed: repeat this block from global memory
@@ -677,12 +690,16 @@ cudaError_t jb_launch_framing(const JbFrameArgs& f_in, cudaStream_t s) {
     if ((size_t)f.max_tiles <= (size_t)f.n_planes * (JB_STITCH_CAP / 4u)) {
         // many short streams (a batch of images): the rest of the framing in one launch, one CTA per stream;
         // a stream of more than `cap` tiles (far longer than its peers) takes the serial walk
-        unsigned cap = f.max_tiles < JB_STITCH_CAP ? f.max_tiles : JB_STITCH_CAP;
+        // The kernel is a chain of short dependent phases (latency bound): streams of a few hundred tiles get
+        // narrower CTAs and half the table space, so that twice as many of them are resident per SM.
+        const bool small = (size_t)f.max_tiles <= (size_t)f.n_planes * 256u;
+        const unsigned cap_max = small ? JB_STITCH_CAP / 2u : JB_STITCH_CAP;
+        unsigned cap = f.max_tiles < cap_max ? f.max_tiles : cap_max;
         cap = (cap + 7u) & ~7u;
         size_t smem = 5 * (size_t)cap;
         if (smem < (JB_SERIAL_WORDS + 8) * 4) smem = (JB_SERIAL_WORDS + 8) * 4;
         f.stitch_cap = cap;
-        jb_frame_stitch_kernel<<<f.n_planes, JB_STITCH_THREADS, smem, s>>>(f);
+        jb_frame_stitch_kernel<<<f.n_planes, small ? JB_STITCH_THREADS / 2 : JB_STITCH_THREADS, smem, s>>>(f);
         return cudaGetLastError();
     }
     {   // chain of tiles: streams of up to 4096 tiles (1 MB) in 20 KB of shared memory, longer ones in 200 KB
