@@ -19,6 +19,7 @@ JB_ERR_BAD_STREAM, JB_ERR_NO_DEVICE = -9, -10
 JB_FLAG_FORCE_GENERIC, JB_FLAG_NO_TMA, JB_FLAG_NO_REFINE, JB_FLAG_SERIAL_FRAMING = 1, 2, 4, 8
 JB_FLAG_REUSE_TABLES = 16
 JB_FLAG_STRIP_DECODER = 32
+JB_FLAG_TILE_DECODER = 64
 JB_STATUS_WORDS = 4
 JB_MAX_DCT_SIZE = 32
 JB_MAX_BLOCK_SIZE = 255
@@ -62,6 +63,7 @@ SYMBOLS = {
     "jb_ycbcr_planes_to_rgb": (_I, [_P, _SZ, _SZ, _I, _I, _I, _P, _SZ, _SZ, _P]),
     "jb_containers_max_bytes": (_SZ, [_I, _I, _SZ]),
     "jb_pack_containers": (_I, [_P, _P, _I, ctypes.c_char_p, _I, _P, _SZ, _P, _P, _P]),
+    "jb_debug_kernel_events": (_I, [_P, _P, _P, _P]),
 }
 
 _lib = None

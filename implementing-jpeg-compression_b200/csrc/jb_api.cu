@@ -126,6 +126,7 @@ static int jb_forward_common(int mode, const uint8_t* d_planes, size_t plane_str
     a.chunk_cap = w.chunk_cap;
     a.coeffs_out = d_coeffs_out; a.coeffs_in = d_coeffs_in;
     if (mode != 2 && !(g.flags & JB_FLAG_REUSE_TABLES)) JB_CUDA_TRY(jb_launch_build_tables(g, a.t, s));
+    if (mode == 0) jb_prof_mark(0, s);                 // (the matching end mark sits in jb_launch_scan_gather)
     if (mode != 2 && !(g.flags & JB_FLAG_FORCE_GENERIC) && jb_fwd_fast_eligible(g))
         JB_CUDA_TRY(jb_launch_fwd_fast(a, mode, s));
     else if (mode != 2 && !(g.flags & JB_FLAG_FORCE_GENERIC) && jb_fwd_mid_eligible(g))
@@ -174,6 +175,20 @@ extern "C" int jb_stage_pack(const int32_t* d_coeffs, int n_planes, int blocks_p
     g.bs = 1;
     return jb_forward_common(2, nullptr, 0, 0, n_planes, g, d_out, out_cap, d_plane_off, d_status, nullptr,
                              d_coeffs, d_ws, ws_bytes, (cudaStream_t)stream);
+}
+
+// ---- measurement hook ------------------------------------------------------------------------------
+static cudaEvent_t g_prof_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+
+extern "C" int jb_debug_kernel_events(void* fwd_begin, void* fwd_end, void* inv_begin, void* inv_end) {
+    if ((fwd_begin == nullptr) != (fwd_end == nullptr) || (inv_begin == nullptr) != (inv_end == nullptr)) return JB_ERR_BAD_PARAM;
+    g_prof_ev[0] = (cudaEvent_t)fwd_begin; g_prof_ev[1] = (cudaEvent_t)fwd_end;
+    g_prof_ev[2] = (cudaEvent_t)inv_begin; g_prof_ev[3] = (cudaEvent_t)inv_end;
+    return JB_OK;
+}
+
+void jb_prof_mark(int which, cudaStream_t s) {
+    if (g_prof_ev[which]) cudaEventRecord(g_prof_ev[which], s);
 }
 
 // ---- decompress --------------------------------------------------------------------------------
@@ -245,12 +260,14 @@ static int jb_inverse_common(int mode, const uint8_t* d_in, size_t in_bytes, con
         return JB_ERR_WORKSPACE;
     }
     if (mode != 1 && !(g.flags & JB_FLAG_REUSE_TABLES)) JB_CUDA_TRY(jb_launch_build_tables(g, a.t, s));
+    if (mode == 0) jb_prof_mark(2, s);
     if (mode != 1 && !(g.flags & JB_FLAG_FORCE_GENERIC) && jb_inv_fast_eligible(g))
         JB_CUDA_TRY(jb_launch_inv_fast(a, mode, s));
     else if (mode != 1 && !(g.flags & JB_FLAG_FORCE_GENERIC) && jb_inv_mid_eligible(g))
         JB_CUDA_TRY(jb_launch_inv_mid(a, mode, s));
     else
         JB_CUDA_TRY(jb_launch_inv_generic(a, mode, s));
+    if (mode == 0) jb_prof_mark(3, s);
     return JB_OK;
 }
 

@@ -142,3 +142,6 @@ __device__ __forceinline__ unsigned jb_block_excl_scan(unsigned v, unsigned* s_w
 // Host-side API internals shared between translation units.
 int jb_make_geom(const jb_params* p, JbGeom* g);
 cudaError_t jb_launch_build_tables(const JbGeom& g, const JbTables& t, cudaStream_t s);
+// Measurement hook (jb_debug_kernel_events): records event `which` (0/1 around the fused forward kernel, 2/3
+// around the fused inverse kernel) on the stream if the caller armed it; a no-op otherwise.
+void jb_prof_mark(int which, cudaStream_t s);

@@ -339,6 +339,7 @@ __global__ void __launch_bounds__(256) jb_gather_chunks_kernel(JbFwdArgs a) {
 }
 
 cudaError_t jb_launch_scan_gather(const JbFwdArgs& a, cudaStream_t s) {
+    jb_prof_mark(1, s);                                // the fused forward kernel was launched just before
     if (a.n_chunks == 0) return cudaSuccess;
     const unsigned n_seg = (a.n_chunks + JB_SCAN_SEG - 1) / JB_SCAN_SEG;
     jb_scan_local_kernel<<<n_seg, JB_SCAN_SEG, 0, s>>>(a);

@@ -692,7 +692,8 @@ cudaError_t jb_launch_framing(const JbFrameArgs& f_in, cudaStream_t s) {
         // a stream of more than `cap` tiles (far longer than its peers) takes the serial walk
         // The kernel is a chain of short dependent phases (latency bound): streams of a few hundred tiles get
         // narrower CTAs and half the table space, so that twice as many of them are resident per SM.
-        const bool small = (size_t)f.max_tiles <= (size_t)f.n_planes * 256u;
+        // (not when every stream already has its own CTA of full width in a single wave: 148 SMs x 8)
+        const bool small = (size_t)f.max_tiles <= (size_t)f.n_planes * 256u && f.n_planes > 148 * 8;
         const unsigned cap_max = small ? JB_STITCH_CAP / 2u : JB_STITCH_CAP;
         unsigned cap = f.max_tiles < cap_max ? f.max_tiles : cap_max;
         cap = (cap + 7u) & ~7u;

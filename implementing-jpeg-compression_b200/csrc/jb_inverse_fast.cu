@@ -22,8 +22,20 @@
 
 #define FI_WARPS 16
 #define FI_RING 2
+#define FI_SAMPLE_PITCH 68              // bytes per block in the sample buffer of the row-store variant (64 + 4:
+                                        // the word reads of a store row fall into distinct banks)
 #define FI_STREAM_WORDS 400             // staged chunk bytes (1.6 KB; the average chunk is ~0.6 KB); denser
                                         // chunks are decoded straight from global memory
+
+#define FI_ROWS_WARPS 24                // row-store variant: 72 registers and 7.8 KB of shared memory per warp
+#define FI_ROWS_STAGE_WORDS 512
+
+// per-warp shared memory of the row-store variant: the chunk's bytes, then (once decoded) its 8-bit samples
+struct __align__(128) FiRowsSmem {
+    uint8_t buf[2304];                  // max(4 FI_ROWS_STAGE_WORDS, 32 FI_SAMPLE_PITCH)
+    float scr[4 * FF_BLK_W];
+    uint32_t coef[JB_CHUNK * FF_COEF_W];
+};
 
 struct __align__(128) FiWarpSmem {
     uint8_t tile[FI_RING][FF_TILE_BYTES];
@@ -86,15 +98,20 @@ __device__ __forceinline__ int fi_tile_kind(const JbGeom& g, int nvalid, const F
     return ((c.bx + 4) * 32 <= g.W && (c.by + 1) * 32 <= g.H) ? 0 : 1;
 }
 
-template <bool DFT, int MODE>
-__global__ void __launch_bounds__(FI_WARPS * 32, 1)
+template <bool DFT, int MODE, bool ROWS>
+__global__ void __launch_bounds__((ROWS ? FI_ROWS_WARPS : FI_WARPS) * 32, 1)
 jb_inv_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FiKernelArgs ka) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const JbInvArgs& a = ka.a;
     const JbGeom& g = a.g;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t* s_izz = (uint8_t*)smem_raw;                               // zigzag position -> natural index
-    FiWarpSmem& ws = *(FiWarpSmem*)(smem_raw + 128 + (size_t)warp * sizeof(FiWarpSmem));
+    constexpr int NWARPS = ROWS ? FI_ROWS_WARPS : FI_WARPS;
+    constexpr unsigned STAGE_WORDS = ROWS ? FI_ROWS_STAGE_WORDS : FI_STREAM_WORDS;
+    FiWarpSmem& ws = *(FiWarpSmem*)(smem_raw + 128 + (size_t)warp * sizeof(FiWarpSmem));           // tile variant
+    FiRowsSmem& wr = *(FiRowsSmem*)(smem_raw + 128 + (size_t)warp * sizeof(FiRowsSmem));           // row variant
+    uint32_t* const w_coef = ROWS ? wr.coef : ws.coef;
+    float* const w_scr = ROWS ? wr.scr : ws.scr;
     for (int i = threadIdx.x; i < 64; i += blockDim.x) s_izz[i] = (uint8_t)a.t.izz[i];
     __syncthreads();
 
@@ -108,9 +125,9 @@ jb_inv_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FiKernelArgs 
         dq[v] = a.t.dqmult[li * 8 + v] * sc;
     }
 
-    const unsigned total_warps = gridDim.x * FI_WARPS;
+    const unsigned total_warps = gridDim.x * NWARPS;
     unsigned store_seq = 0;
-    for (unsigned chunk = blockIdx.x * FI_WARPS + warp; chunk < a.n_chunks; chunk += total_warps) {
+    for (unsigned chunk = blockIdx.x * NWARPS + warp; chunk < a.n_chunks; chunk += total_warps) {
         const int plane = (int)(chunk / (unsigned)g.cpp);
         const int blk0 = (int)(chunk % (unsigned)g.cpp) * JB_CHUNK;
         const int nvalid = jb_min(JB_CHUNK, g.nblocks - blk0);
@@ -118,14 +135,14 @@ jb_inv_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FiKernelArgs 
 
         // ---- coefficients of the chunk in natural order ----
         {
-            uint4* z = (uint4*)ws.coef;
+            uint4* z = (uint4*)w_coef;
             for (int i = lane; i < JB_CHUNK * FF_COEF_W / 4; i += 32) z[i] = make_uint4(0, 0, 0, 0);
         }
         __syncwarp();
         if (MODE == 2) {
             const int16_t* src = a.coeffs_in + ((size_t)plane * g.nblocks + blk0) * 64;
             for (int idx = lane; idx < nvalid * 64; idx += 32)
-                ((int16_t*)(ws.coef + (idx >> 6) * FF_COEF_W))[s_izz[idx & 63]] = src[idx];
+                ((int16_t*)(w_coef + (idx >> 6) * FF_COEF_W))[s_izz[idx & 63]] = src[idx];
         } else {
             const unsigned long long len = a.plane_len[plane];
             const uint8_t* stream = a.in + a.plane_off[plane];
@@ -139,18 +156,20 @@ jb_inv_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FiKernelArgs 
             const bool ok = c_start <= c_end && c_end <= len;
             const uint32_t* wsrc = (const uint32_t*)(uintptr_t)(addr0 - mis);
             const unsigned nwords = ok ? (((c_end - c_start) + mis + 3u) >> 2) : 0u;
-            const bool staged = nwords <= FI_STREAM_WORDS;
+            const bool staged = nwords <= STAGE_WORDS;
             // the chunk's bytes are staged in the ring slot that the next tile will use: the store issued
             // from it two tiles ago has to be done reading it
-            uint32_t* sbytes = (uint32_t*)ws.tile[store_seq % FI_RING];
-            if (lane == 0) ff_bulk_wait_read<FI_RING - 1>();
-            __syncwarp();
+            uint32_t* sbytes = ROWS ? (uint32_t*)wr.buf : (uint32_t*)ws.tile[store_seq % FI_RING];
+            if (!ROWS) {
+                if (lane == 0) ff_bulk_wait_read<FI_RING - 1>();
+                __syncwarp();
+            }
             if (ok && staged)
                 for (unsigned i = lane; i < nwords; i += 32) sbytes[i] = __ldg(wsrc + i);
             __syncwarp();
             int bad = ok ? 0 : 1;
             if (ok && lane < nvalid) {
-                int16_t* row = (int16_t*)(ws.coef + lane * FF_COEF_W);
+                int16_t* row = (int16_t*)(w_coef + lane * FF_COEF_W);
                 const uint32_t bit0 = (my_start - c_start + mis) * 8u, bitl = (c_end - c_start + mis) * 8u;
                 if (my_start < c_start || my_start >= c_end) bad = 1;
                 else if (staged) bad = fi_decode_block<false>(sbytes, nwords, bit0, bitl, row, s_izz);
@@ -166,14 +185,16 @@ jb_inv_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FiKernelArgs 
         for (int it = 0; it < nit; ++it) {
             const int slot = (int)(store_seq % FI_RING);
             uint8_t* tile = ws.tile[slot];
-            const int kind = fi_tile_kind(g, nvalid, cur, ka.aligned != 0);
+            const int kind = ROWS ? 0 : fi_tile_kind(g, nvalid, cur, ka.aligned != 0);
             // the TMA store issued FI_RING tiles ago must have finished reading this slot
-            if (lane == 0) ff_bulk_wait_read<FI_RING - 1>();
-            __syncwarp();
+            if (!ROWS) {
+                if (lane == 0) ff_bulk_wait_read<FI_RING - 1>();
+                __syncwarp();
+            }
 
             float z[8], r[8];
             {
-                const uint4 w = *(const uint4*)(ws.coef + (4 * it + lb) * FF_COEF_W + li * 4);
+                const uint4 w = *(const uint4*)(w_coef + (4 * it + lb) * FF_COEF_W + li * 4);
                 z[0] = (float)(short)(w.x & 0xFFFFu) * dq[0]; z[1] = (float)(short)(w.x >> 16) * dq[1];
                 z[2] = (float)(short)(w.y & 0xFFFFu) * dq[2]; z[3] = (float)(short)(w.y >> 16) * dq[3];
                 z[4] = (float)(short)(w.z & 0xFFFFu) * dq[4]; z[5] = (float)(short)(w.z >> 16) * dq[5];
@@ -181,7 +202,7 @@ jb_inv_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FiKernelArgs 
             }
             if (DFT) ff_rdft8(z, r); else ff_idct8(z, r);
             {
-                float4* sc = (float4*)(ws.scr + lb * FF_BLK_W + li * 8);
+                float4* sc = (float4*)(w_scr + lb * FF_BLK_W + li * 8);
                 const int h0 = li & 1;
                 const float4 r0 = make_float4(r[0], r[1], r[2], r[3]), r1 = make_float4(r[4], r[5], r[6], r[7]);
                 sc[h0] = h0 ? r1 : r0; sc[h0 ^ 1] = h0 ? r0 : r1;
@@ -189,11 +210,24 @@ jb_inv_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FiKernelArgs 
             __syncwarp();
             float col[8], x[8];
             #pragma unroll
-            for (int k = 0; k < 8; ++k) col[k] = ws.scr[lb * FF_BLK_W + k * 8 + li];
+            for (int k = 0; k < 8; ++k) col[k] = w_scr[lb * FF_BLK_W + k * 8 + li];
             if (DFT) ff_dft_column_stage(col, li, x); else ff_idct8(col, x);
 
-            // round half-even, clamp to 0..255, replicate 4x4: word column 8b + ncol, rows 4m..4m+3
+            // round half-even, clamp to 0..255
             uint32_t* t32 = (uint32_t*)tile;
+            if (ROWS) {
+                // sample (m, ncol) of block 4 it + lb, one byte each; the chunk goes out row by row below
+                uint8_t* sp = wr.buf + (4 * it + lb) * FI_SAMPLE_PITCH + ncol;
+                #pragma unroll
+                for (int m = 0; m < 8; ++m) {
+                    int p = __float_as_int(x[m] + 12582912.0f) - 0x4B400000;
+                    sp[m * 8] = (uint8_t)max(0, min(255, p));
+                }
+                ++cur.it;
+                __syncwarp();
+                continue;
+            }
+            // replicate 4x4: word column 8b + ncol, rows 4m..4m+3
             #pragma unroll
             for (int m = 0; m < 8; ++m) {
                 int p = __float_as_int(x[m] + 12582912.0f) - 0x4B400000;
@@ -241,9 +275,55 @@ jb_inv_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FiKernelArgs 
             while (cur.bx >= g.hb) { cur.bx -= g.hb; ++cur.by; }
             __syncwarp();
         }
+        if (ROWS) {
+            // ---- the chunk, pixel row by pixel row: a lane pair owns a block (lane & 1 = its left / right half),
+            // blocks blk0 .. blk0+15 in the first store of a row and blk0+16 .. blk0+31 in the second, so one store
+            // instruction covers up to 512 contiguous bytes and the chunk's 32 rows are 1 KB runs.  HBM takes such
+            // rows at ~6.1 TB/s, 32-row x 128-byte tiles at ~5.2 (tools/dram_probe_rows.cu).  Every sample byte
+            // becomes 4 bytes (util.inflate along x) and every sample row 4 pixel rows (along y); rows and columns
+            // beyond the image are not written (the two crops). ----
+            const int half = lane & 1;
+            uint8_t* plane_ptr = a.planes_out + (size_t)plane * a.plane_stride;
+            uint8_t* dstp[2];
+            int rows_ok[2], cols_ok[2];
+            #pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int b = 16 * h + (lane >> 1);
+                const int blk = blk0 + b;
+                const int by = blk / g.hb, bx = blk - by * g.hb;
+                const int x0 = bx * 32 + 16 * half;
+                dstp[h] = plane_ptr + (size_t)by * 32 * a.row_pitch + x0;
+                rows_ok[h] = b < nvalid ? jb_min(32, g.H - by * 32) : 0;
+                cols_ok[h] = jb_min(16, g.W - x0);
+            }
+            const uint8_t* sbase = wr.buf + (lane >> 1) * FI_SAMPLE_PITCH + 4 * half;
+            #pragma unroll 2
+            for (int m = 0; m < 8; ++m) {
+                #pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t w = *(const uint32_t*)(sbase + 16 * h * FI_SAMPLE_PITCH + m * 8);
+                    const uint4 v = make_uint4(__byte_perm(w, 0, 0x0000), __byte_perm(w, 0, 0x1111),
+                                               __byte_perm(w, 0, 0x2222), __byte_perm(w, 0, 0x3333));
+                    uint8_t* d = dstp[h] + (size_t)(4 * m) * a.row_pitch;
+                    const int nrows = rows_ok[h] - 4 * m;
+                    if (ka.aligned && cols_ok[h] == 16) {
+                        #pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (k < nrows) *(uint4*)(d + (size_t)k * a.row_pitch) = v;
+                    } else if (cols_ok[h] > 0) {
+                        const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+                        for (int k = 0; k < 4 && k < nrows; ++k)
+                            for (int q = 0; q < cols_ok[h]; ++q) d[(size_t)k * a.row_pitch + q] = (uint8_t)vv[q >> 2];
+                    }
+                }
+            }
+            __syncwarp();                                     // the sample buffer is rewritten by the next chunk
+        }
     }
-    if (lane == 0) ff_bulk_wait_read<0>();
-    __syncwarp();
+    if (!ROWS) {
+        if (lane == 0) ff_bulk_wait_read<0>();
+        __syncwarp();
+    }
 }
 
 // =====================================================================================================
@@ -492,22 +572,29 @@ cudaError_t jb_launch_inv_strip(const JbInvArgs& a, cudaStream_t s) {
 
 bool jb_inv_fast_eligible(const JbGeom& g) { return g.d == 8 && g.bs == 4; }
 
-template <bool DFT, int MODE>
+template <bool DFT, int MODE, bool ROWS>
 static cudaError_t jb_inv_fast_launch_t(const CUtensorMap& map, const FiKernelArgs& ka, cudaStream_t s) {
-    const size_t smem = 128 + (size_t)FI_WARPS * sizeof(FiWarpSmem);
-    cudaError_t e = cudaFuncSetAttribute(jb_inv_fast_kernel<DFT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    constexpr int NWARPS = ROWS ? FI_ROWS_WARPS : FI_WARPS;
+    const size_t smem = 128 + (size_t)NWARPS * (ROWS ? sizeof(FiRowsSmem) : sizeof(FiWarpSmem));
+    cudaError_t e = cudaFuncSetAttribute(jb_inv_fast_kernel<DFT, MODE, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jb_inv_fast_kernel<DFT, MODE>, FI_WARPS * 32, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jb_inv_fast_kernel<DFT, MODE, ROWS>, NWARPS * 32, smem);
     if (per_sm < 1) per_sm = 1;
-    unsigned want = (ka.a.n_chunks + FI_WARPS - 1) / FI_WARPS;
+    unsigned want = (ka.a.n_chunks + NWARPS - 1) / NWARPS;
     unsigned grid = want < (unsigned)(sms * per_sm) ? want : (unsigned)(sms * per_sm);
     if (grid == 0) return cudaSuccess;
-    jb_inv_fast_kernel<DFT, MODE><<<grid, FI_WARPS * 32, smem, s>>>(map, ka);
+    jb_inv_fast_kernel<DFT, MODE, ROWS><<<grid, NWARPS * 32, smem, s>>>(map, ka);
     return cudaGetLastError();
+}
+
+template <bool ROWS>
+static cudaError_t jb_inv_fast_launch_r(const CUtensorMap& map, const FiKernelArgs& ka, bool dft, int mode, cudaStream_t s) {
+    if (mode == 0) return dft ? jb_inv_fast_launch_t<true, 0, ROWS>(map, ka, s) : jb_inv_fast_launch_t<false, 0, ROWS>(map, ka, s);
+    return dft ? jb_inv_fast_launch_t<true, 2, ROWS>(map, ka, s) : jb_inv_fast_launch_t<false, 2, ROWS>(map, ka, s);
 }
 
 cudaError_t jb_launch_inv_fast(const JbInvArgs& a, int mode, cudaStream_t s) {
@@ -520,9 +607,11 @@ cudaError_t jb_launch_inv_fast(const JbInvArgs& a, int mode, cudaStream_t s) {
     CUtensorMap map;
     memset(&map, 0, sizeof(map));
     ka.use_tma = 0;
+    const bool dft = g.transform == JB_TRANSFORM_DFT;
+    // default: the chunk goes out row by row with 128-bit stores (no tile, no tensor map); JB_FLAG_TILE_DECODER keeps
+    // the 4-block tiles, stored by TMA (or by plain stores with JB_FLAG_NO_TMA)
+    if (!(g.flags & JB_FLAG_TILE_DECODER)) return jb_inv_fast_launch_r<true>(map, ka, dft, mode, s);
     if (!(g.flags & JB_FLAG_NO_TMA) && ka.aligned)
         ka.use_tma = jb_make_plane_tensor_map(&map, a.planes_out, g.W, g.H, a.n_planes, a.row_pitch, a.plane_stride) ? 1 : 0;
-    const bool dft = g.transform == JB_TRANSFORM_DFT;
-    if (mode == 0) return dft ? jb_inv_fast_launch_t<true, 0>(map, ka, s) : jb_inv_fast_launch_t<false, 0>(map, ka, s);
-    return dft ? jb_inv_fast_launch_t<true, 2>(map, ka, s) : jb_inv_fast_launch_t<false, 2>(map, ka, s);
+    return jb_inv_fast_launch_r<false>(map, ka, dft, mode, s);
 }

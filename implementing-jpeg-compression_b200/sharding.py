@@ -41,3 +41,34 @@ def concat_band_streams(per_rank_streams):
     contribute nothing).  Returns one stream per colour plane for the whole image."""
     n_planes = max((len(s) for s in per_rank_streams if s), default=0)
     return [b"".join(s[c] for s in per_rank_streams if s) for c in range(n_planes)]
+
+
+def bind_host_to_device(device_index):
+    """Pin the calling process to the CPU cores next to GPU `device_index` (NVML's ideal CPU affinity), so that
+    the pinned staging buffers it allocates afterwards are first-touched on the GPU's own NUMA node.  With one
+    process per GPU the host side of the PCIe links is the bound of the end-to-end path (6.5 GB each way per
+    batch), and copies that cross the socket interconnect share its bandwidth between all ranks.
+
+    Returns the sorted list of cores, or None when NVML or the affinity call is unavailable (nothing is changed
+    then).  The device is looked up by UUID, so CUDA_VISIBLE_DEVICES remapping is honoured."""
+    import os
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            handle = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (n_cpu + 63) // 64)
+        cores = [64 * i + b for i, wd in enumerate(words) for b in range(64) if (int(wd) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cores = sorted(c for c in cores if c in allowed)
+        if not cores:
+            return None
+        os.sched_setaffinity(0, cores)
+        return cores
+    except Exception:
+        return None

@@ -82,6 +82,8 @@ typedef struct jb_params {
 #define JB_FLAG_SERIAL_FRAMING 8 /* decoder: find block boundaries with the serial fallback walk only */
 #define JB_FLAG_STRIP_DECODER 32 /* decoder: use the CTA-wide strip kernel where it applies (dense planes, width a
                                    whole number of 48..64-block segments); experimental, measured slower */
+#define JB_FLAG_TILE_DECODER 64  /* decoder, 8x8 / block_size 4 kernel: store 32-row x 128-byte tiles (TMA tensor stores,
+                                   or plain stores with JB_FLAG_NO_TMA) instead of whole chunk rows; kept for comparison */
 #define JB_FLAG_REUSE_TABLES  16 /* the caller promises that this workspace was last used by a call of the same
                                    direction with identical transform / size / quantiser parameters and has not
                                    been written since: the table builder launch is skipped */
@@ -202,6 +204,15 @@ size_t jb_containers_max_bytes(int n_images, int header_len, size_t stream_bytes
 int jb_pack_containers(const uint8_t* d_streams, const uint64_t* d_plane_off, int n_images, const uint8_t* header,
                        int header_len, uint8_t* d_out, size_t out_cap, uint64_t* d_image_off, uint64_t* d_status,
                        void* stream);
+
+/* ---- measurement hook (bench.py's roofline figure) ----------------------------------------------------------
+ * Brackets the dominant kernel of the next calls with caller-owned CUDA events (cudaEvent_t handles, created
+ * with timing enabled): jb_compress_planes records fwd_begin / fwd_end around its fused transform kernel only
+ * (not the scan and gather launches that follow), jb_decompress_planes records inv_begin / inv_end around its
+ * fused inverse kernel only (not the framing launches before it).  NULL handles switch a pair off; all NULL is
+ * the default.  Process-wide and not thread safe: a profiling aid, not part of the data path; do not capture
+ * calls into a CUDA graph while it is armed.  The reference has no counterpart. */
+int jb_debug_kernel_events(void* fwd_begin, void* fwd_end, void* inv_begin, void* inv_end);
 
 #ifdef __cplusplus
 }

@@ -10,8 +10,10 @@ from parity import check_pixels, check_quantised
 
 pytestmark = pytest.mark.gpu
 
-# JB_FLAG_FORCE_GENERIC = 1, JB_FLAG_NO_TMA = 2 (specialised kernels with plain loads / stores)
-FLAG_SETS = [pytest.param(0, id="default"), pytest.param(1, id="generic"), pytest.param(2, id="no_tma")]
+# JB_FLAG_FORCE_GENERIC = 1, JB_FLAG_NO_TMA = 2 (specialised kernels with plain loads / stores),
+# JB_FLAG_TILE_DECODER = 64 (8x8 decoder stores 4-block tiles -- by TMA, or with 2 by plain stores -- instead of chunk rows)
+FLAG_SETS = [pytest.param(0, id="default"), pytest.param(1, id="generic"), pytest.param(2, id="no_tma"),
+             pytest.param(64, id="tile_decoder"), pytest.param(66, id="tile_decoder_no_tma")]
 
 
 @pytest.fixture(scope="module")
@@ -78,6 +80,8 @@ GRID = [
     (64, 64, 2, 16, "DCT", "divide", 20), (50, 60, 1, 32, "DCT", "divide", 50),
     (30, 30, 7, 3, "DCT", "none", None), (20, 20, 1, 1, "DCT", "none", None),
     (64, 64, 16, 2, "DFT", "none", None),
+    # aligned planes whose last block column is half inside the image (the row stores of the 8x8 decoder)
+    (40, 48, 4, 8, "DCT", "qtable", None), (72, 176, 4, 8, "DFT", "qtable", None),
 ]
 
 
@@ -360,11 +364,12 @@ def test_strip_decoder_equals_tile_decoder(jb, h, w, n, tr):
     comp = jb.compress_planes(torch.from_numpy(planes).cuda(), cfg)
     lens = comp.offsets[1:] - comp.offsets[:-1]
     outs = {}
-    for flags in (0, 32, 1):
+    for flags in (0, 64, 32, 1):
         out, status = jb.decompress_planes(comp.data, comp.offsets[:-1], lens, cfg, n, in_bytes=comp.total_bytes(), flags=flags)
         jb.check_status(status)
         outs[flags] = out.cpu().numpy()
     assert np.array_equal(outs[0], outs[32])
+    assert np.array_equal(outs[0], outs[64])
     assert np.abs(outs[0].astype(np.int64) - outs[1].astype(np.int64)).max() <= 1
     streams = comp.to_bytes_list()
     want = rp.decompress_band(streams[n - 1], ocfg)
