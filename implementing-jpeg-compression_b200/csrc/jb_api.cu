@@ -249,6 +249,7 @@ static int jb_inverse_common(int mode, const uint8_t* d_in, size_t in_bytes, con
         f.tile_hops = (unsigned*)(ws + L.tile_hops);
         f.tile_base = (unsigned*)(ws + L.tile_base);
         f.vbits = (uint32_t*)(ws + L.vbits);
+        f.ticket = (unsigned*)(ws + L.ticket);
         f.status = (unsigned long long*)d_status;
         // (a stream that fails framing leaves its part of block_start unwritten; the call then reports
         // JB_ERR_BAD_STREAM and the transform kernels check every offset they read against the stream bounds)
@@ -256,6 +257,7 @@ static int jb_inverse_common(int mode, const uint8_t* d_in, size_t in_bytes, con
         a.in = d_in; a.in_bytes = in_bytes;
         a.plane_off = f.plane_off; a.plane_len = f.plane_len;
         a.block_start = f.block_start;
+        a.ticket = f.ticket;
     } else if (ws_bytes < table_bytes) {
         return JB_ERR_WORKSPACE;
     }

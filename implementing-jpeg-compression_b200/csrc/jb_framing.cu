@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(1024) jb_frame_prep_kernel(JbFrameArgs f) {
     __shared__ unsigned s_warp[33];
     unsigned carry = 0;
     bool bad = false;
-    if (threadIdx.x == 0) f.big_list[0] = 0u;
+    if (threadIdx.x == 0) { f.big_list[0] = 0u; *f.ticket = 0u; }
     // first kernel of the decompress call: reset the status block (word 1 = "no bad code yet")
     if (threadIdx.x < JB_STATUS_WORDS) f.status[threadIdx.x] = threadIdx.x == 1 ? ~0ull : 0ull;
     __syncthreads();

@@ -36,6 +36,7 @@ struct JbDecLayout {
     size_t tile_hops;    // uint32 [max_tiles]  true blocks that start inside the tile
     size_t tile_base;    // uint32 [max_tiles]  ordinal (within the stream) of the tile's first true block
     size_t vbits;        // uint32 [max_tiles * tile_bytes / 32]  bit b of a tile: its walk saw a block start at byte b
+    size_t ticket;       // uint32  next chunk of the transform kernel (reset by the framing prep kernel)
     size_t total;
     unsigned max_tiles;
     unsigned tile_bytes;
@@ -59,6 +60,7 @@ static inline JbDecLayout jb_dec_layout(int d, int n_planes, long long nblocks_p
     L.tile_hops = o;   o += jb_align_up((size_t)L.max_tiles * 4, 256);
     L.tile_base = o;   o += jb_align_up((size_t)L.max_tiles * 4, 256);
     L.vbits = o;       o += jb_align_up((size_t)L.max_tiles * (L.tile_bytes / 8), 256);
+    L.ticket = o;      o += 256;
     L.total = o;
     return L;
 }
@@ -85,6 +87,7 @@ struct JbFrameArgs {
     unsigned* tile_hops;
     unsigned* tile_base;
     uint32_t* vbits;
+    unsigned* ticket;
     unsigned long long* status;
 };
 
@@ -102,6 +105,7 @@ struct JbInvArgs {
     size_t plane_stride, row_pitch;
     int16_t* coeffs_out;        // MODE 1
     const int16_t* coeffs_in;   // MODE 2
+    unsigned* ticket;           // chunks are claimed from this counter (zero at launch); nullptr: dealt round-robin
     unsigned long long* status;
 };
 

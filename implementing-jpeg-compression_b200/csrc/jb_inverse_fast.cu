@@ -15,6 +15,7 @@
 //     bounds; tiles that wrap a block row or belong to a partial group use bounded stores.
 #include <cuda.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include "jb_common.cuh"
 #include "jb_fast_common.cuh"
@@ -27,7 +28,11 @@
 #define FI_STREAM_WORDS 400             // staged chunk bytes (1.6 KB; the average chunk is ~0.6 KB); denser
                                         // chunks are decoded straight from global memory
 
-#define FI_ROWS_WARPS 24                // row-store variant: 72 registers and 7.8 KB of shared memory per warp
+// Row-store variant: 72 registers and 7.8 KB of shared memory per warp would allow 28 warps per SM, but the kernel is
+// bound by the HBM write path, not by latency: measured 1.12 / 1.10 / 1.12 / 1.14 / 1.06 / 1.11 / 1.13 / 1.15 ms with
+// 8 / 10 / 12 / 14 / 16 / 20 / 24 / 28 warps (1024 x 1080p).  JB_DEBUG_ROWS_WARPS overrides the default (tuning aid).
+#define FI_ROWS_MAX_WARPS 28
+#define FI_ROWS_WARPS 16
 #define FI_ROWS_STAGE_WORDS 512
 
 // per-warp shared memory of the row-store variant: the chunk's bytes, then (once decoded) its 8-bit samples
@@ -99,14 +104,14 @@ __device__ __forceinline__ int fi_tile_kind(const JbGeom& g, int nvalid, const F
 }
 
 template <bool DFT, int MODE, bool ROWS>
-__global__ void __launch_bounds__((ROWS ? FI_ROWS_WARPS : FI_WARPS) * 32, 1)
+__global__ void __launch_bounds__((ROWS ? FI_ROWS_MAX_WARPS : FI_WARPS) * 32, 1)
 jb_inv_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FiKernelArgs ka) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const JbInvArgs& a = ka.a;
     const JbGeom& g = a.g;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t* s_izz = (uint8_t*)smem_raw;                               // zigzag position -> natural index
-    constexpr int NWARPS = ROWS ? FI_ROWS_WARPS : FI_WARPS;
+    const int NWARPS = blockDim.x >> 5;
     constexpr unsigned STAGE_WORDS = ROWS ? FI_ROWS_STAGE_WORDS : FI_STREAM_WORDS;
     FiWarpSmem& ws = *(FiWarpSmem*)(smem_raw + 128 + (size_t)warp * sizeof(FiWarpSmem));           // tile variant
     FiRowsSmem& wr = *(FiRowsSmem*)(smem_raw + 128 + (size_t)warp * sizeof(FiRowsSmem));           // row variant
@@ -125,9 +130,22 @@ jb_inv_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FiKernelArgs 
         dq[v] = a.t.dqmult[li * 8 + v] * sc;
     }
 
+    // Chunks are claimed from a device-wide counter, one ahead (the claim of the next chunk travels while this one
+    // is processed): with a fixed deal the slowest SM finished 36 % later than the fastest (ncu, sm__cycles_active
+    // min / max), i.e. the kernel ran 13 % longer than its average SM.  Without a counter (stage entry points,
+    // whose workspace holds only the tables) chunks are dealt round-robin.
     const unsigned total_warps = gridDim.x * NWARPS;
     unsigned store_seq = 0;
-    for (unsigned chunk = blockIdx.x * NWARPS + warp; chunk < a.n_chunks; chunk += total_warps) {
+    auto claim = [&](unsigned prev) -> unsigned {
+        if (a.ticket == nullptr) return prev + total_warps;
+        unsigned c = 0;
+        if (lane == 0) c = atomicAdd(a.ticket, 1u);
+        return __shfl_sync(0xffffffffu, c, 0);
+    };
+    unsigned next_chunk = a.ticket ? claim(0) : blockIdx.x * NWARPS + warp;
+    while (next_chunk < a.n_chunks) {
+        const unsigned chunk = next_chunk;
+        next_chunk = claim(chunk);
         const int plane = (int)(chunk / (unsigned)g.cpp);
         const int blk0 = (int)(chunk % (unsigned)g.cpp) * JB_CHUNK;
         const int nvalid = jb_min(JB_CHUNK, g.nblocks - blk0);
@@ -574,7 +592,8 @@ bool jb_inv_fast_eligible(const JbGeom& g) { return g.d == 8 && g.bs == 4; }
 
 template <bool DFT, int MODE, bool ROWS>
 static cudaError_t jb_inv_fast_launch_t(const CUtensorMap& map, const FiKernelArgs& ka, cudaStream_t s) {
-    constexpr int NWARPS = ROWS ? FI_ROWS_WARPS : FI_WARPS;
+    int NWARPS = ROWS ? FI_ROWS_WARPS : FI_WARPS;
+    if (ROWS) { const char* e = getenv("JB_DEBUG_ROWS_WARPS"); if (e && atoi(e) >= 4 && atoi(e) <= FI_ROWS_MAX_WARPS) NWARPS = atoi(e); }
     const size_t smem = 128 + (size_t)NWARPS * (ROWS ? sizeof(FiRowsSmem) : sizeof(FiWarpSmem));
     cudaError_t e = cudaFuncSetAttribute(jb_inv_fast_kernel<DFT, MODE, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
