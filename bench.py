@@ -9,8 +9,11 @@ of 1024 synthetic 1920x1080 three-band images, --block_size 4 --dct_size 8 --tra
 table quantisation, sharded by image across the ranks (strong scaling, no collective on the
 data path).  One step = compress the rank's images, then decompress the streams just
 produced.  `value` = source megapixels of the whole batch / step time (device-timed, inputs
-resident in HBM); `e2e` = the same through BatchCodec.compress_host / decompress_host with
-pinned host buffers, host<->device copies inside the timed region.
+resident in HBM); `e2e` = the same through BatchCodec.roundtrip_host with pinned host buffers,
+host<->device copies inside the timed region.  `roofline.achieved` = algorithmic bytes of one launch /
+the fused kernel's own duration, measured live: the library records caller-owned CUDA events right
+before and after that kernel (jb_debug_kernel_events) in K direct launches after the timed region;
+`whole_call_*` are the same bytes over the complete library call of the timed region.
 
 --impl reference times the CPU restatement of the reference (oracle/ref_port.py: the reference
 is pure Python and does not exist on the GPU box) on all host cores, on a bounded sample.
@@ -403,16 +406,16 @@ def run_ours(args, rank, world, local_rank):
                          "frac_of_nominal_8000": a_c / (tk_c * 1e-3) / 1e9 / 8000.0,
                          "whole_call_ms": t_c, "whole_call_achieved": ach_c, "whole_call_frac": ach_c / peak,
                          # dram__bytes_read+write of one launch from `ncu --set full` at 1024 images on one GPU
-                         # (profiles/r1_ncu_full_v8_jb_fwd_fast.txt: 6.418 GB + 0.127 GB), scaled to this rank's share
-                         "traffic": 6.545e9 * n_img / 1024.0, "traffic_source": "profiles/r1_ncu_full_v8_jb_fwd_fast.txt",
+                         # (profiles/r1_ncu_full_v11_jb_fwd_fast.txt: 6.419 GB + 0.129 GB), scaled to this rank's share
+                         "traffic": 6.549e9 * n_img / 1024.0, "traffic_source": "profiles/r1_ncu_full_v11_jb_fwd_fast.txt",
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": a_c},
             "roofline_decompress": {"bound": "hbm", "kernel": "jb_inv_fast_kernel (fused decompress)", "kernel_ms": tk_d,
                                     "achieved": a_d / (tk_d * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                     "frac": a_d / (tk_d * 1e-3) / 1e9 / peak,
                                     "frac_of_nominal_8000": a_d / (tk_d * 1e-3) / 1e9 / 8000.0,
                                     "whole_call_ms": t_d, "whole_call_achieved": ach_d, "whole_call_frac": ach_d / peak,
-                                    "traffic": 6.461e9 * n_img / 1024.0,
-                                    "traffic_source": "profiles/r1_ncu_full_v8_jb_inv_fast.txt (fused inverse kernel only)",
+                                    "traffic": 6.458e9 * n_img / 1024.0,
+                                    "traffic_source": "profiles/r1_ncu_full_v12_jb_inv_fast.txt (0.146 GB read + 6.313 GB written)",
                                     "algorithmic_bytes_per_launch": a_d},
             "cpu_baseline": cpu,
             "e2e": e2e,

@@ -10,6 +10,8 @@
 //   * each stream is cut into tiles of T bytes (256 for typical content).  WALK: one thread per tile starts
 //     at the first such offset in its tile and follows block extents to the tile end, recording every start
 //     it visits (one bit per byte of the tile) and where it leaves the tile (its exit; a long block may carry it over several tiles).
+//     A warp owns 32 consecutive tiles of one stream and stages them in shared memory as one contiguous region;
+//     the walk reads two codes per pass from one 32-bit window.
 //     The walk of tile 0 starts at offset 0, which is a true block start; a walk that starts on a
 //     false offset re-synchronises with the true chain within a block or two (it lands after a 0x00
 //     byte, and nearly all of those are true ends);
