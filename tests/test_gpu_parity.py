@@ -147,6 +147,40 @@ def test_pack_unpack_random_coefficients(jb, n, density, bits):
     assert np.array_equal(back, zz)
 
 
+def test_framing_stream_lengths_around_the_walk_warp_boundaries(jb):
+    """The walk gives every stream whole warps of 32 tiles (256 bytes each here): streams whose tile counts sit
+    on and around 32 and 64, a one-tile stream and an all-EOB stream in one batch, decoded block for block."""
+    n_blocks, n = 400, 64
+    rng = np.random.default_rng(2024)
+    # bytes per block grow with the density; find densities whose streams land on the wanted tile counts
+    wanted = [1, 2, 31, 32, 33, 40, 63, 64, 65, 90]
+    planes, got = [], []
+    for tiles in wanted:
+        target = tiles * 256 - 100
+        lo, hi = 0.0, 1.0
+        for _ in range(30):                       # bisection on the density (same random field every time)
+            mid = (lo + hi) / 2
+            field = np.random.default_rng(tiles).random((n_blocks, n))
+            vals = np.random.default_rng(tiles + 1).integers(1, 128, (n_blocks, n))
+            zz = np.where(field < mid, vals, 0).astype(np.int64)
+            size = len(rp.pack_blocks(zz))
+            if size > target:
+                hi = mid
+            else:
+                lo = mid
+        planes.append(zz)
+        got.append(-(-size // 256))
+    planes.append(np.zeros((n_blocks, n), dtype=np.int64))             # every block a lone EOB
+    zz = np.stack(planes)
+    streams = [rp.pack_blocks(z) for z in zz]
+    tiles = [-(-len(x) // 256) for x in streams]
+    assert {32, 64} & set(tiles) and min(tiles) <= 2 and max(tiles) >= 80, tiles
+    assert len({t % 32 for t in tiles}) >= 6, tiles
+    back = jb.stages.unpack_streams(streams, n_blocks, 8)
+    assert np.array_equal(back, zz)
+    assert jb.stages.pack_coefficients(zz, 8) == streams
+
+
 def test_serial_framing_fallback_matches(jb):
     """JB_FLAG_SERIAL_FRAMING (8) routes every stream through the single-thread fallback walk."""
     cfg, ocfg = _cfgs(jb, (200, 328, 4, 8, "DCT", "qtable", None))
