@@ -251,6 +251,7 @@ static int jb_inverse_common(int mode, const uint8_t* d_in, size_t in_bytes, con
         f.vbits = (uint32_t*)(ws + L.vbits);
         f.ticket = (unsigned*)(ws + L.ticket);
         f.warp_first = (unsigned*)(ws + L.warp_first);
+        f.warp_stream = (unsigned*)(ws + L.warp_stream);
         f.status = (unsigned long long*)d_status;
         // (a stream that fails framing leaves its part of block_start unwritten; the call then reports
         // JB_ERR_BAD_STREAM and the transform kernels check every offset they read against the stream bounds)

@@ -158,7 +158,11 @@ __global__ void __launch_bounds__(1024) jb_frame_prep_kernel(JbFrameArgs f) {
         carry += total;
         // the walk gives every stream whole warps (32 tiles each)
         ex = jb_block_excl_scan((nt + 31u) >> 5, s_warp, &total);
-        if (s < f.n_planes) f.warp_first[s] = wcarry + ex;
+        if (s < f.n_planes) {
+            f.warp_first[s] = wcarry + ex;
+            const unsigned wmax = f.max_tiles / 32u + (unsigned)f.n_planes + 1u;            // capacity of warp_stream
+            for (unsigned j = 0, w = wcarry + ex; j < ((nt + 31u) >> 5) && w < wmax; ++j, ++w) f.warp_stream[w] = (unsigned)s;
+        }
         wcarry += total;
     }
     if (__syncthreads_or(bad ? 1 : 0)) carry = 0xFFFFFFFFu;
@@ -285,9 +289,7 @@ __global__ void __launch_bounds__(JB_WALK_THREADS) jb_frame_walk_smem_kernel(JbF
     if (gwarp >= f.warp_first[f.n_planes]) return;                      // (whole warps)
     uint32_t* region = s_words + (size_t)(threadIdx.x >> 5) * warp_words;
     uint32_t* bm = region + region_words + (size_t)lane * wpt;
-    int s = 0;
-    if (lane == 0) s = jb_stream_of_tile(f.warp_first, f.n_planes, gwarp);
-    s = __shfl_sync(0xffffffffu, s, 0);
+    const int s = (int)f.warp_stream[gwarp];                            // (written by the prep kernel)
     const unsigned t0 = (gwarp - f.warp_first[s]) * 32u;                // first tile of the warp, stream-relative
     const unsigned nt = f.tile_first[s + 1] - f.tile_first[s];
     const bool live = t0 + (unsigned)lane < nt;

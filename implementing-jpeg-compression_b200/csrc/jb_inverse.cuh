@@ -38,6 +38,7 @@ struct JbDecLayout {
     size_t vbits;        // uint32 [max_tiles * tile_bytes / 32]  bit b of a tile: its walk saw a block start at byte b
     size_t ticket;       // uint32  next chunk of the transform kernel (reset by the framing prep kernel)
     size_t warp_first;   // uint32 [n_planes + 1]   first warp of each stream in the walk (32 tiles per warp); [n_planes] = warps
+    size_t warp_stream;  // uint32 [max_tiles / 32 + n_planes + 1]   stream of every walk warp
     size_t total;
     unsigned max_tiles;
     unsigned tile_bytes;
@@ -63,6 +64,7 @@ static inline JbDecLayout jb_dec_layout(int d, int n_planes, long long nblocks_p
     L.vbits = o;       o += jb_align_up((size_t)L.max_tiles * (L.tile_bytes / 8), 256);
     L.ticket = o;      o += 256;
     L.warp_first = o;  o += jb_align_up(((size_t)n_planes + 1) * 4, 256);
+    L.warp_stream = o; o += jb_align_up(((size_t)L.max_tiles / 32 + (size_t)n_planes + 1) * 4, 256);
     L.total = o;
     return L;
 }
@@ -91,6 +93,7 @@ struct JbFrameArgs {
     uint32_t* vbits;
     unsigned* ticket;
     unsigned* warp_first;
+    unsigned* warp_stream;
     unsigned long long* status;
 };
 

@@ -8,11 +8,17 @@
 //   * 8 iterations over 4 blocks: lane (u, b) dequantises row u (quantizers.py restore, with
 //     the 1/|c_k|^2 scale of transforms.py:14-26 folded in), 8-point inverse transform along
 //     the row, transpose through shared memory, 8-point inverse transform down the column,
-//     np.round + clamp (basis_change.py:43, normalization.py:10-14), 4x4 replication
-//     (util.inflate) into a 32-row x 128-byte tile in shared memory;
-//   * the tile goes out by TMA store (cp.async.bulk.tensor shared -> global), which also
-//     performs the crops of dct_padding.py:11-21 / padding.py:14-16 by clipping at the tensor
-//     bounds; tiles that wrap a block row or belong to a partial group use bounded stores.
+//     np.round + clamp (basis_change.py:43, normalization.py:10-14);
+//   * default (ROWS): the 8-bit samples of the chunk stay in shared memory and the chunk goes out
+//     pixel row by pixel row -- a lane pair owns a block, one 128-bit store instruction covers 512
+//     contiguous bytes, the 4x4 replication (util.inflate) happens in registers, the crops of
+//     dct_padding.py:11-21 / padding.py:14-16 by predication.  HBM takes the chunk's 1 KB row runs at
+//     6.1 TB/s, 32-row x 128-byte tiles only at 5.2 (tools/dram_probe_rows.cu);
+//   * JB_FLAG_TILE_DECODER (the former default, kept for comparison): 4x4 replication into a 32-row x
+//     128-byte tile in shared memory, which goes out by TMA store (cp.async.bulk.tensor shared ->
+//     global, clipping at the tensor bounds performs the crops); tiles that wrap a block row or belong
+//     to a partial group use bounded stores;
+//   * chunks are claimed from a device-wide counter (see the kernel).
 #include <cuda.h>
 #include <string.h>
 #include <stdlib.h>
