@@ -599,7 +599,14 @@ bool jb_inv_fast_eligible(const JbGeom& g) { return g.d == 8 && g.bs == 4; }
 template <bool DFT, int MODE, bool ROWS>
 static cudaError_t jb_inv_fast_launch_t(const CUtensorMap& map, const FiKernelArgs& ka, cudaStream_t s) {
     int NWARPS = ROWS ? FI_ROWS_WARPS : FI_WARPS;
-    if (ROWS) { const char* e = getenv("JB_DEBUG_ROWS_WARPS"); if (e && atoi(e) >= 4 && atoi(e) <= FI_ROWS_MAX_WARPS) NWARPS = atoi(e); }
+    if (ROWS) {
+        static const int tuned = [] {                          // tuning aid, read once per process
+            const char* e = getenv("JB_DEBUG_ROWS_WARPS");
+            const int w = e ? atoi(e) : 0;
+            return (w >= 4 && w <= FI_ROWS_MAX_WARPS) ? w : 0;
+        }();
+        if (tuned) NWARPS = tuned;
+    }
     const size_t smem = 128 + (size_t)NWARPS * (ROWS ? sizeof(FiRowsSmem) : sizeof(FiWarpSmem));
     cudaError_t e = cudaFuncSetAttribute(jb_inv_fast_kernel<DFT, MODE, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
