@@ -125,3 +125,18 @@ def test_no_cpu_fallback_without_cuda():
         jb.compress_band(np.zeros((8, 8), dtype=np.uint8), cfg)
     with pytest.raises(jb.NativeLibraryError):
         jb.decompress_band(b"\0", cfg)
+
+
+def test_bind_host_to_device_is_a_no_op_without_nvml_or_gpu():
+    """sharding.bind_host_to_device narrows the CPU affinity to the cores next to a GPU; where NVML or the device
+    is missing it must change nothing and say so (bench.py calls it unconditionally)."""
+    import os
+    import torch
+    before = os.sched_getaffinity(0)
+    got = jb.sharding.bind_host_to_device(0)
+    after = os.sched_getaffinity(0)
+    if not torch.cuda.is_available():
+        assert got is None and after == before
+    else:
+        assert got is None or (set(got) == after and after <= before)
+        os.sched_setaffinity(0, before)
