@@ -1,4 +1,4 @@
-"""Command-line front ends (tools/compress.py, tools/decompress.py): the flags of the reference's
+"""Command-line front ends (tools/jb_compress.py, tools/jb_decompress.py): the flags of the reference's
 compress.py:20-62 / decompress.py:13-24, plus the batch mode of SURVEY.md section 8(f) row 4."""
 import importlib.util
 import os
@@ -17,7 +17,7 @@ def _load(name):
 
 
 def test_defaults_are_the_reference_defaults():
-    args = _load("compress").build_parser().parse_args(["in.png", "out.jb"])
+    args = _load("jb_compress").build_parser().parse_args(["in.png", "out.jb"])
     assert (args.block_size, args.dct_size, args.transform, args.quantization, args.qkeep, args.qdivisor) == \
         (4, 8, "DCT", "qtable", 2, 40)
 
@@ -28,7 +28,7 @@ def test_defaults_are_the_reference_defaults():
                                   ["in.png"],
                                   ["in.png", "out.jb", "--batch", "a.png"]])
 def test_bad_arguments_are_refused_before_any_work(argv):
-    cli = _load("compress")
+    cli = _load("jb_compress")
     with pytest.raises(SystemExit) as e:
         cli.main(argv)
     assert e.value.code not in (0, None)
@@ -36,7 +36,7 @@ def test_bad_arguments_are_refused_before_any_work(argv):
 
 def test_decompress_needs_both_paths():
     with pytest.raises(SystemExit):
-        _load("decompress").main(["only_one"])
+        _load("jb_decompress").main(["only_one"])
 
 
 @pytest.mark.gpu
@@ -51,7 +51,7 @@ def test_cli_round_trip_and_batch_match_the_oracle(tmp_path):
         rgb = np.stack([synth_plane(h, w, 40 + 3 * k + i) for i in range(3)], axis=-1).astype(np.uint8)
         paths.append(str(tmp_path / ("img%d.png" % k)))
         Image.fromarray(rgb, "RGB").save(paths[-1])
-    comp, dec = _load("compress"), _load("decompress")
+    comp, dec = _load("jb_compress"), _load("jb_decompress")
     out = str(tmp_path / "one.jb")
     assert comp.main([paths[0], out, "--quantization", "divide", "--qdivisor", "30", "--block_size", "2"]) == 0
     blob = open(out, "rb").read()

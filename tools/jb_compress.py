@@ -1,8 +1,8 @@
 """Command-line front end with the flags of the reference's compress.py (compress.py:20-62), on the CUDA path.
 
-    python tools/compress.py in.png out.jb [--block_size 4 --dct_size 8 --transform DCT
+    python tools/jb_compress.py in.png out.jb [--block_size 4 --dct_size 8 --transform DCT
                                             --quantization qtable --qkeep 2 --qdivisor 40]
-    python tools/compress.py --batch a.png b.png c.png --outdir compressed/      
+    python tools/jb_compress.py --batch a.png b.png c.png --outdir compressed/      
 
 The output file is the reference's container (file_format.py:67-93) and decodes through the reference's
 decompress.py.  In batch mode images of equal size go through one device batch (colour conversion, compression
@@ -21,16 +21,16 @@ TRANSFORMS = ("DCT", "DFT")
 
 def build_parser():
     p = argparse.ArgumentParser(description="Given an image, compress it using the block-transform codec on a B200")
-    p.add_argument("infile", nargs="?", help="a path to the file to compress")
-    p.add_argument("outfile", nargs="?", help="a destination path")
+    p.add_argument("infile", nargs="?", help="image file to read (any format Pillow opens)")
+    p.add_argument("outfile", nargs="?", help="container file to write")
     p.add_argument("--batch", nargs="+", metavar="IMAGE", help="compress several images in one device batch")
     p.add_argument("--outdir", default=".", help="destination directory of --batch outputs")
-    p.add_argument("--block_size", type=int, default=4, help="size of sub-sampling block")
-    p.add_argument("--dct_size", type=int, default=8, help="size of block for the discrete transform")
-    p.add_argument("--transform", default="DCT", help="type of discrete transform (DCT vs DFT)")
-    p.add_argument("--quantization", default="qtable", help="one of none, discard, divide, qtable")
-    p.add_argument("--qkeep", type=int, default=2, help="coefficients kept along both axes (discard)")
-    p.add_argument("--qdivisor", type=int, default=40, help="integer the coefficients are divided by (divide)")
+    p.add_argument("--block_size", type=int, default=4, help="edge of the box each band is averaged over before the transform")
+    p.add_argument("--dct_size", type=int, default=8, help="edge of the transform blocks")
+    p.add_argument("--transform", default="DCT", help="DCT or DFT (real part)")
+    p.add_argument("--quantization", default="qtable", help="quantiser: none | discard | divide | qtable")
+    p.add_argument("--qkeep", type=int, default=2, help="discard: rows and columns of coefficients that survive")
+    p.add_argument("--qdivisor", type=int, default=40, help="divide: the common divisor")
     return p
 
 
@@ -56,7 +56,7 @@ def validate(args):
         if args.infile or args.outfile:
             raise SystemExit("--batch takes its inputs after the flag; give no positional infile/outfile")
     elif not (args.infile and args.outfile):
-        raise SystemExit("usage: compress.py infile outfile [options]  |  compress.py --batch IMAGE... --outdir DIR")
+        raise SystemExit("usage: jb_compress.py infile outfile [options]  |  jb_compress.py --batch IMAGE... --outdir DIR")
 
 
 def main(argv=None):

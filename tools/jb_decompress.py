@@ -1,7 +1,7 @@
 """Command-line front end with the interface of the reference's decompress.py (decompress.py:5-24), on the CUDA path.
 
-    python tools/decompress.py in.jb out.png
-    python tools/decompress.py --batch a.jb b.jb --outdir restored/        
+    python tools/jb_decompress.py in.jb out.png
+    python tools/jb_decompress.py --batch a.jb b.jb --outdir restored/        
 
 Reads the reference's container (file_format.py:96-111); decoding and the YCbCr -> RGB conversion run on the GPU
 (`Jpeg.decompress_rgb`), with the pixels `Jpeg.decompress(data).convert('RGB')` would give.
@@ -14,9 +14,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
 def build_parser():
-    p = argparse.ArgumentParser(description="Restore an image from a file written by compress.py")
-    p.add_argument("infile", nargs="?", help="a path to the compressed file")
-    p.add_argument("outfile", nargs="?", help="a destination path (format chosen by its extension)")
+    p = argparse.ArgumentParser(description="Restore an image from a container file")
+    p.add_argument("infile", nargs="?", help="container file written by jb_compress.py or the reference")
+    p.add_argument("outfile", nargs="?", help="image file to write (format from the extension)")
     p.add_argument("--batch", nargs="+", metavar="FILE", help="restore several files")
     p.add_argument("--outdir", default=".", help="destination directory of --batch outputs (PNG)")
     return p
@@ -28,7 +28,7 @@ def main(argv=None):
         if args.infile or args.outfile:
             raise SystemExit("--batch takes its inputs after the flag; give no positional infile/outfile")
     elif not (args.infile and args.outfile):
-        raise SystemExit("usage: decompress.py infile outfile  |  decompress.py --batch FILE... --outdir DIR")
+        raise SystemExit("usage: jb_decompress.py infile outfile  |  jb_decompress.py --batch FILE... --outdir DIR")
     import jpeg_b200 as jb
 
     def restore(src, dst):
