@@ -51,6 +51,7 @@ SYMBOLS = {
     "jb_max_stream_bytes": (_SZ, [_PP, _I]),
     "jb_compress_workspace_bytes": (_SZ, [_PP, _I]),
     "jb_decompress_workspace_bytes": (_SZ, [_PP, _I, _SZ]),
+    "jb_decompress_framing_path": (_I, [_PP, _I, _SZ]),
     "jb_compress_planes": (_I, [_P, _SZ, _SZ, _I, _PP, _P, _SZ, _P, _P, _P, _SZ, _P]),
     "jb_decompress_planes": (_I, [_P, _SZ, _P, _P, _I, _PP, _P, _SZ, _SZ, _P, _P, _SZ, _P]),
     "jb_stage_forward_coeffs": (_I, [_P, _SZ, _SZ, _I, _PP, _P, _P, _P, _SZ, _P]),

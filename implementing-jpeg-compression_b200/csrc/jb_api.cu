@@ -203,6 +203,15 @@ extern "C" size_t jb_stage_unpack_workspace_bytes(int n_planes, int blocks_per_p
     return jb_dec_layout(dct_size, n_planes, blocks_per_plane, in_bytes, jb_table_layout(dct_size).total).total;
 }
 
+extern "C" int jb_decompress_framing_path(const jb_params* p, int n_planes, size_t in_bytes) {
+    JbGeom g;
+    int rc = jb_make_geom(p, &g);
+    if (rc != JB_OK) return rc;
+    if (n_planes <= 0) return JB_ERR_BAD_PARAM;
+    JbDecLayout L = jb_dec_layout(g.d, n_planes, g.nblocks, in_bytes, jb_table_layout(g.d).total);
+    return jb_framing_is_chain(L.max_tiles, n_planes) ? JB_FRAMING_CHAIN : JB_FRAMING_STITCH;
+}
+
 static int jb_inverse_common(int mode, const uint8_t* d_in, size_t in_bytes, const uint64_t* d_plane_off,
                              const uint64_t* d_plane_len, int n_planes, const JbGeom& g,
                              uint8_t* d_planes_out, size_t plane_stride, size_t row_pitch,

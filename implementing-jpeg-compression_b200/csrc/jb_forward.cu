@@ -15,6 +15,7 @@
 // pass costs ~4 % more traffic and needs no inter-block waiting).
 #include "jb_common.cuh"
 #include "jb_forward.cuh"
+#include "jb_refine.cuh"
 
 // ----------------------------------------------------------------------------------------------
 // generic kernel
@@ -51,35 +52,6 @@ __host__ __device__ inline JbFwdSmemLayout jb_fwd_smem_layout(int d, bool dft) {
 }
 
 size_t jb_fwd_generic_smem_bytes(int d, bool dft) { return jb_fwd_smem_layout(d, dft).total; }
-
-// float64 re-evaluation of one coefficient the way the reference computes it
-// (transforms.py:46-58 rows then columns; quantizers.py:27-28,47-49).
-__device__ double jb_refine_coefficient(const int* X, int u, int v, const JbGeom& g, const JbTables& t) {
-    const int d = g.d;
-    const double bs2 = (double)(g.bs * g.bs);
-    double y = 0.0;
-    if (g.transform == JB_TRANSFORM_DCT) {
-        for (int i = 0; i < d; ++i) {
-            double m = 0.0;
-            for (int j = 0; j < d; ++j) m += t.fA64[v * d + j] * ((double)X[i * d + j] / bs2);
-            y += t.fA64[u * d + i] * m;
-        }
-    } else {
-        for (int i = 0; i < d; ++i) {
-            double mc = 0.0, ms = 0.0;
-            for (int j = 0; j < d; ++j) {
-                double x = (double)X[i * d + j] / bs2;
-                mc += t.fA64[v * d + j] * x;
-                ms += t.fB64[v * d + j] * x;
-            }
-            y += t.fA64[u * d + i] * mc - t.fB64[u * d + i] * ms;
-        }
-    }
-    double r = t.qrecip[u * d + v];
-    if (g.qmode == JB_Q_QTABLE) return y * r;
-    if (g.qmode == JB_Q_DIVIDE) return y / r;
-    return y;
-}
 
 template <int MODE>
 __global__ void __launch_bounds__(JB_GENERIC_THREADS)
@@ -171,7 +143,7 @@ jb_fwd_generic_kernel(const JbFwdArgs a) {
                     float tol = a.t.qtol[idx];
                     if (!(g.flags & JB_FLAG_NO_REFINE) &&
                         fabsf(fabsf(val - r) - 0.5f) < tol + 2.4e-7f * fabsf(val)) {
-                        r = (float)rint(jb_refine_coefficient(X, u, v, g, a.t));
+                        r = (float)rint(jb_refine_f64<int>(X, u, v, d, g.bs, g.transform, g.qmode, a.t.fA64, a.t.fB64, a.t.qrecip[idx]));
                     }
                     int q = (int)r;
                     int zp = a.t.zz[idx];

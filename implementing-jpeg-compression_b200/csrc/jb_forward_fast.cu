@@ -26,6 +26,7 @@
 #include "jb_common.cuh"
 #include "jb_fast_common.cuh"
 #include "jb_forward.cuh"
+#include "jb_refine.cuh"
 
 #define FF_WARPS 16
 #define FF_RING 2
@@ -47,26 +48,6 @@ struct FfCtaSmem {
     double A64[64];
     double B64[64];
 };
-
-// fp64 re-evaluation of coefficient (u, v) from the 8x8 box sums of one block, following the
-// reference's order (rows then columns, transforms.py:46-58; quantizers.py:27-28,47-49).
-template <bool DFT>
-__device__ __noinline__ double ff_refine8(const float* X, int u, int v, const FfCtaSmem& cs, int qmode, double recip) {
-    double y = 0.0;
-    for (int i = 0; i < 8; ++i) {
-        double mc = 0.0, ms = 0.0;
-        for (int j = 0; j < 8; ++j) {
-            double x = (double)X[i * 8 + j] / 16.0;
-            mc += cs.A64[v * 8 + j] * x;
-            if (DFT) ms += cs.B64[v * 8 + j] * x;
-        }
-        y += cs.A64[u * 8 + i] * mc;
-        if (DFT) y -= cs.B64[u * 8 + i] * ms;
-    }
-    if (qmode == JB_Q_QTABLE) return y * recip;
-    if (qmode == JB_Q_DIVIDE) return y / recip;
-    return y;
-}
 
 // ---- tile staging -----------------------------------------------------------------------------
 // kind 0: the 32 x 128 tile lies inside the image, rows 16-byte aligned  -> TMA (LDG.128 when TMA is off)
@@ -378,7 +359,8 @@ jb_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfKernelArgs 
                     #pragma unroll
                     for (int u = 0; u < 8; ++u)
                         if (nearmask >> u & 1u)
-                            qi[u] = (int)rint(ff_refine8<DFT>(X, u, v, cs, g.qmode, a.t.qrecip[u * 8 + v]));
+                            qi[u] = (int)rint(jb_refine_f64<float>(X, u, v, 8, 4, DFT ? JB_TRANSFORM_DFT : JB_TRANSFORM_DCT, g.qmode,
+                                                                   cs.A64, cs.B64, a.t.qrecip[u * 8 + v]));
                 }
                 __syncwarp();
             }

@@ -19,6 +19,7 @@
 // rounding accuracy.
 #include "jb_common.cuh"
 #include "jb_forward.cuh"
+#include "jb_refine.cuh"
 
 #define FM_THREADS 256
 #define FM_STAGE_BYTES 128            // staging row per block; longer blocks are packed again, bytes to the slot
@@ -62,26 +63,6 @@ __host__ __device__ inline FmLayout fm_layout(int d, int bs, bool dft) {
 bool jb_fwd_mid_eligible(const JbGeom& g) {
     if (g.d < 8 || g.d % 4 != 0 || g.d > JB_MAX_DCT_SIZE) return false;
     return fm_layout(g.d, g.bs, g.transform == JB_TRANSFORM_DFT).total <= 200 * 1024;
-}
-
-// fp64 re-evaluation from float box sums (same order as jb_refine_coefficient in jb_forward.cu)
-__device__ __noinline__ double fm_refine(const float* X, int u, int v, int d, int bs, int transform, int qmode,
-                                         const double* A64, const double* B64, double recip) {
-    const double bs2 = (double)(bs * bs);
-    double y = 0.0;
-    for (int i = 0; i < d; ++i) {
-        double mc = 0.0, ms = 0.0;
-        for (int j = 0; j < d; ++j) {
-            const double x = (double)X[i * d + j] / bs2;
-            mc += A64[v * d + j] * x;
-            if (transform == JB_TRANSFORM_DFT) ms += B64[v * d + j] * x;
-        }
-        y += A64[u * d + i] * mc;
-        if (transform == JB_TRANSFORM_DFT) y -= B64[u * d + i] * ms;
-    }
-    if (qmode == JB_Q_QTABLE) return y * recip;
-    if (qmode == JB_Q_DIVIDE) return y / recip;
-    return y;
 }
 
 template <typename Writer>
@@ -260,7 +241,7 @@ jb_fwd_mid_kernel(const JbFwdArgs a) {
                 const float val = y4[k] * sQm[idx];
                 float r = rintf(val);
                 if (refine_on && fabsf(fabsf(val - r) - 0.5f) < sQt[idx] + 2.4e-7f * fabsf(val))
-                    r = (float)rint(fm_refine(sX, u, v, d, bs, g.transform, g.qmode, a.t.fA64, a.t.fB64, a.t.qrecip[idx]));
+                    r = (float)rint(jb_refine_f64<float>(sX, u, v, d, bs, g.transform, g.qmode, a.t.fA64, a.t.fB64, a.t.qrecip[idx]));
                 int q = (int)r;
                 const int zp = sZz[idx];
                 if (MODE == 1) {
@@ -534,7 +515,7 @@ jb_fwd_mid_warp_kernel(const JbFwdArgs a) {
                 const float val = y * sQm[idx];
                 float r = rintf(val);
                 if (refine_on && fabsf(fabsf(val - r) - 0.5f) < sQt[idx] + 2.4e-7f * fabsf(val))
-                    r = (float)rint(fm_refine(sX, u, v, D, bs, g.transform, g.qmode, a.t.fA64, a.t.fB64, a.t.qrecip[idx]));
+                    r = (float)rint(jb_refine_f64<float>(sX, u, v, D, bs, g.transform, g.qmode, a.t.fA64, a.t.fB64, a.t.qrecip[idx]));
                 int q = (int)r;
                 const int zp = sZz[idx];
                 if (MODE == 1) {

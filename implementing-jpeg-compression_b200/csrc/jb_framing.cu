@@ -643,7 +643,6 @@ __global__ void __launch_bounds__(32) jb_frame_serial_kernel(JbFrameArgs f) {
 
 // ---- F2..F4 in one launch, for batches of short streams: one CTA per stream ---------------------------------
 // (the per-tile arrays written by one phase and read by the next stay in L2; __syncthreads orders them)
-#define JB_STITCH_CAP 4096u
 #define JB_STITCH_THREADS 256
 __global__ void __launch_bounds__(JB_STITCH_THREADS) jb_frame_stitch_kernel(JbFrameArgs f) {
     extern __shared__ __align__(16) unsigned char stitch_smem[];       // max(5 * cap, serial window)
@@ -700,7 +699,7 @@ cudaError_t jb_launch_framing(const JbFrameArgs& f_in, cudaStream_t s) {
         jb_frame_walk_kernel<<<(f.max_tiles + JB_WALK_THREADS - 1) / JB_WALK_THREADS, JB_WALK_THREADS, 0, s>>>(f);
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    if ((size_t)f.max_tiles <= (size_t)f.n_planes * (JB_STITCH_CAP / 4u)) {
+    if (!jb_framing_is_chain(f.max_tiles, f.n_planes)) {
         // many short streams (a batch of images): the rest of the framing in one launch, one CTA per stream;
         // a stream of more than `cap` tiles (far longer than its peers) takes the serial walk
         // The kernel is a chain of short dependent phases (latency bound): streams of a few hundred tiles get

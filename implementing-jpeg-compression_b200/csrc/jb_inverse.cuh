@@ -69,6 +69,14 @@ static inline JbDecLayout jb_dec_layout(int d, int n_planes, long long nblocks_p
     return L;
 }
 
+// Which framing kernels a decompress call takes (decided on the host from the sizes alone):
+//   short streams (a batch of images): prep, walk, then one CTA per stream does the rest (jb_frame_stitch_kernel);
+//   long streams (a gigapixel plane):  prep, walk, reach, link, scan, emit, serial -- several CTAs per stream.
+#define JB_STITCH_CAP 4096u
+static inline bool jb_framing_is_chain(unsigned max_tiles, int n_planes) {
+    return (size_t)max_tiles > (size_t)n_planes * (JB_STITCH_CAP / 4u);
+}
+
 struct JbFrameArgs {
     const uint8_t* in;
     const unsigned long long* plane_off;

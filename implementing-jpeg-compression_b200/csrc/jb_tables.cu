@@ -1,5 +1,6 @@
 // jb_tables.cu -- parameter validation, geometry and the per-call table builder.
 #include <math.h>
+#include <mutex>
 
 #include "jb_common.cuh"
 
@@ -53,20 +54,25 @@ __device__ __forceinline__ int jb_zigzag_pos(int i, int j, int n) {
     return before + k;
 }
 
+// The un-normalised DCT-II matrix of transforms.py:4-11, evaluated on the HOST with libm's cos (the function
+// numpy's np.cos agrees with to the last bit on the arguments the reference forms; CUDA's device cos may differ
+// by an ulp) and handed to the builder kernel by value: the float64 re-evaluation path then works on the
+// reference's own matrix.
+struct JbHostMatrix { double a[JB_MAX_DCT_SIZE * JB_MAX_DCT_SIZE]; };
+
 // One thread per (k, m) table entry; one block.  All arithmetic in double, written
 // the way the reference writes it so that the float64 re-evaluation path reproduces
 // its values (transforms.py:4-26, quantizers.py:27-28,47-53).
-__global__ void jb_build_tables_kernel(JbGeom g, JbTables t) {
+__global__ void jb_build_tables_kernel(JbGeom g, JbTables t, const __grid_constant__ JbHostMatrix hm) {
     const int d = g.d, n = g.n;
     __shared__ double rowabs_f[JB_MAX_DCT_SIZE];   // sum_m |A[k][m]| (+|B[k][m]| for the DFT)
     __shared__ double norm2[JB_MAX_DCT_SIZE];      // |c_k|^2
-    const double PI = 3.141592653589793;
     for (int k = threadIdx.x; k < d; k += blockDim.x) {
         double sa = 0.0, s2 = 0.0;
         for (int m = 0; m < d; ++m) {
             double a, b = 0.0;
             if (g.transform == JB_TRANSFORM_DCT) {
-                a = cos(PI / d * (m + 0.5) * k);
+                a = hm.a[k * d + m];
             } else {
                 // (k*m mod d) keeps the angle small; cospi/sinpi make the trivial twiddles
                 // (0, +-1) exact, as they are inside an FFT (np.fft.fft2, basis_change.py:23)
@@ -88,9 +94,9 @@ __global__ void jb_build_tables_kernel(JbGeom g, JbTables t) {
         int k = idx / d, m = idx % d;
         double a, b = 0.0, ia, ib = 0.0;
         if (g.transform == JB_TRANSFORM_DCT) {
-            a = cos(PI / d * (m + 0.5) * k);
+            a = hm.a[idx];
             // inverse: x = W (Dinv y), W[m][k] = C[k][m]/|c_k|, Dinv[k] = 1/|c_k| (transforms.py:14-26,40-44)
-            double ct = cos(PI / d * (k + 0.5) * m);          // C[m][k] read as entry (row k of B = sample k, col m = freq m)
+            double ct = hm.a[m * d + k];                      // C[m][k] read as entry (row k of B = sample k, col m = freq m)
             double nm = sqrt(norm2[m]);
             ia = (ct / nm) * (1.0 / nm);
         } else {
@@ -134,6 +140,16 @@ __global__ void jb_build_tables_kernel(JbGeom g, JbTables t) {
 }
 
 cudaError_t jb_launch_build_tables(const JbGeom& g, const JbTables& t, cudaStream_t s) {
-    jb_build_tables_kernel<<<1, 256, 0, s>>>(g, t);
+    static JbHostMatrix hm;                        // (8 KB: not on the stack; the launch copies it, so reuse is safe)
+    static int hm_d = 0;
+    static std::mutex hm_lock;
+    std::lock_guard<std::mutex> guard(hm_lock);
+    if (g.transform == JB_TRANSFORM_DCT && hm_d != g.d) {
+        const double PI = 3.141592653589793;       // np.pi
+        for (int k = 0; k < g.d; ++k)
+            for (int m = 0; m < g.d; ++m) hm.a[k * g.d + m] = cos(PI / g.d * (m + 0.5) * k);     // transforms.py:9-10
+        hm_d = g.d;
+    }
+    jb_build_tables_kernel<<<1, 256, 0, s>>>(g, t, hm);
     return cudaGetLastError();
 }

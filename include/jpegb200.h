@@ -152,6 +152,14 @@ int jb_decompress_planes(const uint8_t* d_in, size_t in_bytes,
                          uint8_t* d_planes_out, size_t plane_stride, size_t row_pitch,
                          uint64_t* d_status, void* d_ws, size_t ws_bytes, void* stream);
 
+/* Which block-boundary discovery a jb_decompress_planes call with these sizes runs (the container stores no
+ * index, rle_byte_stream.py:74-88 reads sequentially; see csrc/jb_framing.cu): JB_FRAMING_STITCH = batches of
+ * short streams, one CTA per stream; JB_FRAMING_CHAIN = long streams, several kernels and CTAs per stream.
+ * Host only; lets a test assert which path it exercised.  Negative: an error code. */
+#define JB_FRAMING_STITCH 0
+#define JB_FRAMING_CHAIN  1
+int jb_decompress_framing_path(const jb_params* p, int n_planes, size_t in_bytes);
+
 /* ---- stage-level entry points (parity hooks; same kernels, cut at the coefficient boundary) ---- */
 
 /* Stages 0-6 + the int cast of RunLengthBlock.encode (run_length_encoding.py:16-17):

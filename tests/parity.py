@@ -42,7 +42,8 @@ def check_quantised(test, oracle, oracle_prerounding, max_fraction=1e-5, what=""
     # bit of a BLAS dot product / FFT butterfly), so the budget is the larger of the
     # 99.999 % gate and the number of ties the reference value array actually contains.
     allowed = max(2, int(math.ceil(max_fraction * test.size)))
-    if strict_fraction:
+    if strict_fraction or test.size >= 100000:
+        # arrays large enough for the 99.999 % gate to mean something are held to it literally
         assert bad.size <= allowed, "%s: %d tie mismatches in %d entries" % (what, bad.size, test.size)
     else:
         n_ties = int(tie_mask(v).sum())

@@ -433,3 +433,77 @@ def test_batched_containers_equal_generate_data(jb):
             for i in range(n)]
     batch = jb.compress_images_rgb(imgs, cfg)
     assert batch == [jb.Jpeg(cfg).compress(im.convert("YCbCr")) for im in imgs]
+
+
+# ---- BASELINE.json config 5: long streams (gigapixel DFT plane, block-row-band sharding) ------------------------
+def _big_plane(h, w, seed):
+    """Smooth + noise content for planes of tens of megapixels without tens of seconds of rng: a 1024 x 2048
+    synth_plane tiled, plus a cheap position-dependent perturbation so that no two tiles are equal."""
+    base = synth_plane(1024, 2048, seed)
+    a = np.tile(base, (-(-h // 1024), -(-w // 2048)))[:h, :w]
+    yy = np.arange(h, dtype=np.int64)[:, None]
+    xx = np.arange(w, dtype=np.int64)[None, :]
+    return np.clip(a + (yy * 7 + xx * 13 + seed) % 5 - 2, 0, 255)
+
+
+@pytest.mark.parametrize("h,w,n_planes,min_tiles", [(6144, 16384, 1, 4097), (4096, 4096, 3, 1025)])
+def test_long_stream_framing_config5(jb, h, w, n_planes, min_tiles):
+    """The decoder path config 5 takes: streams of thousands of walk tiles go through jb_frame_reach / link /
+    scan / emit (csrc/jb_framing.cu) instead of the one-CTA-per-stream kernel every other test uses -- one plane
+    long enough for the large reach instantiation (> 4096 tiles), and a 3-plane frame for the small one.  All
+    gates against the oracle: quantised integers (strict 1e-5 fraction; the DFT ties are re-evaluated in
+    pocketfft's order, so the streams are byte-identical), packing, pixels, and no serial fallback."""
+    import ctypes
+    import torch
+    cfg, ocfg = _cfgs(jb, (h, w, 4, 8, "DFT", "qtable", None))
+    planes = [_big_plane(h, w, 70 + i) for i in range(n_planes)]
+    d_planes = torch.from_numpy(np.stack(planes).astype(np.uint8)).cuda()
+    comp = jb.compress_planes(d_planes, cfg)
+    streams = comp.to_bytes_list()
+    total = comp.total_bytes()
+    p = cfg.c_params()
+    lib = jb._lib.load()
+    assert lib.jb_decompress_framing_path(ctypes.byref(p), n_planes, total) == 1          # JB_FRAMING_CHAIN
+    tile_bytes = 256
+    while tile_bytes < 4096 and tile_bytes < 12.0 * total / (n_planes * (h // 32) * (w // 32)):
+        tile_bytes *= 2
+    assert min(len(s) for s in streams) // tile_bytes >= min_tiles - 1, [len(s) for s in streams]
+    coeffs = jb.stages.forward_coefficients(d_planes.cpu().numpy(), cfg)
+    n_ties = 0
+    for i, a in enumerate(planes):
+        pre = rp.prerounding_zigzag(a, ocfg)
+        n_ties += check_quantised(coeffs[i], rp.quantised_zigzag(a, ocfg), pre, what="config5 plane %d" % i,
+                                  strict_fraction=True)
+        assert streams[i] == rp.pack_blocks(coeffs[i].reshape(-1, 64))
+    assert n_ties == 0, "%d DFT tie mismatches: the fp64 re-evaluation left pocketfft's order" % n_ties
+    for i, a in enumerate(planes):
+        assert streams[i] == rp.compress_band(a, ocfg)
+    lens = comp.offsets[1:] - comp.offsets[:-1]
+    out, status = jb.decompress_planes(comp.data, comp.offsets[:-1], lens, cfg, n_planes, in_bytes=total)
+    jb.check_status(status)
+    assert int(status.cpu()[2].item()) == 0                    # nobody took the serial fallback walk
+    rec = out.cpu().numpy()
+    for i, a in enumerate(planes):
+        check_pixels(rec[i], rp.decompress_band(streams[i], ocfg), a, what="config5 plane %d" % i)
+
+
+def test_band_sharded_gigapixel_frame_concatenates(jb):
+    """config 5's sharding on one GPU: the 8 block-row bands of a 3-plane 4096 x 4096 DFT frame, compressed as
+    images of their own (what each of 8 ranks does), concatenate per colour plane to the whole-image streams,
+    and every band decodes to the rows the whole-image decode gives."""
+    import torch
+    h = w = 4096
+    cfg, ocfg = _cfgs(jb, (h, w, 4, 8, "DFT", "qtable", None))
+    planes = np.stack([_big_plane(h, w, 80 + i) for i in range(3)]).astype(np.uint8)
+    d_planes = torch.from_numpy(planes).cuda()
+    whole = jb.compress_planes(d_planes, cfg).to_bytes_list()
+    whole_dec = jb.decompress_bands(whole, cfg)
+    parts = []
+    for r0, r1 in jb.sharding.block_row_bands(h, 4, 8, 8):
+        assert r1 - r0 == h // 8
+        sub, _ = _cfgs(jb, (r1 - r0, w, 4, 8, "DFT", "qtable", None))
+        band = jb.compress_planes(d_planes[:, r0:r1].contiguous(), sub).to_bytes_list()
+        parts.append(band)
+        assert np.array_equal(jb.decompress_bands(band, sub), whole_dec[:, r0:r1])
+    assert jb.sharding.concat_band_streams(parts) == whole
+    assert whole[1] == rp.compress_band(planes[1].astype(np.int64), ocfg)
