@@ -1,10 +1,10 @@
-"""Import the UNMODIFIED reference from ``/root/reference`` (dev container only).
+"""Import the UNMODIFIED reference: from ``/root/reference`` in the dev container, from the verbatim copy
+``baseline/_ref/reference`` (tools/install_reference.py; git-ignored, travels with the snapshot) on the GPU box.
 
-TEST INFRASTRUCTURE ONLY -- never imported by the product path, by ``bench.py``
-or by the ``-m gpu`` tests (``/root/reference`` does not exist on the GPU box).
-It is used by ``tests/golden/make_golden.py`` to generate the committed golden
-vectors and by the optional ``tests/test_oracle_vs_reference.py`` pinning test,
-which skips itself when the reference tree is absent.
+TEST / BASELINE INFRASTRUCTURE ONLY -- never imported by the product path.  Users: ``tests/golden/make_golden.py``
+(generates the committed golden vectors), ``tests/test_oracle_vs_reference.py`` (pins the oracle),
+``tests/test_reference_dropin.py`` (cross-decode and the drop-in swap) and ``bench.py``'s CPU legs (``kind:
+"reference"``).  All of them skip or fall back to the oracle port when no reference tree is present.
 
 Two shims are needed because the reference does not import as shipped here
 (SURVEY.md section 0.3):
@@ -20,7 +20,22 @@ import os
 import sys
 import warnings
 
-REFERENCE_ROOT = os.environ.get("JB_REFERENCE_ROOT", "/root/reference")
+_COPY = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref", "reference")
+
+
+def _find_reference():
+    """JB_REFERENCE_ROOT, else the source tree of the dev container, else the verbatim copy that
+    tools/install_reference.py leaves under baseline/_ref/ (the only one that exists on the GPU box)."""
+    env = os.environ.get("JB_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", _COPY):
+        if os.path.isfile(os.path.join(cand, "pipeline", "__init__.py")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference()
 _SHIM_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_shim")
 
 _cached = None
