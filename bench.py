@@ -416,7 +416,19 @@ def run_ours(args, rank, world, local_rank):
         barrier()
         t_e2e = max_over_ranks(e0.elapsed_time(e1) / K)
         wall_e2e = max_over_ranks((time.perf_counter() - t0) / K * 1e3)
+        # (c) the ceiling under (b): the same plane bytes over the same links, pinned buffers and streams, no kernels
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        from link_probe import probe
+        link = probe(device, n_planes * H * W, n_sub, min(K, 5), barrier, max_over_ranks,
+                     h_src=h_planes, h_dst=bc.h_decoded, d_a=bc.d_planes, d_b=bc.d_decoded)
+        job_bytes = N_IMAGES * 3 * H * W
         e2e = {"value": mp_total / (t_e2e * 1e-3), "unit": "MP/s",
+               "link_ceiling_gbs": job_bytes / link["both_ms"] / 1e6, "link_ms_per_step": link["both_ms"],
+               "frac_of_link": link["both_ms"] / t_e2e,
+               "link_probe": {"what": "tools/link_probe.py: the step's plane bytes host->device and device->host at once, "
+                                      "pinned memory, same sub-batches and streams, no kernels; aggregate GB/s per direction",
+                              "h2d_alone_gbs": job_bytes / link["h2d_ms"] / 1e6, "d2h_alone_gbs": job_bytes / link["d2h_ms"] / 1e6,
+                              "both_gbs_per_direction": job_bytes / link["both_ms"] / 1e6},
                "h2d_bytes_per_step": n_planes * H * W + total_bytes + 8 * (n_planes + n_sub),
                "d2h_bytes_per_step": total_bytes + 8 * (n_planes + n_sub) + 64 * n_sub + n_planes * H * W,
                "ms_per_step": t_e2e, "wall_ms_per_step": wall_e2e,
