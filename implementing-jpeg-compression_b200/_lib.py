@@ -18,7 +18,6 @@ JB_ERR_WORKSPACE, JB_ERR_OUT_CAPACITY, JB_ERR_CUDA, JB_ERR_BAD_RLE_CODE = -5, -6
 JB_ERR_BAD_STREAM, JB_ERR_NO_DEVICE = -9, -10
 JB_FLAG_FORCE_GENERIC, JB_FLAG_NO_TMA, JB_FLAG_NO_REFINE, JB_FLAG_SERIAL_FRAMING = 1, 2, 4, 8
 JB_FLAG_REUSE_TABLES = 16
-JB_FLAG_STRIP_DECODER = 32
 JB_FLAG_TILE_DECODER = 64
 JB_STATUS_WORDS = 4
 JB_MAX_DCT_SIZE = 32

@@ -425,20 +425,34 @@ class BatchCodec:
             self.d_planes = torch.empty((self.n_planes, self.h, self.w), dtype=torch.uint8, device=self.device)
             self.d_streams = torch.empty(self.cap, dtype=torch.uint8, device=self.device)
             self.d_decoded = torch.empty((self.n_planes, self.h, self.w), dtype=torch.uint8, device=self.device)
-            # private workspaces: their table region is built by the first call of each direction and
-            # reused by the later ones (JB_FLAG_REUSE_TABLES); nothing else ever writes to them
-            self._ws_fwd = torch.empty(max(256, lib.jb_compress_workspace_bytes(ctypes.byref(p), self.n_planes)),
-                                       dtype=torch.uint8, device=self.device)
+            # private workspaces: tables and control block are set up by the first call and reused by the later
+            # ones (JB_FLAG_REUSE_TABLES: same direction, parameters AND plane count, since the layout behind the
+            # tables depends on it) -- hence one compress workspace per plane count (the sub-batches of
+            # roundtrip_host come in at most two sizes); nothing else ever writes to them
+            self._ws_fwd = {}
+            self._fwd_workspace(self.n_planes)
             self._ws_inv = torch.empty(256, dtype=torch.uint8, device=self.device)      # sized by the first call
-        self._tables_fwd = self._tables_inv = False
+        self._tables_inv = False
         self.pinned = pinned
         self.h_streams = None
         self.h_decoded = None
 
+    def _fwd_workspace(self, n_planes):
+        """[workspace tensor, set-up done] for compress calls on n_planes planes."""
+        ent = self._ws_fwd.get(n_planes)
+        if ent is None:
+            p = self.config.c_params(self.flags)
+            need = _lib.load().jb_compress_workspace_bytes(ctypes.byref(p), int(n_planes))
+            with torch.cuda.device(self.device):
+                ent = [torch.empty(max(256, int(need)), dtype=torch.uint8, device=self.device), False]
+            self._ws_fwd[n_planes] = ent
+        return ent
+
     def _compress(self, planes, out):
-        fl = self.flags | (_lib.JB_FLAG_REUSE_TABLES if self._tables_fwd else 0)
-        comp = compress_planes(planes, self.config, flags=fl, out=out, ws=self._ws_fwd)
-        self._tables_fwd = True
+        ent = self._fwd_workspace(int(planes.shape[0]))
+        fl = self.flags | (_lib.JB_FLAG_REUSE_TABLES if ent[1] else 0)
+        comp = compress_planes(planes, self.config, flags=fl, out=out, ws=ent[0])
+        ent[1] = True
         return comp
 
     def _decompress(self, data, offsets, lengths, n_planes, in_bytes, out):

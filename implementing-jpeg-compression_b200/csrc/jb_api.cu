@@ -53,16 +53,17 @@ extern "C" size_t jb_max_stream_bytes(const jb_params* p, int n_planes) {
 }
 
 // ---- compress ----------------------------------------------------------------------------------
-struct JbFwdWs { size_t ticket, chunk_len, chunk_off, seg_total, tmp_small, tmp, total; unsigned chunk_cap; };
+struct JbFwdWs { size_t ctrl, seg1, seg2, chunk_len, tmp_small, tmp, total; size_t n_seg_words; unsigned chunk_cap; };
 static JbFwdWs jb_fwd_ws(int d, size_t n_chunks) {
     JbFwdWs w;
     size_t o = jb_align_up(jb_table_layout(d).total, 256);
     w.chunk_cap = (unsigned)jb_align_up((size_t)JB_CHUNK * jb_max_block_bytes(d * d) + 32, 16);
     if (w.chunk_cap < 1024 + 32) w.chunk_cap = 1024 + 32;      // the gather kernel reads 1 KB ahead
-    w.ticket = o;    o += 256;
+    w.ctrl = o;      o += JB_CTRL_BYTES;
+    w.seg1 = o;      o += jb_align_up(2 * ((n_chunks + JB_SEG1 - 1) / JB_SEG1) * 8, 256);     // two sets each
+    w.seg2 = o;      o += jb_align_up(2 * ((n_chunks + JB_SEG2 - 1) / JB_SEG2) * 8, 256);
+    w.n_seg_words = (o - w.seg1) / 8;                          // (the two arrays are adjacent: zeroed as one)
     w.chunk_len = o; o += jb_align_up(n_chunks * 4, 256);
-    w.chunk_off = o; o += jb_align_up(n_chunks * 4, 256);
-    w.seg_total = o; o += jb_align_up(((n_chunks + JB_SCAN_SEG - 1) / JB_SCAN_SEG) * 8, 256);
     w.tmp_small = o; o += jb_align_up(n_chunks * (size_t)JB_SLOT_STRIDE, 256);
     w.tmp = o;       o += jb_align_up(n_chunks * (size_t)w.chunk_cap, 256);
     w.total = o;
@@ -81,8 +82,7 @@ extern "C" size_t jb_stage_pack_workspace_bytes(int n_planes, int blocks_per_pla
     return jb_fwd_ws(dct_size, (size_t)n_planes * cpp).total;
 }
 
-// One small launch instead of three memset nodes: the status block (word 1 = "no bad code yet" = all ones) and,
-// for the compress direction, the chunk ticket.
+// The status block of calls that do not run the self-cleaning protocol (word 1 = "no bad code yet" = all ones).
 __global__ void jb_init_kernel(unsigned long long* status, unsigned* ticket) {
     const int t = threadIdx.x;
     if (t < JB_STATUS_WORDS) status[t] = t == 1 ? ~0ull : 0ull;
@@ -105,8 +105,11 @@ static int jb_forward_common(int mode, const uint8_t* d_planes, size_t plane_str
     if (!d_ws || ws_bytes < w.total) return JB_ERR_WORKSPACE;
     if (((uintptr_t)d_ws & 255) != 0) return JB_ERR_BAD_PARAM;
     char* ws = (char*)d_ws;
-    int rc = jb_reset_status(d_status, (unsigned*)(ws + w.ticket), s);
-    if (rc != JB_OK) return rc;
+    // Control block protocol (jb_forward.cuh): a call without JB_FLAG_REUSE_TABLES establishes the clean state
+    // together with the tables; every call leaves it clean again.  Two launches per call after the first one:
+    // the fused transform kernel and the gather.
+    if (!(g.flags & JB_FLAG_REUSE_TABLES))
+        JB_CUDA_TRY(jb_launch_init_ctrl((unsigned*)(ws + w.ctrl), (unsigned long long*)(ws + w.seg1), w.n_seg_words, s));
 
     JbFwdArgs a;
     memset(&a, 0, sizeof(a));
@@ -116,11 +119,13 @@ static int jb_forward_common(int mode, const uint8_t* d_planes, size_t plane_str
     a.n_planes = n_planes; a.n_chunks = (unsigned)n_chunks;
     a.out = d_out; a.out_cap = out_cap;
     a.plane_off = (unsigned long long*)d_plane_off;
-    a.status = (unsigned long long*)d_status;
-    a.ticket = (unsigned*)(ws + w.ticket);
+    a.ctrl = (unsigned*)(ws + w.ctrl);
+    a.status_out = (unsigned long long*)d_status;
+    a.n_seg1 = (unsigned)((n_chunks + JB_SEG1 - 1) / JB_SEG1);
+    a.n_seg2 = (unsigned)((n_chunks + JB_SEG2 - 1) / JB_SEG2);
     a.chunk_len = (unsigned*)(ws + w.chunk_len);
-    a.chunk_off = (unsigned*)(ws + w.chunk_off);
-    a.seg_total = (unsigned long long*)(ws + w.seg_total);
+    a.seg1 = (unsigned long long*)(ws + w.seg1);
+    a.seg2 = (unsigned long long*)(ws + w.seg2);
     a.tmp = (uint8_t*)(ws + w.tmp);
     a.tmp_small = (uint8_t*)(ws + w.tmp_small);
     a.chunk_cap = w.chunk_cap;
@@ -133,6 +138,7 @@ static int jb_forward_common(int mode, const uint8_t* d_planes, size_t plane_str
         JB_CUDA_TRY(jb_launch_fwd_mid(a, mode, s));
     else
         JB_CUDA_TRY(jb_launch_fwd_generic(a, mode, s));
+    if (mode == 1) JB_CUDA_TRY(jb_launch_finish(a, s));      // (modes 0 and 2 end with the gather, which does this)
     return JB_OK;
 }
 

@@ -49,6 +49,13 @@ struct FfCtaSmem {
     double B64[64];
 };
 
+// fp64 re-evaluation of coefficient (u, v) from the 8x8 box sums of one block (jb_refine.cuh); out of line and
+// with few operands: the fused kernel pays nothing for it in registers.
+template <bool DFT>
+__device__ __noinline__ double ff_refine8(const float* X, int u, int v, const FfCtaSmem& cs, int qmode, double recip) {
+    return jb_refine_f64<float>(X, u, v, 8, 4, DFT ? JB_TRANSFORM_DFT : JB_TRANSFORM_DCT, qmode, cs.A64, cs.B64, recip);
+}
+
 // ---- tile staging -----------------------------------------------------------------------------
 // kind 0: the 32 x 128 tile lies inside the image, rows 16-byte aligned  -> TMA (LDG.128 when TMA is off)
 // kind 1: same columns, but rows run past the bottom edge              -> LDG.128 with replicated rows
@@ -212,9 +219,11 @@ jb_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfKernelArgs 
     const bool aligned = ka.aligned != 0;
     const bool use_tma = ka.use_tma != 0;
 
+    const int P = jb_ctrl_parity(a);                           // which set of the control block this call uses
+    unsigned* const ticket = jb_ctrl_ticket(a, P);
     auto claim = [&]() -> unsigned {
         unsigned c = 0;
-        if (lane == 0) c = atomicAdd(a.ticket, 1u);
+        if (lane == 0) { c = atomicAdd(ticket, 1u); jb_ctrl_note_first(a, P, c); }
         return __shfl_sync(0xffffffffu, c, 0);
     };
 
@@ -359,8 +368,7 @@ jb_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfKernelArgs 
                     #pragma unroll
                     for (int u = 0; u < 8; ++u)
                         if (nearmask >> u & 1u)
-                            qi[u] = (int)rint(jb_refine_f64<float>(X, u, v, 8, 4, DFT ? JB_TRANSFORM_DFT : JB_TRANSFORM_DCT, g.qmode,
-                                                                   cs.A64, cs.B64, a.t.qrecip[u * 8 + v]));
+                            qi[u] = (int)rint(ff_refine8<DFT>(X, u, v, cs, g.qmode, a.t.qrecip[u * 8 + v]));
                 }
                 __syncwarp();
             }
@@ -413,7 +421,7 @@ jb_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfKernelArgs 
                     const int nb = jb_min(ws.nbig, FF_BIG_CAP);
                     for (int k = 0; k < nb; ++k)
                         if (ws.big_blk[k] == lane && ws.big_pos[k] == bad_pos) amp = ws.big_amp[k];
-                    jb_report_bad_code(a.status, (unsigned long long)ck.plane * g.nblocks + ck.blk0 + lane,
+                    jb_report_bad_code(jb_ctrl_status(a, P), (unsigned long long)ck.plane * g.nblocks + ck.blk0 + lane,
                                        bad_pos, bad_run, amp);
                 }
             }
@@ -425,7 +433,7 @@ jb_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfKernelArgs 
             }
             const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
             const unsigned excl = incl - len;
-            if (lane == 0) a.chunk_len[ck.chunk] = total;
+            if (lane == 0) jb_record_chunk_len(a, P, ck.chunk, total);
             uint8_t* slot = jb_chunk_slot(a, ck.chunk, total);
             const bool small = total <= FF_COMPACT_BYTES && !__any_sync(0xffffffffu, len > FF_STAGE_CAP * 4);
             if (small) {
@@ -532,7 +540,7 @@ cudaError_t jb_launch_fwd_fast(const JbFwdArgs& a, int mode, cudaStream_t s) {
     if (mode == 0) {
         cudaError_t e = dft ? jb_fwd_fast_launch_t<true, 0>(map, ka, s) : jb_fwd_fast_launch_t<false, 0>(map, ka, s);
         if (e != cudaSuccess) return e;
-        return jb_launch_scan_gather(a, s);
+        return jb_launch_gather(a, s);
     }
     return dft ? jb_fwd_fast_launch_t<true, 1>(map, ka, s) : jb_fwd_fast_launch_t<false, 1>(map, ka, s);
 }

@@ -65,6 +65,12 @@ bool jb_fwd_mid_eligible(const JbGeom& g) {
     return fm_layout(g.d, g.bs, g.transform == JB_TRANSFORM_DFT).total <= 200 * 1024;
 }
 
+// fp64 re-evaluation from float box sums (jb_refine.cuh), out of line
+__device__ __noinline__ double fm_refine(const float* X, int u, int v, int d, int bs, int transform, int qmode,
+                                         const double* A64, const double* B64, double recip) {
+    return jb_refine_f64<float>(X, u, v, d, bs, transform, qmode, A64, B64, recip);
+}
+
 template <typename Writer>
 __device__ __forceinline__ void fm_pack_masked(const int16_t* c, const uint32_t* mask, int mask_words, Writer& bw,
                                                int& bad_pos, int& bad_run) {
@@ -108,10 +114,15 @@ jb_fwd_mid_kernel(const JbFwdArgs a) {
     __shared__ unsigned s_chunk;
     __shared__ unsigned s_blen[JB_CHUNK], s_boff[JB_CHUNK];
     __shared__ int s_big_blk[FM_BIG_CAP], s_big_pos[FM_BIG_CAP], s_big_amp[FM_BIG_CAP];
-    __shared__ int s_nbig, s_slow;
+    __shared__ int s_nbig, s_slow, s_P;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { s_chunk = atomicAdd(a.ticket, 1u); s_nbig = 0; s_slow = 0; }
+    if (tid == 0) {
+        s_P = jb_ctrl_parity(a);
+        s_chunk = atomicAdd(jb_ctrl_ticket(a, s_P), 1u);
+        jb_ctrl_note_first(a, s_P, s_chunk);
+        s_nbig = 0; s_slow = 0;
+    }
     for (int idx = tid; idx < n; idx += FM_THREADS) {
         const int v = idx / d, j = idx - v * d;
         sAt[j * d + v] = a.t.fA[idx];
@@ -122,6 +133,7 @@ jb_fwd_mid_kernel(const JbFwdArgs a) {
     }
     __syncthreads();
     const unsigned chunk = s_chunk;
+    const int P = s_P;
     if (chunk >= a.n_chunks) return;
     const int plane = chunk / g.cpp;
     const int blk0 = (chunk % g.cpp) * JB_CHUNK;
@@ -241,7 +253,7 @@ jb_fwd_mid_kernel(const JbFwdArgs a) {
                 const float val = y4[k] * sQm[idx];
                 float r = rintf(val);
                 if (refine_on && fabsf(fabsf(val - r) - 0.5f) < sQt[idx] + 2.4e-7f * fabsf(val))
-                    r = (float)rint(jb_refine_f64<float>(sX, u, v, d, bs, g.transform, g.qmode, a.t.fA64, a.t.fB64, a.t.qrecip[idx]));
+                    r = (float)rint(fm_refine(sX, u, v, d, bs, g.transform, g.qmode, a.t.fA64, a.t.fB64, a.t.qrecip[idx]));
                 int q = (int)r;
                 const int zp = sZz[idx];
                 if (MODE == 1) {
@@ -287,7 +299,7 @@ jb_fwd_mid_kernel(const JbFwdArgs a) {
                 const int nb = jb_min(s_nbig, FM_BIG_CAP);
                 for (int k = 0; k < nb; ++k)
                     if (s_big_blk[k] == tid && s_big_pos[k] == bad_pos) amp = s_big_amp[k];
-                jb_report_bad_code(a.status, (unsigned long long)plane * g.nblocks + blk0 + tid, bad_pos, bad_run, amp);
+                jb_report_bad_code(jb_ctrl_status(a, P), (unsigned long long)plane * g.nblocks + blk0 + tid, bad_pos, bad_run, amp);
             }
         }
         unsigned incl = len;
@@ -298,7 +310,7 @@ jb_fwd_mid_kernel(const JbFwdArgs a) {
         }
         s_blen[tid] = len;
         s_boff[tid] = incl - len;
-        if (tid == 31) a.chunk_len[chunk] = incl;
+        if (tid == 31) jb_record_chunk_len(a, P, chunk, incl);
     }
     __syncthreads();
     // ---- 6. chunk bytes -> slot ----
@@ -392,12 +404,17 @@ jb_fwd_mid_warp_kernel(const JbFwdArgs a) {
     __shared__ unsigned s_chunk;
     __shared__ unsigned s_blen[JB_CHUNK], s_boff[JB_CHUNK];
     __shared__ int s_big_blk[FM_BIG_CAP], s_big_pos[FM_BIG_CAP], s_big_amp[FM_BIG_CAP];
-    __shared__ int s_nbig, s_slow;
+    __shared__ int s_nbig, s_slow, s_P;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float* sX = (float*)(smem + L.x) + warp * n;
     uint16_t* sV = (uint16_t*)(smem + L.vrow) + (size_t)warp * 2 * L.vrowW * 2;     // two band rows per warp
-    if (tid == 0) { s_chunk = atomicAdd(a.ticket, 1u); s_nbig = 0; s_slow = 0; }
+    if (tid == 0) {
+        s_P = jb_ctrl_parity(a);
+        s_chunk = atomicAdd(jb_ctrl_ticket(a, s_P), 1u);
+        jb_ctrl_note_first(a, s_P, s_chunk);
+        s_nbig = 0; s_slow = 0;
+    }
     for (int idx = tid; idx < n; idx += FW_WARPS * 32) {
         sA[idx] = a.t.fA[idx];
         sQm[idx] = a.t.qmult[idx];
@@ -406,6 +423,7 @@ jb_fwd_mid_warp_kernel(const JbFwdArgs a) {
     }
     __syncthreads();
     const unsigned chunk = s_chunk;
+    const int P = s_P;
     if (chunk >= a.n_chunks) return;
     const int plane = chunk / g.cpp;
     const int blk0 = (chunk % g.cpp) * JB_CHUNK;
@@ -515,7 +533,7 @@ jb_fwd_mid_warp_kernel(const JbFwdArgs a) {
                 const float val = y * sQm[idx];
                 float r = rintf(val);
                 if (refine_on && fabsf(fabsf(val - r) - 0.5f) < sQt[idx] + 2.4e-7f * fabsf(val))
-                    r = (float)rint(jb_refine_f64<float>(sX, u, v, D, bs, g.transform, g.qmode, a.t.fA64, a.t.fB64, a.t.qrecip[idx]));
+                    r = (float)rint(fm_refine(sX, u, v, D, bs, g.transform, g.qmode, a.t.fA64, a.t.fB64, a.t.qrecip[idx]));
                 int q = (int)r;
                 const int zp = sZz[idx];
                 if (MODE == 1) {
@@ -562,7 +580,7 @@ jb_fwd_mid_warp_kernel(const JbFwdArgs a) {
                     const int nb = jb_min(s_nbig, FM_BIG_CAP);
                     for (int k = 0; k < nb; ++k)
                         if (s_big_blk[k] == my_gi && s_big_pos[k] == bad_pos) amp = s_big_amp[k];
-                    jb_report_bad_code(a.status, (unsigned long long)plane * g.nblocks + blk0 + my_gi, bad_pos, bad_run, amp);
+                    jb_report_bad_code(jb_ctrl_status(a, P), (unsigned long long)plane * g.nblocks + blk0 + my_gi, bad_pos, bad_run, amp);
                 }
             }
             s_blen[my_gi] = len;
@@ -578,7 +596,7 @@ jb_fwd_mid_warp_kernel(const JbFwdArgs a) {
             if (tid >= o) incl += y;
         }
         s_boff[tid] = incl - len;
-        if (tid == 31) a.chunk_len[chunk] = incl;
+        if (tid == 31) jb_record_chunk_len(a, P, chunk, incl);
     }
     __syncthreads();
     uint8_t* slot = jb_chunk_slot(a, chunk, s_boff[JB_CHUNK - 1] + s_blen[JB_CHUNK - 1]);
@@ -632,14 +650,14 @@ cudaError_t jb_launch_fwd_mid(const JbFwdArgs& a, int mode, cudaStream_t s) {
         if (mode == 0) {
             cudaError_t e = fw_launch_d<0>(a, s);
             if (e != cudaSuccess) return e;
-            return jb_launch_scan_gather(a, s);
+            return jb_launch_gather(a, s);
         }
         return fw_launch_d<1>(a, s);
     }
     if (mode == 0) {
         cudaError_t e = dft ? fm_launch_t<true, 0>(a, s) : fm_launch_t<false, 0>(a, s);
         if (e != cudaSuccess) return e;
-        return jb_launch_scan_gather(a, s);
+        return jb_launch_gather(a, s);
     }
     return dft ? fm_launch_t<true, 1>(a, s) : fm_launch_t<false, 1>(a, s);
 }

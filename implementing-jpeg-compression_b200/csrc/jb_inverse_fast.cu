@@ -21,7 +21,6 @@
 //   * chunks are claimed from a device-wide counter (see the kernel).
 #include <cuda.h>
 #include <string.h>
-#include <stdlib.h>
 
 #include "jb_common.cuh"
 #include "jb_fast_common.cuh"
@@ -36,8 +35,8 @@
 
 // Row-store variant: 72 registers and 7.8 KB of shared memory per warp would allow 28 warps per SM, but the kernel is
 // bound by the HBM write path, not by latency: measured 1.12 / 1.10 / 1.12 / 1.14 / 1.06 / 1.11 / 1.13 / 1.15 ms with
-// 8 / 10 / 12 / 14 / 16 / 20 / 24 / 28 warps (1024 x 1080p).  JB_DEBUG_ROWS_WARPS overrides the default (tuning aid).
-#define FI_ROWS_MAX_WARPS 28
+// 8 / 10 / 12 / 14 / 16 / 20 / 24 / 28 warps (1024 x 1080p, profiles/r1_sweep_inv_warps.txt).
+#define FI_ROWS_MAX_WARPS 16
 #define FI_ROWS_WARPS 16
 #define FI_ROWS_STAGE_WORDS 512
 
@@ -350,263 +349,11 @@ jb_inv_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FiKernelArgs 
     }
 }
 
-// =====================================================================================================
-// Strip variant: dense planes whose width is a whole number of 4-block groups (1080p, 4K, ...).
-//
-// Opt-in (JB_FLAG_STRIP_DECODER): measured 1.48 ms against 1.40 ms for the tile kernel on 1024 x 1080p -- the
-// linear stores it buys are paid for with six CTA-wide synchronisation points per 240 blocks, where the tile
-// kernel's warps never wait for each other.  Kept because it is the only way found so far to issue linear writes.
-//
-// HBM writes of 32-row x 128-byte pieces top out near 5.1 TB/s on this part, linear writes near 6.3 TB/s
-// (tools/dram_probe.cu), and the tile kernel above is bound by exactly that.  Here a CTA of 8 working warps
-// (two CTAs per SM, so that one decodes while the other stores) works in rounds of up to 256 consecutive
-// blocks = nseg segments of S blocks; a segment is a whole block row, or an S-block piece of one:
-//   1. decode: warp w decodes blocks 32w .. 32w+31 of the round, one lane per block, into a CTA-wide
-//      coefficient pool (the round's bytes are contiguous in the input, also across a plane boundary when the
-//      streams are stored back to back);
-//   2. transform: for every segment, warp t transforms the 4-block tiles t, t+8 and writes their 128-byte
-//      column bands into the strip buffer of 32 rows x (32 S) bytes; when all bands are in, a ninth warp sends
-//      the strip out with 1-D bulk copies -- one copy for a whole block row of a dense plane (rows_valid x W
-//      contiguous bytes), else one per row -- and hands the buffer back when the copy engine has read it
-//      (mbarriers "full" / "empty"); the working warps meanwhile transform the next segment in registers.
-// =====================================================================================================
-#define FS_WARPS 8                      // working warps; one more warp issues the stores
-#define FS_POOL_BLOCKS (FS_WARPS * JB_CHUNK)
-
-struct FsKernelArgs {
-    JbInvArgs a;
-    int S;                  // blocks per segment (multiple of 4, divides blocks per row)
-    int nseg;               // segments per round
-    int spr;                // segments per block row
-    int spp;                // segments per plane
-    unsigned total_segs, n_rounds;
-};
-
-template <bool DFT>
-__global__ void __launch_bounds__((FS_WARPS + 1) * 32, 2) jb_inv_strip_kernel(const FsKernelArgs ka) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const JbInvArgs& a = ka.a;
-    const JbGeom& g = a.g;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint8_t* s_izz = (uint8_t*)smem_raw;                                             // 64 bytes
-    unsigned long long* s_full = (unsigned long long*)(smem_raw + 64);
-    unsigned long long* s_empty = s_full + 1;
-    uint32_t* s_coef = (uint32_t*)(smem_raw + 128);                                  // [256][FF_COEF_W]
-    float* s_scr = (float*)(smem_raw + 128 + FS_POOL_BLOCKS * FF_COEF_W * 4) + (warp % FS_WARPS) * (4 * FF_BLK_W);
-    uint8_t* s_strip = smem_raw + 128 + FS_POOL_BLOCKS * FF_COEF_W * 4 + FS_WARPS * 4 * FF_BLK_W * 4;
-    const int S = ka.S, TS = S >> 2, nseg = ka.nseg;
-    const int strip_pitch = S * 32;
-    const bool worker = warp < FS_WARPS;
-
-    for (int i = tid; i < 64; i += blockDim.x) s_izz[i] = (uint8_t)a.t.izz[i];
-    if (tid == 0) {
-        ff_mbar_init(s_full, FS_WARPS);
-        ff_mbar_init(s_empty, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (tid == 0) ff_mbar_arrive(s_empty);                   // the strip buffer starts out free
-
-    const int li = lane >> 2, lb = lane & 3;
-    const int ncol = DFT ? (li < 5 ? li : 12 - li) : li;
-    float dq[8];
-    #pragma unroll
-    for (int v = 0; v < 8; ++v) {
-        const float sc = DFT ? (1.0f / 64.0f) : ((li == 0 ? 0.125f : 0.25f) * (v == 0 ? 0.125f : 0.25f));
-        dq[v] = a.t.dqmult[li * 8 + v] * sc;
-    }
-    unsigned uses = 0;                                       // how often the strip buffer has been filled (CTA-uniform)
-
-    for (unsigned r = blockIdx.x; r < ka.n_rounds; r += gridDim.x) {
-        // ---------------- 1. decode the round's blocks into the pool ----------------
-        if (worker) {
-            {
-                uint4* z = (uint4*)(s_coef + (size_t)warp * JB_CHUNK * FF_COEF_W);
-                for (int i = lane; i < JB_CHUNK * FF_COEF_W / 4; i += 32) z[i] = make_uint4(0, 0, 0, 0);
-            }
-            const int q = warp * 32 + lane;
-            const int seg_q = q / S;
-            const unsigned gseg_q = r * (unsigned)nseg + (unsigned)seg_q;
-            const bool valid = seg_q < nseg && gseg_q < ka.total_segs;
-            unsigned long long abs_start = 0, abs_end = 0;
-            bool lane_ok = true;
-            if (valid) {
-                const int plane = (int)(gseg_q / (unsigned)ka.spp);
-                const int blk = (int)(gseg_q % (unsigned)ka.spp) * S + (q - seg_q * S);
-                const unsigned long long len = a.plane_len[plane], base = a.plane_off[plane];
-                const unsigned* bs = a.block_start + (size_t)plane * g.nblocks + blk;
-                const unsigned long long st = bs[0], en = (blk + 1 < g.nblocks) ? (unsigned long long)bs[1] : len;
-                lane_ok = st < en && en <= len && base + en <= a.in_bytes;
-                abs_start = base + st; abs_end = base + en;
-            }
-            const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-            const int nv = __popc(vmask);                    // valid lanes are 0 .. nv-1
-            const unsigned long long next_start = __shfl_down_sync(0xffffffffu, abs_start, 1);
-            const bool mono = !valid || lane + 1 >= nv || abs_end <= next_start;
-            const bool all_ok = __all_sync(0xffffffffu, lane_ok && mono);
-            int bad = __any_sync(0xffffffffu, !lane_ok) ? 1 : 0;
-            if (nv > 0 && !bad) {
-                const unsigned long long a0 = __shfl_sync(0xffffffffu, abs_start, 0);
-                const unsigned long long e1 = __shfl_sync(0xffffffffu, abs_end, nv - 1);
-                const unsigned long long addr0 = (unsigned long long)(uintptr_t)a.in + a0;
-                const unsigned mis = (unsigned)(addr0 & 3ull);
-                const unsigned long long nw64 = (e1 - a0 + mis + 3ull) >> 2;
-                const bool staged = all_ok && nw64 <= FI_STREAM_WORDS;
-                int16_t* row = (int16_t*)(s_coef + (size_t)q * FF_COEF_W);
-                if (staged) {
-                    // (the staging rows live in the strip buffer: its last store was waited for at the end of the last round)
-                    uint32_t* sb = (uint32_t*)s_strip + warp * FI_STREAM_WORDS;
-                    const uint32_t* wsrc = (const uint32_t*)(uintptr_t)(addr0 - mis);
-                    const unsigned nwords = (unsigned)nw64;
-                    for (unsigned i = lane; i < nwords; i += 32) sb[i] = __ldg(wsrc + i);
-                    __syncwarp();
-                    if (valid)
-                        bad = fi_decode_block<false>(sb, nwords, (uint32_t)(abs_start - a0 + mis) * 8u,
-                                                     (uint32_t)(abs_end - a0 + mis) * 8u, row, s_izz);
-                } else if (valid) {
-                    const unsigned long long ad = (unsigned long long)(uintptr_t)a.in + abs_start;
-                    const unsigned m2 = (unsigned)(ad & 3ull);
-                    const unsigned nwords = (unsigned)((abs_end - abs_start + m2 + 3ull) >> 2);
-                    bad = fi_decode_block<true>((const uint32_t*)(uintptr_t)(ad - m2), nwords, m2 * 8u,
-                                                (uint32_t)(abs_end - abs_start + m2) * 8u, row, s_izz);
-                }
-            }
-            if (__any_sync(0xffffffffu, bad) && lane == 0) jb_set_error(a.status, JB_ERR_BAD_STREAM);
-        }
-        __syncthreads();                                     // the pool is complete; the staging rows are dead
-
-        // ---------------- 2. transform and store, segment by segment ----------------
-        for (int seg = 0; seg < nseg; ++seg) {
-            const unsigned gseg = r * (unsigned)nseg + (unsigned)seg;
-            if (gseg >= ka.total_segs) break;
-            const unsigned k = uses++;
-            if (worker) {
-                uint32_t packed[2][8];                       // the two tiles of this warp, one byte value per sample row
-                #pragma unroll
-                for (int pass = 0; pass < 2; ++pass) {
-                    const int tile = warp + pass * FS_WARPS;
-                    if (tile < TS) {
-                        float z[8], rr[8];
-                        {
-                            const uint4 w = *(const uint4*)(s_coef + (size_t)(seg * S + 4 * tile + lb) * FF_COEF_W + li * 4);
-                            z[0] = (float)(short)(w.x & 0xFFFFu) * dq[0]; z[1] = (float)(short)(w.x >> 16) * dq[1];
-                            z[2] = (float)(short)(w.y & 0xFFFFu) * dq[2]; z[3] = (float)(short)(w.y >> 16) * dq[3];
-                            z[4] = (float)(short)(w.z & 0xFFFFu) * dq[4]; z[5] = (float)(short)(w.z >> 16) * dq[5];
-                            z[6] = (float)(short)(w.w & 0xFFFFu) * dq[6]; z[7] = (float)(short)(w.w >> 16) * dq[7];
-                        }
-                        if (DFT) ff_rdft8(z, rr); else ff_idct8(z, rr);
-                        {
-                            float4* sc = (float4*)(s_scr + lb * FF_BLK_W + li * 8);
-                            const int h0 = li & 1;
-                            const float4 r0 = make_float4(rr[0], rr[1], rr[2], rr[3]), r1 = make_float4(rr[4], rr[5], rr[6], rr[7]);
-                            sc[h0] = h0 ? r1 : r0; sc[h0 ^ 1] = h0 ? r0 : r1;
-                        }
-                        __syncwarp();
-                        float col[8], x[8];
-                        #pragma unroll
-                        for (int kk = 0; kk < 8; ++kk) col[kk] = s_scr[lb * FF_BLK_W + kk * 8 + li];
-                        if (DFT) ff_dft_column_stage(col, li, x); else ff_idct8(col, x);
-                        #pragma unroll
-                        for (int m = 0; m < 8; ++m) {
-                            int p = __float_as_int(x[m] + 12582912.0f) - 0x4B400000;
-                            packed[pass][m] = (uint32_t)max(0, min(255, p)) * 0x01010101u;
-                        }
-                        __syncwarp();
-                    }
-                }
-                // the store that last used the strip buffer must have read it
-                while (!ff_mbar_try_wait(s_empty, k & 1u)) { }
-                const int pw = strip_pitch >> 2;
-                #pragma unroll
-                for (int pass = 0; pass < 2; ++pass) {
-                    const int tile = warp + pass * FS_WARPS;
-                    if (tile < TS) {
-                        uint32_t* t32 = (uint32_t*)s_strip + tile * 32 + 8 * lb + ncol;
-                        #pragma unroll
-                        for (int m = 0; m < 8; ++m) {
-                            #pragma unroll
-                            for (int kk = 0; kk < 4; ++kk) t32[(4 * m + kk) * pw] = packed[pass][m];
-                        }
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) { ff_fence_proxy_async(); ff_mbar_arrive(s_full); }
-            } else if (lane == 0) {
-                while (!ff_mbar_try_wait(s_full, k & 1u)) { }
-                ff_fence_proxy_async();
-                const int plane = (int)(gseg / (unsigned)ka.spp);
-                const int sg = (int)(gseg % (unsigned)ka.spp);
-                const int by = sg / ka.spr, sx = sg - by * ka.spr;
-                const int rows = jb_min(32, g.H - by * 32);
-                uint8_t* dst = a.planes_out + (size_t)plane * a.plane_stride + (size_t)by * 32 * a.row_pitch + (size_t)sx * strip_pitch;
-                if (ka.spr == 1) {
-                    ff_bulk_store_1d(dst, s_strip, (uint32_t)(rows * strip_pitch));
-                } else {
-                    for (int y = 0; y < rows; ++y)
-                        ff_bulk_store_1d(dst + (size_t)y * a.row_pitch, s_strip + (size_t)y * strip_pitch, (uint32_t)strip_pitch);
-                }
-                ff_bulk_commit();
-                ff_bulk_wait_read<0>();                      // the copy engine has read the strip: hand the buffer back
-                ff_mbar_arrive(s_empty);
-            }
-        }
-        __syncthreads();                                     // pool and staging rows may be overwritten
-    }
-}
-
-static int fs_segment_blocks(int hb) {
-    for (int s = 64; s >= 48; s -= 4)
-        if (hb % s == 0) return s;
-    return 0;
-}
-
-bool jb_inv_strip_eligible(const JbInvArgs& a) {
-    const JbGeom& g = a.g;
-    if (g.d != 8 || g.bs != 4 || (g.flags & JB_FLAG_NO_TMA)) return false;
-    if (g.W != g.hb * 32 || a.row_pitch != (size_t)g.W) return false;               // dense rows, no crop on the right
-    if (a.n_planes > 1 && a.plane_stride != (size_t)g.H * g.W) return false;
-    if (((uintptr_t)a.planes_out & 15) || (((size_t)g.H * g.W) & 15)) return false;
-    return fs_segment_blocks(g.hb) != 0;
-}
-
-cudaError_t jb_launch_inv_strip(const JbInvArgs& a, cudaStream_t s) {
-    FsKernelArgs ka;
-    ka.a = a;
-    const JbGeom& g = a.g;
-    ka.S = fs_segment_blocks(g.hb);
-    ka.nseg = FS_POOL_BLOCKS / ka.S;
-    ka.spr = g.hb / ka.S;
-    ka.spp = ka.spr * g.vb;
-    ka.total_segs = (unsigned)a.n_planes * (unsigned)ka.spp;
-    ka.n_rounds = (ka.total_segs + ka.nseg - 1) / ka.nseg;
-    const size_t smem = 128 + (size_t)FS_POOL_BLOCKS * FF_COEF_W * 4 + (size_t)FS_WARPS * 4 * FF_BLK_W * 4 + (size_t)32 * ka.S * 32;
-    const bool dft = g.transform == JB_TRANSFORM_DFT;
-    cudaError_t e = dft ? cudaFuncSetAttribute(jb_inv_strip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                        : cudaFuncSetAttribute(jb_inv_strip_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const unsigned grid = ka.n_rounds < 2u * (unsigned)sms ? ka.n_rounds : 2u * (unsigned)sms;
-    if (grid == 0) return cudaSuccess;
-    if (dft) jb_inv_strip_kernel<true><<<grid, (FS_WARPS + 1) * 32, smem, s>>>(ka);
-    else jb_inv_strip_kernel<false><<<grid, (FS_WARPS + 1) * 32, smem, s>>>(ka);
-    return cudaGetLastError();
-}
-
 bool jb_inv_fast_eligible(const JbGeom& g) { return g.d == 8 && g.bs == 4; }
 
 template <bool DFT, int MODE, bool ROWS>
 static cudaError_t jb_inv_fast_launch_t(const CUtensorMap& map, const FiKernelArgs& ka, cudaStream_t s) {
-    int NWARPS = ROWS ? FI_ROWS_WARPS : FI_WARPS;
-    if (ROWS) {
-        static const int tuned = [] {                          // tuning aid, read once per process
-            const char* e = getenv("JB_DEBUG_ROWS_WARPS");
-            const int w = e ? atoi(e) : 0;
-            return (w >= 4 && w <= FI_ROWS_MAX_WARPS) ? w : 0;
-        }();
-        if (tuned) NWARPS = tuned;
-    }
+    const int NWARPS = ROWS ? FI_ROWS_WARPS : FI_WARPS;
     const size_t smem = 128 + (size_t)NWARPS * (ROWS ? sizeof(FiRowsSmem) : sizeof(FiWarpSmem));
     cudaError_t e = cudaFuncSetAttribute(jb_inv_fast_kernel<DFT, MODE, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -630,7 +377,6 @@ static cudaError_t jb_inv_fast_launch_r(const CUtensorMap& map, const FiKernelAr
 }
 
 cudaError_t jb_launch_inv_fast(const JbInvArgs& a, int mode, cudaStream_t s) {
-    if (mode == 0 && (a.g.flags & JB_FLAG_STRIP_DECODER) && jb_inv_strip_eligible(a)) return jb_launch_inv_strip(a, s);
     FiKernelArgs ka;
     ka.a = a;
     const JbGeom& g = a.g;

@@ -21,7 +21,9 @@ __device__ __forceinline__ JbC64 jb_rot90(JbC64 a) { return {a.i, -a.r}; }      
 
 // pocketfft (C++, as built into numpy >= 2.0) cfftp::pass8<fwd = true> with ido = l1 = 1, the whole plan of a
 // length-8 transform: PM / PMINPLACE / ROTX90 / ROTX45 / ROTX135 in its order, hsqt2 = sqrt(1/2) rounded.
-__device__ __forceinline__ void jb_pf_pass8(const JbC64 (&c)[8], JbC64 (&ch)[8]) {
+// (Not inlined, operands through memory: this path runs for a few coefficients in a thousand, and kept out of
+// line it costs the calling kernels no registers.)
+static __device__ __noinline__ void jb_pf_pass8(const JbC64* c, JbC64* ch) {
     const double h = 0.70710678118654752440;
     JbC64 a0, a1, a2, a3, a4, a5, a6, a7, s, t;
     a1 = jb_cadd(c[1], c[5]); a5 = jb_csub(c[1], c[5]);
@@ -43,8 +45,9 @@ __device__ __forceinline__ void jb_pf_pass8(const JbC64 (&c)[8], JbC64 (&ch)[8])
 
 // X: the d x d box sums of the block (exact integers, as int or float); returns the value the reference hands to
 // np.round for coefficient (u, v).  A64 / B64: the fp64 transform matrices of jb_tables.cu; recip: qrecip[u*d+v].
+// (Inlined into a small __noinline__ wrapper per kernel file, so that the hot kernels see a call with few operands.)
 template <typename XT>
-__device__ __noinline__ double jb_refine_f64(const XT* X, int u, int v, int d, int bs, int transform, int qmode,
+__device__ __forceinline__ double jb_refine_f64(const XT* X, int u, int v, int d, int bs, int transform, int qmode,
                                              const double* A64, const double* B64, double recip) {
     const double bs2 = (double)(bs * bs);          // np.mean: exact integer sum / count (subsampling.py:9-11)
     double y;

@@ -14,7 +14,10 @@
  * Conventions
  *  - every pointer named d_* is a DEVICE pointer on the current CUDA device; the
  *    caller owns every buffer, including the workspace; the library allocates
- *    nothing and keeps no state between calls;
+ *    nothing on the device and keeps no per-call state.  Process-wide state is limited to
+ *    two read-mostly caches behind a lock (the host-evaluated DCT matrix of the last
+ *    dct_size, the driver entry point of the tensor-map encoder) and the measurement hook
+ *    jb_debug_kernel_events, which is off unless a profiler arms it;
  *  - calls are asynchronous and ordered on `stream` (a cudaStream_t passed as
  *    void*; NULL = the legacy default stream).  Host-detectable problems return
  *    a negative code at once; problems only the device can see (an amplitude
@@ -80,13 +83,13 @@ typedef struct jb_params {
 #define JB_FLAG_NO_TMA        2  /* specialised kernels stage tiles with plain loads/stores */
 #define JB_FLAG_NO_REFINE     4  /* skip the float64 re-evaluation of near-tie coefficients */
 #define JB_FLAG_SERIAL_FRAMING 8 /* decoder: find block boundaries with the serial fallback walk only */
-#define JB_FLAG_STRIP_DECODER 32 /* decoder: use the CTA-wide strip kernel where it applies (dense planes, width a
-                                   whole number of 48..64-block segments); experimental, measured slower */
 #define JB_FLAG_TILE_DECODER 64  /* decoder, 8x8 / block_size 4 kernel: store 32-row x 128-byte tiles (TMA tensor stores,
                                    or plain stores with JB_FLAG_NO_TMA) instead of whole chunk rows; kept for comparison */
-#define JB_FLAG_REUSE_TABLES  16 /* the caller promises that this workspace was last used by a call of the same
-                                   direction with identical transform / size / quantiser parameters and has not
-                                   been written since: the table builder launch is skipped */
+#define JB_FLAG_REUSE_TABLES  16 /* the caller promises that this workspace was last used by a COMPLETED-OR-QUEUED call of
+                                   the same direction with identical jb_params and n_planes (on the same stream, or
+                                   ordered before this one) and has not been written since: the launches that build the
+                                   tables and clean the control block are skipped -- a compress call is then two
+                                   launches, the fused transform kernel and the gather */
 
 /* Derived sizes (pipeline/run_length_encoding.py:80-88, pipeline/dct_padding.py:11-21). */
 typedef struct jb_geometry {

@@ -388,21 +388,20 @@ def test_rgb_front_ends_equal_the_pillow_flow(jb):
 
 @pytest.mark.parametrize("tr", ["DCT", "DFT"])
 @pytest.mark.parametrize("h,w,n", [(90, 1536, 5), (64, 1920, 7), (200, 3840, 2), (33, 2048, 3)])
-def test_strip_decoder_equals_tile_decoder(jb, h, w, n, tr):
-    """JB_FLAG_STRIP_DECODER (32): dense planes whose width is a whole number of 48..64-block segments go through
-    the CTA-wide strip kernel (rounds of 256 blocks that may span plane boundaries, bottom crop, one bulk copy per
-    strip or per row): same pixels as the per-warp tile kernel, the generic kernel and, within 1 LSB, the oracle."""
+def test_decoder_variants_agree_on_wide_planes(jb, h, w, n, tr):
+    """Dense, wide planes (bottom crop, several planes per batch): the row-store decoder (default), the tile decoder
+    (64) and the generic kernel (1) give the same pixels -- the fast variants bit for bit, the generic one and the
+    oracle within 1 LSB."""
     import torch
     cfg, ocfg = _cfgs(jb, (h, w, 4, 8, tr, "qtable", None))
     planes = np.stack([synth_plane(h, w, 300 + i) for i in range(n)]).astype(np.uint8)
     comp = jb.compress_planes(torch.from_numpy(planes).cuda(), cfg)
     lens = comp.offsets[1:] - comp.offsets[:-1]
     outs = {}
-    for flags in (0, 64, 32, 1):
+    for flags in (0, 64, 1):
         out, status = jb.decompress_planes(comp.data, comp.offsets[:-1], lens, cfg, n, in_bytes=comp.total_bytes(), flags=flags)
         jb.check_status(status)
         outs[flags] = out.cpu().numpy()
-    assert np.array_equal(outs[0], outs[32])
     assert np.array_equal(outs[0], outs[64])
     assert np.abs(outs[0].astype(np.int64) - outs[1].astype(np.int64)).max() <= 1
     streams = comp.to_bytes_list()
