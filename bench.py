@@ -275,7 +275,7 @@ def run_ours(args, rank, world, local_rank):
     n_planes = 3 * n_img
     cfg = jb.Configuration(width=W, height=H, block_size=BS, dct_size=D, transform=TRANSFORM,
                            quantization=jb.QuantizationMethod(QNAME))
-    bc = jb.BatchCodec(cfg, n_planes, device=device)
+    bc = jb.BatchCodec(cfg, n_planes, device=device, flags=(jb._lib.JB_FLAG_PDL if args.pdl else 0))
     bc.d_planes.copy_(synth_planes_device(n_img, device, i0))
     torch.cuda.synchronize()
     mp_rank = n_img * H * W / 1e6
@@ -320,6 +320,8 @@ def run_ours(args, rank, world, local_rank):
     def direct_d():
         bc.decompress_device(state["comp"], total_bytes)
     run_c, run_d = direct_c, direct_d
+    run_step = None
+    two_streams = None
     if not args.no_graph:
         try:
             side = torch.cuda.Stream()
@@ -341,9 +343,55 @@ def run_ours(args, rank, world, local_rank):
             state["comp"] = comp_g
             run_c, run_d = g_c.replay, g_d.replay
             launch_mode = "cuda graphs (one per library call)"
+            if args.step_graph:
+                # the step's two calls in ONE graph: no graph-launch gap between compress and decompress
+                g_s = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_s, pool=g_c.pool()):
+                    comp_s = bc.compress_device()
+                    out_s, status_s = bc.decompress_device(comp_s, total_bytes)
+                g_s.replay()
+                torch.cuda.synchronize()
+                jb.check_status(comp_s.status); jb.check_status(status_s)
+                if comp_s.total_bytes() != total_bytes or not torch.equal(out_s[:3], out[:3]):
+                    raise RuntimeError("step graph replay differs from the direct calls")
+                run_step = g_s.replay
+                launch_mode = "cuda graph (one per step: compress + decompress)"
+                if args.streams == 2:
+                    # Consecutive steps are independent batches: a second codec object (own buffers, own workspaces)
+                    # on a second CUDA stream takes every other step, so the head of one step overlaps the tail of
+                    # the step before it.  Every step still compresses and decompresses this rank's whole batch.
+                    bc2 = jb.BatchCodec(cfg, n_planes, device=device, flags=bc.flags)
+                    bc2.d_planes.copy_(bc.d_planes)
+                    comp2 = bc2.compress_device()
+                    if comp2.total_bytes() != total_bytes:
+                        raise RuntimeError("second codec disagrees on the stream size")
+                    out2, st2 = bc2.decompress_device(comp2, total_bytes)
+                    jb.check_status(st2)
+                    side.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(side):
+                        bc2.compress_device(); bc2.decompress_device(comp2, total_bytes)
+                    torch.cuda.current_stream().wait_stream(side)
+                    torch.cuda.synchronize()
+                    g_s2 = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g_s2):
+                        comp_s2 = bc2.compress_device()
+                        out_s2, status_s2 = bc2.decompress_device(comp_s2, total_bytes)
+                    g_s2.replay()
+                    torch.cuda.synchronize()
+                    jb.check_status(comp_s2.status); jb.check_status(status_s2)
+                    if not torch.equal(out_s2, out_s):
+                        raise RuntimeError("second codec decodes differently")
+                    s_a, s_b = torch.cuda.Stream(), torch.cuda.Stream()
+
+                    def run_pair(step, _ga=g_s, _gb=g_s2, _sa=s_a, _sb=s_b):
+                        with torch.cuda.stream(_sa if step % 2 == 0 else _sb):
+                            (_ga if step % 2 == 0 else _gb).replay()
+                    two_streams = (s_a, s_b, run_pair)
+                    launch_mode = ("cuda graph (one per step: compress + decompress); steps alternate between two codec "
+                                   "objects on two CUDA streams")
         except Exception as exc:                          # noqa: BLE001 -- report and fall back to direct launches
             launch_mode = "direct (graph capture failed: %s)" % str(exc).splitlines()[0][:120]
-            run_c, run_d = direct_c, direct_d
+            run_c, run_d, run_step, two_streams = direct_c, direct_d, None, None
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
     for step in range(Wm):
         run_c(); run_d()
@@ -358,7 +406,31 @@ def run_ours(args, rank, world, local_rank):
     t_c = sum(e[0].elapsed_time(e[1]) for e in ev) / K           # ms per step, compress part
     t_d = sum(e[1].elapsed_time(e[2]) for e in ev) / K
     t_all = ev[0][0].elapsed_time(ev[-1][2]) / K
-    t_c, t_d, t_all = max_over_ranks(t_c), max_over_ranks(t_d), max_over_ranks(t_all)
+    t_split = t_all
+    if run_step is not None:
+        # the timed region proper: K steps, one graph each; the split above (same kernels, one graph per call)
+        # is kept for the compress / decompress breakdown
+        cur = torch.cuda.current_stream()
+
+        def run_steps(count):
+            if two_streams is None:
+                for step in range(count):
+                    run_step()
+                return
+            s_a, s_b, run_pair = two_streams
+            s_a.wait_stream(cur); s_b.wait_stream(cur)
+            for step in range(count):
+                run_pair(step)
+            cur.wait_stream(s_a); cur.wait_stream(s_b)
+        run_steps(Wm)
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run_steps(K)
+        e1.record()
+        barrier()
+        t_all = e0.elapsed_time(e1) / K
+    t_c, t_d, t_all, t_split = max_over_ranks(t_c), max_over_ranks(t_d), max_over_ranks(t_all), max_over_ranks(t_split)
     comp = state["comp"]
     jb.check_status(comp.status)
 
@@ -467,7 +539,8 @@ def run_ours(args, rank, world, local_rank):
             "steps": K, "warmup": Wm, "ms_per_step": t_all, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
             "compress_mps": mp_total / (t_c * 1e-3), "decompress_mps": mp_total / (t_d * 1e-3),
-            "ms_compress": t_c, "ms_decompress": t_d, "stream_bytes": stream_total,
+            "ms_compress": t_c, "ms_decompress": t_d, "ms_per_step_two_graphs": t_split, "stream_bytes": stream_total,
+            "pdl": bool(args.pdl), "streams": 2 if two_streams is not None else 1,
             "decoder_serial_fallback_streams_rank0": serial_streams, "launch": launch_mode,
             "bytes_per_pixel": stream_total / (N_IMAGES * H * W),
             # achieved = algorithmic bytes of one launch / the fused kernel's own duration (CUDA events recorded by the
@@ -580,6 +653,12 @@ def main():
     ap.add_argument("--images", type=int, default=N_IMAGES, help="batch size (profiling runs use a smaller one)")
     ap.add_argument("--e2e-sub", type=int, default=32, help="sub-batches of the pipelined end-to-end round trip")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels directly instead of replaying CUDA graphs")
+    ap.add_argument("--no-pdl", dest="pdl", action="store_false",
+                    help="launch the kernels without programmatic dependent launch (JB_FLAG_PDL is the default)")
+    ap.add_argument("--call-graphs", dest="step_graph", action="store_false",
+                    help="time one CUDA graph per library call instead of one per step (compress + decompress)")
+    ap.add_argument("--streams", type=int, default=2, choices=[1, 2],
+                    help="2: consecutive steps alternate between two codec objects on two CUDA streams (default); 1: one stream")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
     args = ap.parse_args()

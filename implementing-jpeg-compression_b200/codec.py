@@ -13,6 +13,7 @@ production caller use.  PyTorch is only the buffer carrier (device memory, the
 current stream); every byte of codec work happens in the CUDA kernels.
 """
 import ctypes
+import threading
 
 import numpy as np
 import torch
@@ -107,19 +108,25 @@ class CompressedPlanes:
 
 
 class _Workspace:
-    """Grow-only cache of device scratch buffers, one set per device (the library itself
-    allocates nothing)."""
+    """Grow-only cache of device scratch buffers (the library itself allocates nothing): one buffer per
+    (direction, device, CUDA stream, host thread).  Calls are asynchronous on the current stream and use the
+    workspace until they finish, so two streams -- or two threads -- must never share one; calls queued on the
+    SAME stream run in order and may.  A buffer that is outgrown is handed back to the caching allocator, which
+    keeps it alive for the work already queued on the stream it was allocated on (the one that used it)."""
 
     def __init__(self):
         self._bufs = {}
+        self._lock = threading.Lock()
 
     def get(self, key, nbytes, device):
-        k = (key, device.index)
-        t = self._bufs.get(k)
-        if t is None or t.numel() < nbytes:
-            t = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
-            self._bufs[k] = t
-        return t
+        k = (key, device.index, torch.cuda.current_stream(device).cuda_stream, threading.get_ident())
+        with self._lock:
+            t = self._bufs.get(k)
+            if t is None or t.numel() < nbytes:
+                with torch.cuda.device(device):
+                    t = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+                self._bufs[k] = t
+            return t
 
 
 _workspace = _Workspace()
@@ -130,7 +137,10 @@ def compress_planes(planes, config, flags=0, out=None, ws=None):
 
     ``planes``: uint8 CUDA tensor [n, H, W] (or [H, W]); rows contiguous.  Returns a
     ``CompressedPlanes`` whose buffers stay on the device; the call is asynchronous on the
-    current stream.  Replaces ``compress_band`` applied to each plane in turn."""
+    current stream.  Replaces ``compress_band`` applied to each plane in turn.
+
+    ``ws``: caller-owned scratch (``jb_compress_workspace_bytes``); by default a cached buffer private to the
+    current (device, stream, thread).  A caller that passes its own must not use it from two streams at once."""
     lib = _lib.load()
     if planes.dim() == 2:
         planes = planes.unsqueeze(0)
@@ -459,8 +469,12 @@ class BatchCodec:
         p = self.config.c_params(self.flags)
         need = _lib.load().jb_decompress_workspace_bytes(ctypes.byref(p), int(n_planes), int(in_bytes))
         if self._ws_inv.numel() < need:                    # the layout depends on the stream bytes: grow, rebuild tables
+            old = self._ws_inv
             with torch.cuda.device(self.device):
                 self._ws_inv = torch.empty(int(need) + (int(need) >> 2), dtype=torch.uint8, device=self.device)
+            # work queued on the current stream may still be using the old buffer: keep the allocator from
+            # recycling it before that work is done
+            old.record_stream(torch.cuda.current_stream(self.device))
             self._tables_inv = False
         fl = self.flags | (_lib.JB_FLAG_REUSE_TABLES if self._tables_inv else 0)
         res = decompress_planes(data, offsets, lengths, self.config, n_planes, in_bytes=in_bytes, flags=fl, out=out,
@@ -521,6 +535,8 @@ class BatchCodec:
                     "h_streams": None,
                 }
             rt = self._rt
+            # (allocated on the caller's stream, used on sa / sb: tell the caching allocator)
+            rt["d_work"].record_stream(rt["sa"]); rt["d_work"].record_stream(rt["sb"]); rt["d_back"].record_stream(rt["sb"])
             if self.h_decoded is None:
                 self.h_decoded = torch.empty((self.n_planes, self.h, self.w), dtype=torch.uint8, pin_memory=self.pinned)
             cur = torch.cuda.current_stream()

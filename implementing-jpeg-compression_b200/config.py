@@ -31,6 +31,10 @@ class QuantizationMethod:
             raise BadQuantizationError(error_msg)      # unexpected keyword, as the class call would fail
         self.mode = mode
         self.param = kwargs.get(pname, default) if pname else 0
+        # The kernels take --qkeep / --qdivisor as the integers the CLI produces (compress.py:45-51).  The reference's
+        # quantiser classes would also accept a fractional divisor or a negative keep (Python slice semantics); the
+        # CUDA path does not, and says so here, at construction, rather than at the first call.
+        self.c_param()
 
     def to_json(self):
         d = dict(self.params)
@@ -50,9 +54,13 @@ class QuantizationMethod:
         p = self.param
         if p is None:
             return 0
-        if int(p) != p:
-            raise BadQuantizationError("name {}, params {}: the CUDA path takes integer parameters"
-                                       .format(self.name, self.params))
+        try:
+            integral = int(p) == p
+        except (TypeError, ValueError):
+            integral = False
+        if not integral or (self.name == "discard" and int(p) < 0) or (self.name == "divide" and int(p) == 0):
+            raise BadQuantizationError("name {}, params {}: the CUDA path takes integer parameters "
+                                       "(keep >= 0, divisor != 0)".format(self.name, self.params))
         return int(p)
 
 

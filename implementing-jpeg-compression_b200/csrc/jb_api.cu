@@ -53,17 +53,16 @@ extern "C" size_t jb_max_stream_bytes(const jb_params* p, int n_planes) {
 }
 
 // ---- compress ----------------------------------------------------------------------------------
-struct JbFwdWs { size_t ctrl, seg1, seg2, chunk_len, tmp_small, tmp, total; size_t n_seg_words; unsigned chunk_cap; };
+struct JbFwdWs { size_t ctrl, chunk_len, chunk_off, seg_total, tmp_small, tmp, total; unsigned chunk_cap; };
 static JbFwdWs jb_fwd_ws(int d, size_t n_chunks) {
     JbFwdWs w;
     size_t o = jb_align_up(jb_table_layout(d).total, 256);
-    w.chunk_cap = (unsigned)jb_align_up((size_t)JB_CHUNK * jb_max_block_bytes(d * d) + 32, 16);
+    w.chunk_cap = (unsigned)jb_align_up((size_t)jb_chunk_blocks(d) * jb_max_block_bytes(d * d) + 32, 16);
     if (w.chunk_cap < 1024 + 32) w.chunk_cap = 1024 + 32;      // the gather kernel reads 1 KB ahead
     w.ctrl = o;      o += JB_CTRL_BYTES;
-    w.seg1 = o;      o += jb_align_up(2 * ((n_chunks + JB_SEG1 - 1) / JB_SEG1) * 8, 256);     // two sets each
-    w.seg2 = o;      o += jb_align_up(2 * ((n_chunks + JB_SEG2 - 1) / JB_SEG2) * 8, 256);
-    w.n_seg_words = (o - w.seg1) / 8;                          // (the two arrays are adjacent: zeroed as one)
     w.chunk_len = o; o += jb_align_up(n_chunks * 4, 256);
+    w.chunk_off = o; o += jb_align_up(n_chunks * 4, 256);
+    w.seg_total = o; o += jb_align_up(((n_chunks + JB_SCAN_SEG - 1) / JB_SCAN_SEG) * 8, 256);
     w.tmp_small = o; o += jb_align_up(n_chunks * (size_t)JB_SLOT_STRIDE, 256);
     w.tmp = o;       o += jb_align_up(n_chunks * (size_t)w.chunk_cap, 256);
     w.total = o;
@@ -78,7 +77,8 @@ extern "C" size_t jb_compress_workspace_bytes(const jb_params* p, int n_planes) 
 
 extern "C" size_t jb_stage_pack_workspace_bytes(int n_planes, int blocks_per_plane, int dct_size) {
     if (n_planes <= 0 || blocks_per_plane <= 0 || dct_size < 1 || dct_size > JB_MAX_DCT_SIZE) return 0;
-    size_t cpp = ((size_t)blocks_per_plane + JB_CHUNK - 1) / JB_CHUNK;
+    const size_t cb = (size_t)jb_chunk_blocks(dct_size);
+    size_t cpp = ((size_t)blocks_per_plane + cb - 1) / cb;
     return jb_fwd_ws(dct_size, (size_t)n_planes * cpp).total;
 }
 
@@ -109,7 +109,7 @@ static int jb_forward_common(int mode, const uint8_t* d_planes, size_t plane_str
     // together with the tables; every call leaves it clean again.  Two launches per call after the first one:
     // the fused transform kernel and the gather.
     if (!(g.flags & JB_FLAG_REUSE_TABLES))
-        JB_CUDA_TRY(jb_launch_init_ctrl((unsigned*)(ws + w.ctrl), (unsigned long long*)(ws + w.seg1), w.n_seg_words, s));
+        JB_CUDA_TRY(jb_launch_init_ctrl((unsigned*)(ws + w.ctrl), nullptr, 0, s));
 
     JbFwdArgs a;
     memset(&a, 0, sizeof(a));
@@ -121,11 +121,9 @@ static int jb_forward_common(int mode, const uint8_t* d_planes, size_t plane_str
     a.plane_off = (unsigned long long*)d_plane_off;
     a.ctrl = (unsigned*)(ws + w.ctrl);
     a.status_out = (unsigned long long*)d_status;
-    a.n_seg1 = (unsigned)((n_chunks + JB_SEG1 - 1) / JB_SEG1);
-    a.n_seg2 = (unsigned)((n_chunks + JB_SEG2 - 1) / JB_SEG2);
     a.chunk_len = (unsigned*)(ws + w.chunk_len);
-    a.seg1 = (unsigned long long*)(ws + w.seg1);
-    a.seg2 = (unsigned long long*)(ws + w.seg2);
+    a.chunk_off = (unsigned*)(ws + w.chunk_off);
+    a.seg_total = (unsigned long long*)(ws + w.seg_total);
     a.tmp = (uint8_t*)(ws + w.tmp);
     a.tmp_small = (uint8_t*)(ws + w.tmp_small);
     a.chunk_cap = w.chunk_cap;
@@ -134,8 +132,8 @@ static int jb_forward_common(int mode, const uint8_t* d_planes, size_t plane_str
     if (mode == 0) jb_prof_mark(0, s);                 // (the matching end mark sits in jb_launch_scan_gather)
     if (mode != 2 && !(g.flags & JB_FLAG_FORCE_GENERIC) && jb_fwd_fast_eligible(g))
         JB_CUDA_TRY(jb_launch_fwd_fast(a, mode, s));
-    else if (mode != 2 && !(g.flags & JB_FLAG_FORCE_GENERIC) && jb_fwd_mid_eligible(g))
-        JB_CUDA_TRY(jb_launch_fwd_mid(a, mode, s));
+    else if (mode != 2 && !(g.flags & JB_FLAG_FORCE_GENERIC) && jb_fwd_large_eligible(g))
+        JB_CUDA_TRY(jb_launch_fwd_large(a, mode, s));
     else
         JB_CUDA_TRY(jb_launch_fwd_generic(a, mode, s));
     if (mode == 1) JB_CUDA_TRY(jb_launch_finish(a, s));      // (modes 0 and 2 end with the gather, which does this)
@@ -177,7 +175,8 @@ extern "C" int jb_stage_pack(const int32_t* d_coeffs, int n_planes, int blocks_p
     memset(&g, 0, sizeof(g));
     g.d = dct_size; g.n = dct_size * dct_size; g.nblocks = blocks_per_plane;
     g.maxblk = jb_max_block_bytes(g.n);
-    g.cpp = (blocks_per_plane + JB_CHUNK - 1) / JB_CHUNK;
+    g.chunk = jb_chunk_blocks(dct_size);
+    g.cpp = (blocks_per_plane + g.chunk - 1) / g.chunk;
     g.bs = 1;
     return jb_forward_common(2, nullptr, 0, 0, n_planes, g, d_out, out_cap, d_plane_off, d_status, nullptr,
                              d_coeffs, d_ws, ws_bytes, (cudaStream_t)stream);
@@ -240,19 +239,28 @@ static int jb_inverse_common(int mode, const uint8_t* d_in, size_t in_bytes, con
     a.n_planes = n_planes; a.n_chunks = (unsigned)n_chunks;
     a.planes_out = d_planes_out; a.plane_stride = plane_stride; a.row_pitch = row_pitch;
     a.coeffs_out = d_coeffs_out; a.coeffs_in = d_coeffs_in;
-    a.status = (unsigned long long*)d_status;
+    a.status = (unsigned long long*)d_status;          // (mode 2: no framing, no control block: errors go straight out)
 
     if (mode != 2) {
         JbDecLayout L = jb_dec_layout(g.d, n_planes, g.nblocks, in_bytes, table_bytes);
         if (ws_bytes < L.total) return JB_ERR_WORKSPACE;
+        // control block protocol (jb_common.cuh): clean when the call starts, left clean by its last kernel
+        unsigned* ctrl = (unsigned*)(ws + L.ctrl);
+        if (!(g.flags & JB_FLAG_REUSE_TABLES)) JB_CUDA_TRY(jb_launch_init_ctrl(ctrl, nullptr, 0, s));
+        a.status = (unsigned long long*)(ws + L.ctrl + JB_CTRL_STATUS_OFF);
+        a.status_out = (unsigned long long*)d_status;
+        a.ticket = ctrl;
+        a.done = ctrl + 1;
         JbFrameArgs f;
         memset(&f, 0, sizeof(f));
         f.in = d_in;
+        f.in_bytes = in_bytes;
         f.plane_off = (const unsigned long long*)d_plane_off;
         f.plane_len = (const unsigned long long*)d_plane_len;
         f.n_planes = n_planes; f.n = g.n; f.nblocks = g.nblocks; f.maxblk = g.maxblk;
         f.max_tiles = L.max_tiles; f.tile_bytes = L.tile_bytes;
         f.force_serial = (g.flags & JB_FLAG_SERIAL_FRAMING) ? 1 : 0;
+        f.pdl = (g.flags & JB_FLAG_PDL) ? 1 : 0;
         f.tile_first = (unsigned*)(ws + L.tile_first);
         f.fallback = (unsigned*)(ws + L.fallback);
         f.big_list = (unsigned*)(ws + L.big_list);
@@ -264,29 +272,33 @@ static int jb_inverse_common(int mode, const uint8_t* d_in, size_t in_bytes, con
         f.tile_hops = (unsigned*)(ws + L.tile_hops);
         f.tile_base = (unsigned*)(ws + L.tile_base);
         f.vbits = (uint32_t*)(ws + L.vbits);
-        f.ticket = (unsigned*)(ws + L.ticket);
         f.warp_first = (unsigned*)(ws + L.warp_first);
         f.warp_stream = (unsigned*)(ws + L.warp_stream);
-        f.status = (unsigned long long*)d_status;
+        f.status = a.status;
         // (a stream that fails framing leaves its part of block_start unwritten; the call then reports
         // JB_ERR_BAD_STREAM and the transform kernels check every offset they read against the stream bounds)
         JB_CUDA_TRY(jb_launch_framing(f, s));
         a.in = d_in; a.in_bytes = in_bytes;
         a.plane_off = f.plane_off; a.plane_len = f.plane_len;
         a.block_start = f.block_start;
-        a.ticket = f.ticket;
     } else if (ws_bytes < table_bytes) {
         return JB_ERR_WORKSPACE;
     }
     if (mode != 1 && !(g.flags & JB_FLAG_REUSE_TABLES)) JB_CUDA_TRY(jb_launch_build_tables(g, a.t, s));
     if (mode == 0) jb_prof_mark(2, s);
-    if (mode != 1 && !(g.flags & JB_FLAG_FORCE_GENERIC) && jb_inv_fast_eligible(g))
-        JB_CUDA_TRY(jb_launch_inv_fast(a, mode, s));
-    else if (mode != 1 && !(g.flags & JB_FLAG_FORCE_GENERIC) && jb_inv_mid_eligible(g))
-        JB_CUDA_TRY(jb_launch_inv_mid(a, mode, s));
-    else
-        JB_CUDA_TRY(jb_launch_inv_generic(a, mode, s));
-    if (mode == 0) jb_prof_mark(3, s);
+    if (mode != 1 && !(g.flags & JB_FLAG_FORCE_GENERIC) && jb_inv_fast_eligible(g)) {
+        JB_CUDA_TRY(jb_launch_inv_fast(a, mode, s));      // (publishes the status and cleans the control block itself)
+        if (mode == 0) jb_prof_mark(3, s);
+    } else if (mode != 1 && !(g.flags & JB_FLAG_FORCE_GENERIC) && jb_inv_large_eligible(g)) {
+        JB_CUDA_TRY(jb_launch_inv_large(a, mode, s));     // (likewise)
+        if (mode == 0) jb_prof_mark(3, s);
+    } else {
+        {
+            JB_CUDA_TRY(jb_launch_inv_generic(a, mode, s));
+        }
+        if (mode == 0) jb_prof_mark(3, s);
+        if (a.status_out) JB_CUDA_TRY(jb_launch_dec_finish(a, s));
+    }
     return JB_OK;
 }
 
@@ -304,7 +316,7 @@ extern "C" int jb_decompress_planes(const uint8_t* d_in, size_t in_bytes, const 
 }
 
 extern "C" int jb_stage_unpack(const uint8_t* d_in, size_t in_bytes, const uint64_t* d_plane_off,
-                               const uint64_t* d_plane_len, int n_planes, int blocks_per_plane, int dct_size,
+                               const uint64_t* d_plane_len, int n_planes, int blocks_per_plane, int dct_size, int flags,
                                int16_t* d_coeffs, uint64_t* d_status, void* d_ws, size_t ws_bytes, void* stream) {
     if (!d_in || !d_plane_off || !d_plane_len || !d_coeffs || !d_status || n_planes <= 0 || blocks_per_plane <= 0)
         return JB_ERR_BAD_PARAM;
@@ -314,8 +326,10 @@ extern "C" int jb_stage_unpack(const uint8_t* d_in, size_t in_bytes, const uint6
     memset(&g, 0, sizeof(g));
     g.d = dct_size; g.n = dct_size * dct_size; g.nblocks = blocks_per_plane;
     g.maxblk = jb_max_block_bytes(g.n);
-    g.cpp = (blocks_per_plane + JB_CHUNK - 1) / JB_CHUNK;
+    g.chunk = jb_chunk_blocks(dct_size);
+    g.cpp = (blocks_per_plane + g.chunk - 1) / g.chunk;
     g.bs = 1;
+    g.flags = flags & JB_FLAG_SERIAL_FRAMING;
     return jb_inverse_common(1, d_in, in_bytes, d_plane_off, d_plane_len, n_planes, g, nullptr, 0, 0, d_coeffs,
                              nullptr, d_status, d_ws, ws_bytes, (cudaStream_t)stream);
 }

@@ -2,11 +2,15 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/jpegb200.h"
 #include "jb_bits.h"
 
 #define JB_CHUNK 32            // blocks per chunk: one RLE/entropy thread per block, one warp per chunk
+#define JB_CHUNK_LARGE 8       // ... for dct_size >= 16, where a block is hundreds of coefficients and a chunk of 32
+                               // would be megabytes of pixels per scheduling unit (a 4K frame: 54 units for 148 SMs)
+__host__ __device__ inline int jb_chunk_blocks(int d) { return d >= 16 ? JB_CHUNK_LARGE : JB_CHUNK; }
 
 #define JB_U32_NONE 0xFFFFFFFFu
 #define JB_U16_NONE 0xFFFFu
@@ -21,6 +25,7 @@ struct JbGeom {
     int nblocks;       // vb * hb
     int maxblk;        // worst-case bytes per block
     int cpp;           // chunks per plane
+    int chunk;         // blocks per chunk: jb_chunk_blocks(d)
     int transform, qmode, qparam, flags;
 };
 
@@ -138,6 +143,41 @@ __device__ __forceinline__ unsigned jb_block_excl_scan(unsigned v, unsigned* s_w
     *total = s_warp[32];
     return ex + s_warp[warp];
 }
+
+// Control block of a workspace (256 bytes behind the tables).  Compress: see jb_forward.cuh.  Decompress:
+//   uint32 [0] chunk ticket of the fused inverse kernel, uint32 [1] its finished CTAs,
+//   uint64 status[JB_STATUS_WORDS] at byte 64: the kernels of a call record errors HERE (atomics);
+// all of it is clean (zero, status[1] all ones) when a call starts, and the call's last kernel copies the status
+// words to the caller's block and leaves it clean again.  A call without JB_FLAG_REUSE_TABLES cleans it first.
+#define JB_CTRL_BYTES 256
+#define JB_CTRL_STATUS_OFF 64
+cudaError_t jb_launch_init_ctrl(unsigned* ctrl, unsigned long long* seg, size_t n_seg_words, cudaStream_t s);
+
+// ---- programmatic dependent launch (JB_FLAG_PDL) ----------------------------------------------------------
+// The kernels of a call, and the calls that follow each other on a stream, are short enough for launch latency
+// and kernel prologues to matter (128 images per rank: ~170 us kernels).  Launched with the programmatic-stream-
+// serialization attribute, a kernel's CTAs become resident while the tail of its predecessor still runs; it does
+// its prologue (shared-memory setup, constant tables) and then waits in jb_pdl_wait() until the predecessor has
+// completed and its writes are visible.  Every kernel of the hot chain triggers its dependents at once and waits
+// before the first access to anything a predecessor may write.  Without the attribute both are no-ops.
+__device__ __forceinline__ void jb_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void jb_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+static inline cudaError_t jb_launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                       bool pdl, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
 
 // Host-side API internals shared between translation units.
 int jb_make_geom(const jb_params* p, JbGeom* g);

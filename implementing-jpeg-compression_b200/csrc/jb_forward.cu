@@ -55,7 +55,7 @@ size_t jb_fwd_generic_smem_bytes(int d, bool dft) { return jb_fwd_smem_layout(d,
 
 // float64 re-evaluation of one coefficient the way the reference computes it (jb_refine.cuh), out of line
 __device__ __noinline__ double jb_refine_coefficient(const int* X, int u, int v, const JbGeom& g, const JbTables& t) {
-    return jb_refine_f64<int>(X, u, v, g.d, g.bs, g.transform, g.qmode, t.fA64, t.fB64, t.qrecip[u * g.d + v]);
+    return jb_refine_f64(X, u, v, g.d, g.bs, g.transform, g.qmode, t.fA64, t.fB64, t.qrecip[u * g.d + v]);
 }
 
 template <int MODE>
@@ -97,8 +97,8 @@ jb_fwd_generic_kernel(const JbFwdArgs a) {
     const int P = s_P;
     if (chunk >= a.n_chunks) return;
     const int plane = chunk / g.cpp;
-    const int blk0 = (chunk % g.cpp) * JB_CHUNK;
-    const int nvalid = jb_min(JB_CHUNK, g.nblocks - blk0);
+    const int blk0 = (chunk % g.cpp) * g.chunk;
+    const int nvalid = jb_min(g.chunk, g.nblocks - blk0);
 
     if (MODE != 2) {
         const uint8_t* src = a.planes + (size_t)plane * a.plane_stride;
@@ -222,127 +222,136 @@ jb_fwd_generic_kernel(const JbFwdArgs a) {
 }
 
 // ----------------------------------------------------------------------------------------------
-// gather: every chunk from its slot to its place in the output stream.  No scan pass: a CTA (8 chunks, one per
-// warp) derives the offset of its first chunk from the two levels of segment totals the transform kernel
-// accumulated and the few chunk lengths in between.  The CTA that finishes last publishes the status words
-// and leaves the control block and the totals zeroed for the next call on this workspace.
+// device-wide exclusive scan of the chunk lengths in ONE launch, then gather
+//   scan:   one CTA per segment of JB_SCAN_SEG chunks: offsets inside the segment + segment total; the CTA
+//           that finishes last scans the segment totals in place (exclusive bases), writes the grand total and
+//           checks the capacity
+//   gather: one warp per chunk: copy slot -> out[base], record the start of every plane; CTA 0 ends the call:
+//           status words out, the other control set cleaned, parity flipped
 // ----------------------------------------------------------------------------------------------
-#define JB_GATHER_WARPS 8
-
-// The call's last kernel: hand the status words of set P to the caller, clean set P ^ 1 for the next call, flip
-// the parity.  `slice` / `n_slices`: which part of the other set's segment totals this CTA zeroes.
-__device__ __forceinline__ void jb_ctrl_finish(const JbFwdArgs& a, int P, bool leader, unsigned slice, unsigned n_slices,
-                                               unsigned long long extra_error) {
-    const int Q = P ^ 1;
-    for (unsigned i = slice; i < a.n_seg1; i += n_slices) a.seg1[(size_t)Q * a.n_seg1 + i] = 0ull;
-    for (unsigned i = slice; i < a.n_seg2; i += n_slices) a.seg2[(size_t)Q * a.n_seg2 + i] = 0ull;
-    if (leader) {
-        const unsigned long long* st = jb_ctrl_status(a, P);
-        unsigned long long* sq = jb_ctrl_status(a, Q);
-        const unsigned long long e0 = st[0];
-        a.status_out[0] = e0 > extra_error ? e0 : extra_error;
-        #pragma unroll
-        for (int k = 1; k < JB_STATUS_WORDS; ++k) a.status_out[k] = st[k];
-        #pragma unroll
-        for (int k = 0; k < JB_STATUS_WORDS; ++k) sq[k] = k == 1 ? ~0ull : 0ull;
-        *jb_ctrl_ticket(a, Q) = 0u;
-        a.ctrl[0] = (unsigned)Q;
+__global__ void __launch_bounds__(JB_SCAN_SEG) jb_scan_kernel(JbFwdArgs a, unsigned n_seg) {
+    __shared__ unsigned s_warp[33];
+    __shared__ unsigned long long s_carry;
+    __shared__ int s_last;
+    jb_pdl_trigger();
+    jb_pdl_wait();
+    const unsigned c = blockIdx.x * JB_SCAN_SEG + threadIdx.x;
+    const unsigned len = c < a.n_chunks ? a.chunk_len[c] : 0u;
+    unsigned total;
+    const unsigned ex = jb_block_excl_scan(len, s_warp, &total);
+    if (c < a.n_chunks) a.chunk_off[c] = ex;
+    if (threadIdx.x == 0) {
+        a.seg_total[blockIdx.x] = total;
+        __threadfence();
+        s_last = atomicAdd(a.ctrl + 4, 1u) == gridDim.x - 1u ? 1 : 0;
+        s_carry = 0ull;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (unsigned base = 0; base < n_seg; base += JB_SCAN_SEG) {
+        const unsigned i = base + threadIdx.x;
+        // segment totals fit 32 bits but their running sum does not: scan the low 20 bits and the rest separately
+        const unsigned long long v = i < n_seg ? __ldcg(a.seg_total + i) : 0ull;
+        unsigned tlo, thi;
+        const unsigned lo = jb_block_excl_scan((unsigned)(v & 0xFFFFFu), s_warp, &tlo);
+        const unsigned hi = jb_block_excl_scan((unsigned)(v >> 20), s_warp, &thi);
+        const unsigned long long carry = s_carry;
+        if (i < n_seg) a.seg_total[i] = carry + (((unsigned long long)hi) << 20) + lo;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + (((unsigned long long)thi) << 20) + tlo;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const int P = (int)(__ldcg(a.ctrl + 1) & 1u);
+        a.plane_off[a.n_planes] = s_carry;
+        if (s_carry > a.out_cap) jb_set_error(jb_ctrl_status(a, P), JB_ERR_OUT_CAPACITY);
+        a.ctrl[4] = 0u;
     }
 }
 
+#define JB_GATHER_WARPS 8
+
+// The call's last kernel: hand the status words of set P to the caller, clean set P ^ 1 for the next call, flip
+// the parity (one thread).
+__device__ __forceinline__ void jb_ctrl_finish(const JbFwdArgs& a, int P) {
+    const int Q = P ^ 1;
+    const unsigned long long* st = jb_ctrl_status(a, P);
+    unsigned long long* sq = jb_ctrl_status(a, Q);
+    #pragma unroll
+    for (int k = 0; k < JB_STATUS_WORDS; ++k) a.status_out[k] = __ldcg(st + k);
+    #pragma unroll
+    for (int k = 0; k < JB_STATUS_WORDS; ++k) sq[k] = k == 1 ? ~0ull : 0ull;
+    *jb_ctrl_ticket(a, Q) = 0u;
+    a.ctrl[0] = (unsigned)Q;
+}
+
 __global__ void __launch_bounds__(JB_GATHER_WARPS * 32) jb_gather_chunks_kernel(JbFwdArgs a) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned c = blockIdx.x * JB_GATHER_WARPS + warp;
-    const int P = (int)(__ldcg(a.ctrl + 1) & 1u);
-    if (c < a.n_chunks) {
-        const uint8_t* src = a.tmp_small + (size_t)c * JB_SLOT_STRIDE;   // 16-byte aligned, 1 KB + 32 B per slot
-        const uint4* s16 = (const uint4*)src;
-        const uint32_t* s32 = (const uint32_t*)src;
-        // the first kilobyte of the slot is fetched before its length is known: the round trips (metadata, data)
-        // overlap; an average chunk is ~0.6 KB
-        uint4 pv[2];
-        uint32_t pn[2];
+    const int lane = threadIdx.x & 31;
+    const unsigned c = blockIdx.x * JB_GATHER_WARPS + (threadIdx.x >> 5);
+    jb_pdl_trigger();
+    jb_pdl_wait();
+    if (blockIdx.x == 0 && threadIdx.x == 0) jb_ctrl_finish(a, (int)(__ldcg(a.ctrl + 1) & 1u));
+    if (c >= a.n_chunks) return;
+    // 16-byte aligned slots: the dense array of 1 KB + 32 B ones, or the worst-case sized ones
+    const uint8_t* src = a.slots_always_big ? a.tmp + (size_t)c * a.chunk_cap : a.tmp_small + (size_t)c * JB_SLOT_STRIDE;
+    const uint4* s16 = (const uint4*)src;
+    const uint32_t* s32 = (const uint32_t*)src;
+    // the first kilobyte of the slot is fetched before its length is known: the two round trips
+    // (metadata, data) overlap; an average chunk is ~0.6 KB
+    uint4 pv[2];
+    uint32_t pn[2];
+    #pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        pv[k] = __ldg(s16 + lane + 32 * k);
+        pn[k] = __ldg(s32 + 4 * (lane + 32 * k) + 4);
+    }
+    const unsigned len = a.chunk_len[c];
+    if (len > JB_SLOT_SMALL && !a.slots_always_big) {          // a dense chunk: it went to the worst-case-sized slot
+        src = a.tmp + (size_t)c * a.chunk_cap;
+        s16 = (const uint4*)src;
+        s32 = (const uint32_t*)src;
         #pragma unroll
         for (int k = 0; k < 2; ++k) {
             pv[k] = __ldg(s16 + lane + 32 * k);
             pn[k] = __ldg(s32 + 4 * (lane + 32 * k) + 4);
         }
-        // ---- offset of the chunk: second-level totals before its second-level segment, first-level totals before
-        //      its first-level segment inside that, chunk lengths before it inside that: at most
-        //      n_chunks / JB_SEG2 + JB_SEG2 / JB_SEG1 + JB_SEG1 values, a few per lane, all of them hot in L2 ----
-        const unsigned long long* seg1 = a.seg1 + (size_t)P * a.n_seg1;
-        const unsigned long long* seg2 = a.seg2 + (size_t)P * a.n_seg2;
-        const unsigned g2 = c / JB_SEG2, g1 = c / JB_SEG1;
-        unsigned long long base = 0ull;
-        for (unsigned i = lane; i < g2; i += 32) base += __ldcg(seg2 + i);
-        for (unsigned i = g2 * (JB_SEG2 / JB_SEG1) + lane; i < g1; i += 32) base += __ldcg(seg1 + i);
-        for (unsigned i = g1 * JB_SEG1 + lane; i < c; i += 32) base += a.chunk_len[i];
-        #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) base += __shfl_xor_sync(0xffffffffu, base, o);
-        const unsigned len = a.chunk_len[c];
-        if (len > JB_SLOT_SMALL) {                             // a dense chunk: it went to the worst-case-sized slot
-            src = a.tmp + (size_t)c * a.chunk_cap;
-            s16 = (const uint4*)src;
-            s32 = (const uint32_t*)src;
-            #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                pv[k] = __ldg(s16 + lane + 32 * k);
-                pn[k] = __ldg(s32 + 4 * (lane + 32 * k) + 4);
-            }
-        }
-        if (lane == 0 && c % (unsigned)a.g.cpp == 0) a.plane_off[c / (unsigned)a.g.cpp] = base;
-        if (base + len <= a.out_cap) {                         // (otherwise flagged by CTA 0 below)
-            uint8_t* dst = a.out + base;
-            // head bytes up to a 4-byte boundary of dst; then every lane moves 16 bytes per pass: one
-            // 128-bit load + the following word, funnel-shifted into four aligned words; then the tail
-            const unsigned head = (unsigned)jb_min((int)len, (int)((4u - (unsigned)((uintptr_t)dst & 3u)) & 3u));
-            if (lane < (int)head) dst[lane] = src[lane];
-            const unsigned nwords = (len - head) >> 2;
-            uint32_t* d32 = (uint32_t*)(dst + head);
-            const unsigned sh = head * 8u;
-            unsigned pass = 0;
-            for (unsigned j = lane; j * 4u < nwords; j += 32, ++pass) {
-                uint4 v;
-                uint32_t nx;
-                if (pass == 0) { v = pv[0]; nx = pn[0]; }
-                else if (pass == 1) { v = pv[1]; nx = pn[1]; }
-                else { v = __ldg(s16 + j); nx = __ldg(s32 + 4u * j + 4u); }
-                uint32_t w0 = v.x, w1 = v.y, w2 = v.z, w3 = v.w;
-                if (sh) {
-                    w0 = __funnelshift_r(v.x, v.y, sh); w1 = __funnelshift_r(v.y, v.z, sh);
-                    w2 = __funnelshift_r(v.z, v.w, sh); w3 = __funnelshift_r(v.w, nx, sh);
-                }
-                const unsigned w = 4u * j;
-                d32[w] = w0;
-                if (w + 1 < nwords) d32[w + 1] = w1;
-                if (w + 2 < nwords) d32[w + 2] = w2;
-                if (w + 3 < nwords) d32[w + 3] = w3;
-            }
-            const unsigned tail0 = head + nwords * 4u;
-            if (tail0 + lane < len) dst[tail0 + lane] = src[tail0 + lane];
-        }
     }
-    // ---- end of the call: grand total and capacity check (CTA 0), status out, the other set cleaned ----
-    if (warp == 0) {
-        unsigned long long err = 0ull;
-        if (blockIdx.x == 0) {
-            const unsigned long long* seg2 = a.seg2 + (size_t)P * a.n_seg2;
-            unsigned long long tot = 0ull;
-            for (unsigned i = lane; i < a.n_seg2; i += 32) tot += __ldcg(seg2 + i);
-            #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-            if (lane == 0) a.plane_off[a.n_planes] = tot;
-            if (tot > a.out_cap) err = (unsigned long long)(-JB_ERR_OUT_CAPACITY);
+    const unsigned long long base = a.seg_total[c / JB_SCAN_SEG] + a.chunk_off[c];
+    if (lane == 0 && c % (unsigned)a.g.cpp == 0) a.plane_off[c / (unsigned)a.g.cpp] = base;
+    if (base + len > a.out_cap) return;                       // flagged by the scan kernel
+    uint8_t* dst = a.out + base;
+    // head bytes up to a 4-byte boundary of dst; then every lane moves 16 bytes per pass: one
+    // 128-bit load + the following word, funnel-shifted into four aligned words; then the tail
+    const unsigned head = (unsigned)jb_min((int)len, (int)((4u - (unsigned)((uintptr_t)dst & 3u)) & 3u));
+    if (lane < (int)head) dst[lane] = src[lane];
+    const unsigned nwords = (len - head) >> 2;
+    uint32_t* d32 = (uint32_t*)(dst + head);
+    const unsigned sh = head * 8u;
+    unsigned pass = 0;
+    for (unsigned j = lane; j * 4u < nwords; j += 32, ++pass) {
+        uint4 v;
+        uint32_t nx;
+        if (pass == 0) { v = pv[0]; nx = pn[0]; }
+        else if (pass == 1) { v = pv[1]; nx = pn[1]; }
+        else { v = __ldg(s16 + j); nx = __ldg(s32 + 4u * j + 4u); }
+        uint32_t w0 = v.x, w1 = v.y, w2 = v.z, w3 = v.w;
+        if (sh) {
+            w0 = __funnelshift_r(v.x, v.y, sh); w1 = __funnelshift_r(v.y, v.z, sh);
+            w2 = __funnelshift_r(v.z, v.w, sh); w3 = __funnelshift_r(v.w, nx, sh);
         }
-        if (lane == 0) jb_ctrl_finish(a, P, blockIdx.x == 0, blockIdx.x, gridDim.x, err);
+        const unsigned w = 4u * j;
+        d32[w] = w0;
+        if (w + 1 < nwords) d32[w + 1] = w1;
+        if (w + 2 < nwords) d32[w + 2] = w2;
+        if (w + 3 < nwords) d32[w + 3] = w3;
     }
+    const unsigned tail0 = head + nwords * 4u;
+    if (tail0 + lane < len) dst[tail0 + lane] = src[tail0 + lane];
 }
 
 // calls that end without a gather pass (stage entry point: coefficients only)
-__global__ void __launch_bounds__(256) jb_finish_kernel(JbFwdArgs a) {
-    const int P = (int)(__ldcg(a.ctrl + 1) & 1u);
-    jb_ctrl_finish(a, P, threadIdx.x == 0, threadIdx.x, blockDim.x, 0ull);
-}
+__global__ void jb_finish_kernel(JbFwdArgs a) { jb_ctrl_finish(a, (int)(__ldcg(a.ctrl + 1) & 1u)); }
 
 __global__ void __launch_bounds__(256) jb_init_ctrl_kernel(unsigned* ctrl, unsigned long long* seg, size_t n_seg_words) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -367,12 +376,16 @@ cudaError_t jb_launch_init_ctrl(unsigned* ctrl, unsigned long long* seg, size_t 
 cudaError_t jb_launch_gather(const JbFwdArgs& a, cudaStream_t s) {
     jb_prof_mark(1, s);                                // the fused forward kernel was launched just before
     if (a.n_chunks == 0) return jb_launch_finish(a, s);
-    jb_gather_chunks_kernel<<<(a.n_chunks + JB_GATHER_WARPS - 1) / JB_GATHER_WARPS, JB_GATHER_WARPS * 32, 0, s>>>(a);
-    return cudaGetLastError();
+    const bool pdl = (a.g.flags & JB_FLAG_PDL) != 0;
+    const unsigned n_seg = (a.n_chunks + JB_SCAN_SEG - 1) / JB_SCAN_SEG;
+    cudaError_t e = jb_launch_ex(jb_scan_kernel, dim3(n_seg), dim3(JB_SCAN_SEG), 0, s, pdl, a, n_seg);
+    if (e != cudaSuccess) return e;
+    return jb_launch_ex(jb_gather_chunks_kernel, dim3((a.n_chunks + JB_GATHER_WARPS - 1) / JB_GATHER_WARPS),
+                        dim3(JB_GATHER_WARPS * 32), 0, s, pdl, a);
 }
 
 cudaError_t jb_launch_finish(const JbFwdArgs& a, cudaStream_t s) {
-    jb_finish_kernel<<<1, 256, 0, s>>>(a);
+    jb_finish_kernel<<<1, 1, 0, s>>>(a);
     return cudaGetLastError();
 }
 

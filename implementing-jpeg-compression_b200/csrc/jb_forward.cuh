@@ -24,31 +24,26 @@ struct JbFwdArgs {
                                       // gather pass then reads ~1 KB strides instead of worst-case-sized ones)
     unsigned chunk_cap;               // bytes reserved per chunk in tmp (multiple of 16)
     unsigned* chunk_len;              // n_chunks: packed bytes of each chunk
-    unsigned long long* seg1;         // [2][n_seg1] bytes per JB_SEG1 chunks, accumulated by the transform kernel
-    unsigned long long* seg2;         // [2][n_seg2] bytes per JB_SEG2 chunks, likewise
-    unsigned n_seg1, n_seg2;
+    unsigned* chunk_off;              // n_chunks: offset of the chunk inside its scan segment
+    unsigned long long* seg_total;    // per scan segment (JB_SCAN_SEG chunks): bytes, then exclusive base
+    int slots_always_big;             // every chunk was staged in `tmp` (large-block kernel), none in `tmp_small`
     int16_t* coeffs_out;              // MODE 1
     const int32_t* coeffs_in;         // MODE 2
 };
 
-// Stream offsets without a scan pass: the transform kernels add every chunk's byte count to two levels of
-// segment totals (atomics); a gather CTA then sums at most n_chunks / JB_SEG2 + JB_SEG2 / JB_SEG1 + JB_SEG1 values.
-#define JB_SEG1 64                  // chunks per first-level segment (a multiple of the chunks per gather CTA)
-#define JB_SEG2 4096                // chunks per second-level segment (a multiple of JB_SEG1)
+#define JB_SCAN_SEG 1024            // chunks per scan segment (one CTA of the scan kernel)
 
 // Control block of the compress workspace (256 bytes behind the tables): two sets of {chunk ticket, status
-// words, segment totals}, used alternately.
+// words}, used alternately.
 //   uint32 [0] parity P: the set this call uses (read by the transform kernel; stable while it runs)
-//   uint32 [1] the same P, left by the transform kernel for the call's last kernel
+//   uint32 [1] the same P, left by the transform kernel for the kernels behind it
 //   uint32 [2 + P] chunk ticket of set P
+//   uint32 [4] finished CTAs of the scan kernel (reset by its last CTA)
 //   uint64 status[P][JB_STATUS_WORDS] at byte 64 + 32 P
-// A call works on set P, which is clean when it starts (ticket 0, status {0, ~0, 0, 0}, totals 0).  Its last
-// kernel (gather, or jb_finish_kernel) copies status[P] to the caller's block, cleans set P ^ 1 -- last used by
-// the call before, so nobody reads it now -- and flips [0].  No memset node, no "last CTA" counter: a call is the
-// transform kernel and the gather.  jb_init_ctrl_kernel (calls without JB_FLAG_REUSE_TABLES) cleans both sets.
-#define JB_CTRL_BYTES 256
-#define JB_CTRL_STATUS_OFF 64
-
+// A call works on set P, which is clean when it starts (ticket 0, status {0, ~0, 0, 0}).  Its last kernel (gather,
+// or jb_finish_kernel) copies status[P] to the caller's block, cleans set P ^ 1 -- last used by the call before, so
+// nobody reads it now -- and flips [0].  No memset / init node: a call is the transform kernel, one scan kernel and
+// the gather.  jb_init_ctrl_kernel (calls without JB_FLAG_REUSE_TABLES) cleans both sets.
 __device__ __forceinline__ int jb_ctrl_parity(const JbFwdArgs& a) { return (int)(__ldcg(a.ctrl) & 1u); }
 __device__ __forceinline__ unsigned* jb_ctrl_ticket(const JbFwdArgs& a, int P) { return a.ctrl + 2 + P; }
 __device__ __forceinline__ unsigned long long* jb_ctrl_status(const JbFwdArgs& a, int P) {
@@ -60,24 +55,22 @@ __device__ __forceinline__ void jb_ctrl_note_first(const JbFwdArgs& a, int P, un
 }
 
 __device__ __forceinline__ void jb_record_chunk_len(const JbFwdArgs& a, int P, unsigned chunk, unsigned total) {
+    (void)P;
     a.chunk_len[chunk] = total;
-    atomicAdd(a.seg1 + (size_t)P * a.n_seg1 + chunk / JB_SEG1, (unsigned long long)total);
-    atomicAdd(a.seg2 + (size_t)P * a.n_seg2 + chunk / JB_SEG2, (unsigned long long)total);
 }
 
 size_t jb_fwd_generic_smem_bytes(int d, bool dft);
-// gather of the chunks into the output stream (computes every chunk's offset from the segment totals), then
-// publication of the status words and clean-up of the control block
+// device-wide exclusive scan of the chunk lengths (one launch) + gather of the chunks into the output stream, which
+// also publishes the status words and cleans the control block
 cudaError_t jb_launch_gather(const JbFwdArgs& a, cudaStream_t s);
 // the same publication / clean-up for calls that end without a gather pass (stage entry point: coefficients only)
 cudaError_t jb_launch_finish(const JbFwdArgs& a, cudaStream_t s);
-// cleans both sets of the control block and the segment totals (calls without JB_FLAG_REUSE_TABLES)
-cudaError_t jb_launch_init_ctrl(unsigned* ctrl, unsigned long long* seg, size_t n_seg_words, cudaStream_t s);
+
 cudaError_t jb_launch_fwd_generic(const JbFwdArgs& a, int mode, cudaStream_t s);
 
-// large-block path: dct_size a multiple of 4, source tile in shared memory (jb_forward_mid.cu)
-bool jb_fwd_mid_eligible(const JbGeom& g);
-cudaError_t jb_launch_fwd_mid(const JbFwdArgs& a, int mode, cudaStream_t s);
+// large-block path: DCT, dct_size 16 / 24 / 32, tile rows of at most 128 bytes (jb_forward_large.cu)
+bool jb_fwd_large_eligible(const JbGeom& g);
+cudaError_t jb_launch_fwd_large(const JbFwdArgs& a, int mode, cudaStream_t s);
 
 // specialised path: dct_size 8, block_size 4 (jb_forward_fast.cu)
 bool jb_fwd_fast_eligible(const JbGeom& g);

@@ -53,7 +53,7 @@ struct FfCtaSmem {
 // with few operands: the fused kernel pays nothing for it in registers.
 template <bool DFT>
 __device__ __noinline__ double ff_refine8(const float* X, int u, int v, const FfCtaSmem& cs, int qmode, double recip) {
-    return jb_refine_f64<float>(X, u, v, 8, 4, DFT ? JB_TRANSFORM_DFT : JB_TRANSFORM_DCT, qmode, cs.A64, cs.B64, recip);
+    return jb_refine_f64(X, u, v, 8, 4, DFT ? JB_TRANSFORM_DFT : JB_TRANSFORM_DCT, qmode, cs.A64, cs.B64, recip);
 }
 
 // ---- tile staging -----------------------------------------------------------------------------
@@ -182,6 +182,10 @@ jb_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfKernelArgs 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     FfCtaSmem& cs = *(FfCtaSmem*)smem_raw;
     FfWarpSmem& ws = *(FfWarpSmem*)(smem_raw + 1024 + (size_t)warp * sizeof(FfWarpSmem));
+    jb_pdl_trigger();
+    // the tables are constant once built (JB_FLAG_REUSE_TABLES): their loads may overlap the kernel before this one
+    const bool tables_const = (g.flags & JB_FLAG_REUSE_TABLES) != 0;
+    if (!tables_const) jb_pdl_wait();
 
     for (int i = threadIdx.x; i < 64; i += blockDim.x) { cs.A64[i] = a.t.fA64[i]; cs.B64[i] = a.t.fB64[i]; }
     if (lane == 0) {
@@ -219,6 +223,7 @@ jb_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfKernelArgs 
     const bool aligned = ka.aligned != 0;
     const bool use_tma = ka.use_tma != 0;
 
+    if (tables_const) jb_pdl_wait();                           // from here on: data the kernels before this one wrote
     const int P = jb_ctrl_parity(a);                           // which set of the control block this call uses
     unsigned* const ticket = jb_ctrl_ticket(a, P);
     auto claim = [&]() -> unsigned {
@@ -521,8 +526,8 @@ static cudaError_t jb_fwd_fast_launch_t(const CUtensorMap& map, const FfKernelAr
     unsigned want = (ka.a.n_chunks + FF_WARPS - 1) / FF_WARPS;
     unsigned grid = want < (unsigned)(sms * per_sm) ? want : (unsigned)(sms * per_sm);
     if (grid == 0) return cudaSuccess;
-    jb_fwd_fast_kernel<DFT, MODE><<<grid, FF_WARPS * 32, smem, s>>>(map, ka);
-    return cudaGetLastError();
+    return jb_launch_ex(jb_fwd_fast_kernel<DFT, MODE>, dim3(grid), dim3(FF_WARPS * 32), smem, s,
+                        (ka.a.g.flags & JB_FLAG_PDL) != 0, map, ka);
 }
 
 cudaError_t jb_launch_fwd_fast(const JbFwdArgs& a, int mode, cudaStream_t s) {

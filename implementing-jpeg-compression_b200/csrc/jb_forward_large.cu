@@ -1,0 +1,541 @@
+// jb_forward_large.cu -- compress direction for large blocks: DCT, dct_size 16 / 24 / 32, source tile rows of at
+// most 128 bytes (BASELINE.json config 3: --block_size 5 --dct_size 24 --quantization divide --qdivisor 1000).
+//
+// Work unit: a chunk of JB_CHUNK_LARGE = 8 consecutive blocks of one plane, claimed from the ticket counter by a
+// WARP of a persistent grid (one CTA of FL_WARPS warps per SM); the warp takes its blocks through every stage on
+// its own, so nothing in the kernel is CTA-wide after the table preload:
+//   * the (d bs) x (d bs) source tile of a block arrives in the warp's shared-memory slot by TMA (one elected lane,
+//     box 128 bytes x d bs rows, mbarrier completion); the load of the NEXT block is issued as soon as the box sums
+//     have consumed the tile, so it overlaps the arithmetic.  Edge blocks (padding.py:8-12, dct_padding.py:8-9
+//     replicate, TMA would zero-fill) and unaligned planes are filled by the warp with clamped loads;
+//   * box sums (subsampling.py:9-11 without the division): lane j sums the bs x bs bytes of sample (i, j) with
+//     __dp4a under byte masks, row i by row i; the sums of columns j and d-1-j meet in one lane, which stores
+//     Xe = S[j] + S[d-1-j] and Xo = S[j] - S[d-1-j] (exact integers);
+//   * C.X.C^T (transforms.py:46-58) as two half-length contractions: the DCT-II matrix is (anti)symmetric,
+//     C[k][d-1-j] = (-1)^k C[k][j], so even frequencies see only Xe and odd ones only Xo -- d/2 instead of d
+//     multiply-adds per output.  Lane (rg, kg) owns a (d/8) x (d/4) register tile of outputs; operands come from
+//     shared memory as 128-bit rows (bank-conflict free for d = 24); the column pass gets its even / odd sums of
+//     the row-pass results by one lane exchange (__shfl_xor 28) and a trip through shared memory.
+//     fp32 on exact integers; a coefficient within the proven fp32 error bound of a rounding tie is re-evaluated in
+//     fp64 in the reference's order (jb_refine.cuh) -- the bound of jb_tables.cu covers the half-length sums too
+//     (|Xe|, |Xo| <= 2 M, half as many terms);
+//   * quantise, zigzag (int16 row in shared memory), non-zero bitmap by warp ballots;
+//   * run-length code + bit packing by the whole warp (util.py:146-160, 203-221): lane w owns the 32 zigzag positions
+//     of bitmap word w, a warp scan of the code lengths gives every lane its bit offset, the codes are OR-ed into the
+//     block's bytes in shared memory; the bytes go straight to the chunk's slot (blocks of a chunk are produced
+//     in order by one warp, so the slot is compact), and the gather pass of jb_forward.cu places the chunks.
+// No tensor-core variant: after the half-length trick the contraction is ~1 MAC per source byte; ncu
+// (profiles/) shows the FMA pipe far from saturated -- SURVEY.md section 7.2.
+#include <cuda.h>
+#include <string.h>
+
+#include "jb_common.cuh"
+#include "jb_fast_common.cuh"
+#include "jb_forward.cuh"
+#include "jb_refine.cuh"
+
+#define FL_WARPS 9
+#define FL_BLOCK_BUF_WORDS 96          // 384 bytes of packed output per block in shared memory; longer blocks: serial path
+#define FL_TILE_ROW 128                // bytes per tile row in shared memory (= TMA box width)
+#define FL_BIG_CAP 8                   // amplitudes beyond the 15-bit size field remembered per block (for the error report)
+
+struct FlLayout {
+    int h;                  // d / 2
+    int xs;                 // floats per row of Xe / Xo (and of the half matrix)
+    int ts;                 // floats per row of Te / To
+    size_t ch, qm, thr, zz;                         // CTA-wide tables
+    size_t warp0, tile, xe, te, crow, obuf, big, bar, warp_bytes, total;
+};
+
+__host__ __device__ inline FlLayout fl_layout(int d, int side) {
+    FlLayout L;
+    const int n = d * d;
+    L.h = d / 2;
+    L.xs = L.h;                                     // 12 floats = 48 bytes: 16-byte aligned rows, conflict-free for d = 24
+    L.ts = d;
+    size_t o = 0;
+    L.ch = o;   o += jb_align_up((size_t)d * L.xs * 4, 16);       // CH[row(k)][j < h]
+    L.qm = o;   o += (size_t)n * 4;
+    L.thr = o;  o += (size_t)n * 4;
+    L.zz = o;   o += jb_align_up((size_t)n * 2, 16);
+    L.warp0 = jb_align_up(o, 128);
+    size_t w = 0;
+    L.tile = w; w += jb_align_up((size_t)side * FL_TILE_ROW, 128);
+    L.xe = w;   w += jb_align_up((size_t)2 * d * L.xs * 4, 16);   // Xe rows, then Xo rows
+    L.te = w;   w += jb_align_up((size_t)2 * L.h * L.ts * 4, 16); // Te rows (j < h), then To rows
+    L.crow = w; w += jb_align_up((size_t)n * 2, 16);
+    L.obuf = w; w += (size_t)(FL_BLOCK_BUF_WORDS + 2) * 4;
+    L.big = w;  w += (size_t)(1 + 2 * FL_BIG_CAP) * 4;
+    w = jb_align_up(w, 16);
+    L.bar = w;  w += 16;
+    L.warp_bytes = jb_align_up(w, 128);
+    L.total = L.warp0 + (size_t)FL_WARPS * L.warp_bytes;
+    return L;
+}
+
+bool jb_fwd_large_eligible(const JbGeom& g) {
+    if (g.transform != JB_TRANSFORM_DCT) return false;
+    if (g.d != 16 && g.d != 24 && g.d != 32) return false;
+    const int side = g.d * g.bs;
+    return side <= 128 && fl_layout(g.d, side).total <= 227 * 1024;
+}
+
+struct FlKernelArgs {
+    JbFwdArgs a;
+    int use_tma;        // tensor map valid (aligned planes at least one tile large)
+};
+
+// fp64 re-evaluation (jb_refine.cuh) from the even / odd sums: X[i][j] = (Xe + Xo) / 2, X[i][d-1-j] = (Xe - Xo) / 2
+struct FlBoxSums {
+    const float* xe;
+    const float* xo;
+    int d, h, xs;
+    __device__ __forceinline__ float operator[](int idx) const {
+        const int i = idx / d, j = idx - i * d;
+        const int jj = j < h ? j : d - 1 - j;
+        const float e = xe[i * xs + jj], o = xo[i * xs + jj];
+        return (j < h ? e + o : e - o) * 0.5f;
+    }
+};
+
+template <int D>
+__device__ __noinline__ double fl_refine(const float* xe, int uv, int bs_qmode, const double* A64, double recip) {
+    FlBoxSums X = {xe, xe + D * (D / 2), D, D / 2, D / 2};
+    return jb_refine_f64(X, uv / D, uv % D, D, bs_qmode >> 8, JB_TRANSFORM_DCT, bs_qmode & 255, A64, A64, recip);
+}
+
+// serial packing of one block straight to global memory (blocks longer than the shared-memory buffer)
+__device__ __noinline__ unsigned fl_pack_serial(const int16_t* c, const uint32_t* mask, int mask_words, uint8_t* dst) {
+    JbByteWriter bw;
+    bw.init(dst);
+    int prev = -1;
+    for (int wi = 0; wi < mask_words; ++wi) {
+        uint32_t m = mask[wi];
+        while (m) {
+            const int p = wi * 32 + __ffs((int)m) - 1;
+            m &= m - 1;
+            const int amp = c[p];
+            jb_put_coefficient(bw, p - prev - 1, amp);          // (amplitudes that do not fit were reported already)
+            prev = p;
+        }
+    }
+    bw.put(0u, 8);
+    return bw.finish();
+}
+
+template <int D, int MODE>
+__global__ void __launch_bounds__(FL_WARPS * 32, 1)
+jb_fwd_large_kernel(const __grid_constant__ CUtensorMap tmap, const FlKernelArgs ka) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const JbFwdArgs& a = ka.a;
+    const JbGeom& g = a.g;
+    constexpr int n = D * D, H = D / 2, RT = D / 8, KT = D / 4, NW = n / 32;
+    const int bs = g.bs, side = D * bs;
+    const FlLayout L = fl_layout(D, side);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* sCH = (float*)(smem + L.ch);
+    float* sQm = (float*)(smem + L.qm);
+    float* sThr = (float*)(smem + L.thr);
+    uint16_t* sZz = (uint16_t*)(smem + L.zz);
+    unsigned char* wbase = smem + L.warp0 + (size_t)warp * L.warp_bytes;
+    uint8_t* tile = wbase + L.tile;
+    float* sXe = (float*)(wbase + L.xe);
+    float* sXo = sXe + D * L.xs;
+    float* sTe = (float*)(wbase + L.te);
+    float* sTo = sTe + H * L.ts;
+    int16_t* crow = (int16_t*)(wbase + L.crow);
+    uint32_t* obuf = (uint32_t*)(wbase + L.obuf);
+    unsigned long long* bar = (unsigned long long*)(wbase + L.bar);
+    int* big = (int*)(wbase + L.big);                    // [0] = count, then (zigzag position, amplitude) pairs
+
+    jb_pdl_trigger();
+    const bool tables_const = (g.flags & JB_FLAG_REUSE_TABLES) != 0;
+    if (!tables_const) jb_pdl_wait();
+    // CH[row][j]: row = parity * H + m holds frequency k = 2 m + parity, columns j < H (the other half follows by symmetry)
+    for (int idx = threadIdx.x; idx < D * H; idx += blockDim.x) {
+        const int row = idx / H, j = idx - row * H;
+        const int k = 2 * (row % H) + row / H;
+        sCH[row * L.xs + j] = a.t.fA[k * D + j];
+    }
+    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+        sQm[idx] = a.t.qmult[idx];
+        // near a tie  <=>  |frac - .5| < tol + 2.4e-7 |val|  <=>  |val - rint(val)| + 2.4e-7 |val| > .5 - tol
+        const float tol = a.t.qtol[idx];
+        sThr[idx] = tol < 0.f ? 1e30f : 0.5f - tol;
+        sZz[idx] = a.t.zz[idx];
+    }
+    if (lane == 0) {
+        big[0] = 0;
+        ff_mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tables_const) jb_pdl_wait();
+
+    const int P = jb_ctrl_parity(a);
+    unsigned* const ticket = jb_ctrl_ticket(a, P);
+    const bool refine_on = !(g.flags & JB_FLAG_NO_REFINE);
+    const bool use_tma = ka.use_tma != 0;
+    const int hb = g.hb;
+    const int rg = lane >> 2, kg = lane & 3, kpar = kg >> 1, khalf = kg & 1;
+
+    auto claim = [&]() -> unsigned {
+        unsigned c = 0;
+        if (lane == 0) { c = atomicAdd(ticket, 1u); jb_ctrl_note_first(a, P, c); }
+        return __shfl_sync(0xffffffffu, c, 0);
+    };
+    // a block whose whole tile lies inside the image can come by TMA
+    auto interior = [&](int by, int bx) -> bool { return (by + 1) * side <= g.H && (bx + 1) * side <= g.W; };
+    bool dirty = true;                                   // generic-proxy writes to the tile since the last TMA load
+    auto issue = [&](int plane, int by, int bx) {
+        if (lane == 0) {
+            if (dirty) ff_fence_proxy_async();
+            ff_mbar_expect_tx(bar, (uint32_t)(side * FL_TILE_ROW));
+            ff_tma_load_3d(tile, &tmap, bx * side, by * side, plane, bar);
+        }
+    };
+    uint32_t phase = 0;
+
+    unsigned chunk = claim();
+    // (plane, blk0, nvalid) of the chunk, and the state of the tile slot: has the load of the chunk's first block
+    // been issued already (by the previous chunk's last block)?
+    bool first_in_flight = false;
+    if (chunk < a.n_chunks && use_tma) {
+        const int plane = (int)(chunk / (unsigned)g.cpp);
+        const int blk0 = (int)(chunk - (unsigned)plane * (unsigned)g.cpp) * JB_CHUNK_LARGE;
+        const int by = blk0 / hb, bx = blk0 - by * hb;
+        if (interior(by, bx)) { issue(plane, by, bx); first_in_flight = true; }
+        dirty = false;
+    }
+    while (chunk < a.n_chunks) {
+        const int plane = (int)(chunk / (unsigned)g.cpp);
+        const int blk0 = (int)(chunk - (unsigned)plane * (unsigned)g.cpp) * JB_CHUNK_LARGE;
+        const int nvalid = jb_min(JB_CHUNK_LARGE, g.nblocks - blk0);
+        const uint8_t* src = a.planes + (size_t)plane * a.plane_stride;
+        uint8_t* slot = a.tmp + (size_t)chunk * a.chunk_cap;           // (the large path always uses the big slots)
+        unsigned chunk_bytes = 0;
+        unsigned next_chunk = 0;
+        bool in_flight = first_in_flight;
+        first_in_flight = false;
+
+        for (int gi = 0; gi < nvalid; ++gi) {
+            const int blk = blk0 + gi;
+            const int by = blk / hb, bx = blk - by * hb;
+            // ---- the tile of this block ----
+            if (in_flight) {
+                while (!ff_mbar_try_wait(bar, phase)) { }
+                phase ^= 1u;
+            } else {
+                // edge block, or no TMA: the reference's two-level edge replication, byte by byte
+                for (int idx = lane; idx < side * side; idx += 32) {
+                    const int r = idx / side, c = idx - r * side;
+                    const int si = jb_min(by * D + r / bs, g.H1 - 1), sj = jb_min(bx * D + c / bs, g.W1 - 1);
+                    const int y = jb_min(si * bs + r % bs, g.H - 1), x = jb_min(sj * bs + c % bs, g.W - 1);
+                    tile[r * FL_TILE_ROW + c] = src[(size_t)y * a.row_pitch + x];
+                }
+                dirty = true;
+                __syncwarp();
+            }
+            // ---- box sums -> Xe, Xo.  Lane j < D sums sample (i, j): bs rows x bs bytes from byte bs j, under byte masks ----
+            {
+                const int j = lane < D ? lane : D - 1;
+                const int x0 = j * bs;
+                const int w0 = x0 >> 2, o0 = x0 & 3;
+                // masks of the up to three words a bs-byte run (bs <= 8) touches
+                const int nb0 = jb_min(4 - o0, bs);                               // bytes of the run in word 0
+                const uint32_t m0 = (nb0 >= 4 ? 0x01010101u : (0x01010101u >> (8 * (4 - nb0)))) << (8 * o0);
+                const int nb1 = jb_min(4, bs - nb0);
+                const uint32_t m1 = nb1 <= 0 ? 0u : (nb1 >= 4 ? 0x01010101u : (0x01010101u >> (8 * (4 - nb1))));
+                const int nb2 = bs - nb0 - (nb1 > 0 ? nb1 : 0);
+                const uint32_t m2 = nb2 <= 0 ? 0u : (0x01010101u >> (8 * (4 - nb2)));
+                const uint32_t* t32 = (const uint32_t*)tile + w0;
+                const int partner = D - 1 - lane;                                  // (lanes < D)
+                #pragma unroll 2
+                for (int i = 0; i < D; ++i) {
+                    const uint32_t* row = t32 + (size_t)i * bs * (FL_TILE_ROW / 4);
+                    uint32_t s = 0x4B000000u;                  // bit pattern of 2^23: exact int -> float without a conversion
+                    for (int k = 0; k < bs; ++k) {
+                        s = __dp4a(row[0], m0, s);
+                        s = __dp4a(row[1], m1, s);
+                        if (m2) s = __dp4a(row[2], m2, s);
+                        row += FL_TILE_ROW / 4;
+                    }
+                    const float f = __uint_as_float(s) - 8388608.0f;
+                    const float p = __shfl_sync(0xffffffffu, f, partner & 31);
+                    if (lane < H) { sXe[i * L.xs + lane] = f + p; sXo[i * L.xs + lane] = f - p; }
+                }
+            }
+            __syncwarp();
+            // ---- the tile is consumed: the next block's tile may come in (this chunk's, or the next chunk's first) ----
+            in_flight = false;
+            {
+                int nplane = plane, nblk = blk + 1;
+                bool have = gi + 1 < nvalid;
+                if (!have) {
+                    next_chunk = claim();
+                    if (next_chunk < a.n_chunks) {
+                        nplane = (int)(next_chunk / (unsigned)g.cpp);
+                        nblk = (int)(next_chunk - (unsigned)nplane * (unsigned)g.cpp) * JB_CHUNK_LARGE;
+                        have = true;
+                    }
+                }
+                if (have && use_tma) {
+                    const int nby = nblk / hb, nbx = nblk - nby * hb;
+                    if (interior(nby, nbx)) {
+                        issue(nplane, nby, nbx);
+                        dirty = false;
+                        if (gi + 1 < nvalid) in_flight = true; else first_in_flight = true;
+                    }
+                }
+            }
+            // ---- row pass: T[i][k] = sum_{j < H} (k even ? Xe : Xo)[i][j] C[k][j]; lane tile RT rows x KT frequencies ----
+            float t[RT][KT];
+            {
+                const float* xbase = (kpar ? sXo : sXe) + (rg * RT) * L.xs;
+                const float* cbase = sCH + (kpar * H + khalf * KT) * L.xs;
+                #pragma unroll
+                for (int r = 0; r < RT; ++r)
+                    #pragma unroll
+                    for (int q = 0; q < KT; ++q) t[r][q] = 0.f;
+                #pragma unroll
+                for (int j = 0; j < H; j += 4) {
+                    float4 x4[RT], c4[KT];
+                    #pragma unroll
+                    for (int r = 0; r < RT; ++r) x4[r] = *(const float4*)(xbase + r * L.xs + j);
+                    #pragma unroll
+                    for (int q = 0; q < KT; ++q) c4[q] = *(const float4*)(cbase + q * L.xs + j);
+                    #pragma unroll
+                    for (int r = 0; r < RT; ++r)
+                        #pragma unroll
+                        for (int q = 0; q < KT; ++q) {
+                            t[r][q] = fmaf(x4[r].x, c4[q].x, t[r][q]); t[r][q] = fmaf(x4[r].y, c4[q].y, t[r][q]);
+                            t[r][q] = fmaf(x4[r].z, c4[q].z, t[r][q]); t[r][q] = fmaf(x4[r].w, c4[q].w, t[r][q]);
+                        }
+                }
+            }
+            // ---- even / odd sums down the columns: rows i and D-1-i sit in lanes rg and 7 - rg (same kg) ----
+            {
+                float other[RT][KT];
+                #pragma unroll
+                for (int r = 0; r < RT; ++r)
+                    #pragma unroll
+                    for (int q = 0; q < KT; ++q) other[RT - 1 - r][q] = __shfl_xor_sync(0xffffffffu, t[r][q], 28);
+                // lanes rg < 4 hold rows i < H and store Te[i] = T[i] + T[D-1-i]; lanes rg >= 4 hold rows D-1-i' and
+                // store To[i'] = T[i'] - T[D-1-i'] = other - mine
+                const bool low = rg < 4;
+                float* dstT = low ? sTe : sTo;
+                #pragma unroll
+                for (int r = 0; r < RT; ++r) {
+                    const int i = low ? rg * RT + r : D - 1 - (rg * RT + r);
+                    #pragma unroll
+                    for (int q = 0; q < KT; ++q) {
+                        const int k = 2 * (khalf * KT + q) + kpar;
+                        dstT[i * L.ts + k] = low ? t[r][q] + other[r][q] : other[r][q] - t[r][q];
+                    }
+                }
+            }
+            __syncwarp();
+            // ---- column pass: Y[u][k] = sum_{i < H} (u even ? Te : To)[i][k] C[u][i]; lane tile RT frequencies u (one
+            //      parity) x KT consecutive k; quantise, tie check, zigzag ----
+            {
+                const int upar = rg >> 2, ug = rg & 3;                  // u = 2 (ug RT + r) + upar
+                const float* tb = (upar ? sTo : sTe) + kg * KT;
+                const float* cb = sCH + (upar * H + ug * RT) * L.xs;
+                float y[RT][KT];
+                #pragma unroll
+                for (int r = 0; r < RT; ++r)
+                    #pragma unroll
+                    for (int q = 0; q < KT; ++q) y[r][q] = 0.f;
+                #pragma unroll
+                for (int i = 0; i < H; i += 4) {
+                    float4 c4[RT];
+                    #pragma unroll
+                    for (int r = 0; r < RT; ++r) c4[r] = *(const float4*)(cb + r * L.xs + i);
+                    #pragma unroll
+                    for (int ii = 0; ii < 4; ++ii) {
+                        float tv[KT];
+                        #pragma unroll
+                        for (int q = 0; q < KT; q += 2) {
+                            const float2 v2 = *(const float2*)(tb + (i + ii) * L.ts + q);
+                            tv[q] = v2.x; tv[q + 1] = v2.y;
+                        }
+                        #pragma unroll
+                        for (int r = 0; r < RT; ++r) {
+                            const float cv = ii == 0 ? c4[r].x : ii == 1 ? c4[r].y : ii == 2 ? c4[r].z : c4[r].w;
+                            #pragma unroll
+                            for (int q = 0; q < KT; ++q) y[r][q] = fmaf(cv, tv[q], y[r][q]);
+                        }
+                    }
+                }
+                #pragma unroll
+                for (int r = 0; r < RT; ++r) {
+                    const int u = 2 * (ug * RT + r) + upar;
+                    #pragma unroll
+                    for (int q = 0; q < KT; ++q) {
+                        const int k = kg * KT + q;
+                        const int idx = u * D + k;
+                        const float val = y[r][q] * sQm[idx];
+                        const float tt = val + 12582912.0f;             // 1.5 * 2^23: rounds half-even to an integer
+                        int qi = __float_as_int(tt) - 0x4B400000;
+                        const float dd = fabsf(val - (tt - 12582912.0f));
+                        if (refine_on && fmaf(fabsf(val), 2.4e-7f, dd) > sThr[idx])
+                            qi = (int)rint(fl_refine<D>(sXe, idx, (bs << 8) | g.qmode, a.t.fA64, a.t.qrecip[idx]));
+                        const int zp = sZz[idx];
+                        if (MODE == 1) {
+                            a.coeffs_out[((size_t)plane * g.nblocks + blk) * n + zp] = (int16_t)max(-32767, min(32767, qi));
+                        } else {
+                            if (qi > JB_MAX_AMP || qi < -JB_MAX_AMP) {
+                                // BadRleCodeError in the reference (util.py:170-171): remember the true amplitude for the
+                                // report the run-length stage makes, store a saturated value
+                                const int kk = atomicAdd(big, 1);
+                                if (kk < FL_BIG_CAP) { big[1 + 2 * kk] = zp; big[2 + 2 * kk] = qi; }
+                                qi = qi > 0 ? 32767 : -32767;
+                            }
+                            crow[zp] = (int16_t)qi;
+                        }
+                    }
+                }
+            }
+            if (MODE == 1) { __syncwarp(); continue; }
+            __syncwarp();
+            // ---- non-zero bitmap (zigzag order): lane w keeps word w ----
+            uint32_t mybits = 0;
+            #pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                const uint32_t m = __ballot_sync(0xffffffffu, crow[w * 32 + lane] != 0);
+                if (lane == w) mybits = m;
+            }
+            // ---- run-length codes of the whole warp: lane w codes the non-zeros of its 32 positions ----
+            // previous non-zero position before word w: the highest set bit of the nearest non-empty lower word
+            int last_here = mybits ? lane * 32 + 31 - __clz((int)mybits) : -1;
+            int prev_before = -1;
+            {
+                int run_max = last_here;                                   // inclusive max-scan over lanes
+                #pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, run_max, o);
+                    if (lane >= o) run_max = max(run_max, v);
+                }
+                prev_before = __shfl_up_sync(0xffffffffu, run_max, 1);
+                if (lane == 0) prev_before = -1;
+            }
+            // pass 1: bits of my codes
+            unsigned mybitlen = 0;
+            bool bad_amp = false;
+            {
+                int prev = prev_before;
+                for (uint32_t m = mybits; m; m &= m - 1u) {
+                    const int p = lane * 32 + __ffs((int)m) - 1;
+                    const int amp = crow[p];
+                    const uint32_t mag = (uint32_t)(amp < 0 ? -amp : amp);
+                    const int run = p - prev - 1;
+                    prev = p;
+                    if (mag > (uint32_t)JB_MAX_AMP) {                          // nothing is emitted (as in the reference)
+                        long long true_amp = amp;
+                        const int nb = jb_min(big[0], FL_BIG_CAP);
+                        for (int k = 0; k < nb; ++k)
+                            if (big[1 + 2 * k] == p) true_amp = big[2 + 2 * k];
+                        jb_report_bad_code(jb_ctrl_status(a, P), (unsigned long long)plane * g.nblocks + blk, p, run % JB_MAX_RUN, true_amp);
+                        bad_amp = true;
+                        continue;
+                    }
+                    mybitlen += 8u * (unsigned)(run / JB_MAX_RUN) + 8u + (unsigned)(33 - __clz((int)mag));
+                }
+            }
+            unsigned total_bits;
+            unsigned bitoff = jb_warp_excl_scan(mybitlen, lane, &total_bits);
+            total_bits += 8u;                                                   // EOB
+            const unsigned blen = (total_bits + 7u) >> 3;
+            const bool any_bad = __any_sync(0xffffffffu, bad_amp);
+            uint8_t* dst = slot + chunk_bytes;
+            if (blen <= FL_BLOCK_BUF_WORDS * 4u) {
+                for (int i = lane; i < FL_BLOCK_BUF_WORDS + 2; i += 32) obuf[i] = 0u;
+                __syncwarp();
+                int prev = prev_before;
+                for (uint32_t m = mybits; m; m &= m - 1u) {
+                    const int p = lane * 32 + __ffs((int)m) - 1;
+                    const int amp = crow[p];
+                    const uint32_t mag = (uint32_t)(amp < 0 ? -amp : amp);
+                    int run = p - prev - 1;
+                    prev = p;
+                    if (mag > (uint32_t)JB_MAX_AMP) continue;
+                    while (run >= JB_MAX_RUN) {                               // (15, 0): the byte 0xF0
+                        atomicOr(obuf + (bitoff >> 5), 0xF0000000u >> (bitoff & 31u));
+                        if ((bitoff & 31u) > 24u) atomicOr(obuf + (bitoff >> 5) + 1, 0xF0000000u << (32u - (bitoff & 31u)));
+                        bitoff += 8u;
+                        run -= JB_MAX_RUN;
+                    }
+                    const int size = 33 - __clz((int)mag);
+                    const uint32_t code = ((((uint32_t)run << 4) | (uint32_t)size) << size) | ((amp > 0 ? 1u : 0u) << (size - 1)) | mag;
+                    const unsigned len = 8u + (unsigned)size;
+                    const unsigned long long v64 = (unsigned long long)code << (64u - len - (bitoff & 31u));
+                    atomicOr(obuf + (bitoff >> 5), (uint32_t)(v64 >> 32));
+                    if ((uint32_t)v64) atomicOr(obuf + (bitoff >> 5) + 1, (uint32_t)v64);
+                    bitoff += len;
+                }
+                __syncwarp();
+                // bytes of the block -> the chunk's slot (big-endian words = stream order)
+                for (unsigned i = lane; i < blen; i += 32) dst[i] = (uint8_t)(obuf[i >> 2] >> (24u - 8u * (i & 3u)));
+            } else {
+                // a block longer than the shared-memory buffer: lane 0 packs it serially, straight to the slot
+                __shared__ uint32_t s_mask[FL_WARPS][32];
+                if (lane < NW) s_mask[warp][lane] = mybits;
+                __syncwarp();
+                if (lane == 0) fl_pack_serial(crow, s_mask[warp], NW, dst);
+            }
+            chunk_bytes += blen;
+            if (any_bad && lane == 0) big[0] = 0;
+            __syncwarp();
+        }
+        if (MODE == 0 && lane == 0) jb_record_chunk_len(a, P, chunk, chunk_bytes);
+        if (nvalid < 1) next_chunk = claim();               // (cannot happen: every chunk holds a block)
+        chunk = next_chunk;
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+template <int D, int MODE>
+static cudaError_t fl_launch_t(const CUtensorMap& map, const FlKernelArgs& ka, cudaStream_t s) {
+    const size_t smem = fl_layout(D, D * ka.a.g.bs).total;
+    cudaError_t e = cudaFuncSetAttribute(jb_fwd_large_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned want = (ka.a.n_chunks + FL_WARPS - 1) / FL_WARPS;
+    const unsigned grid = want < (unsigned)sms ? want : (unsigned)sms;
+    if (grid == 0) return cudaSuccess;
+    return jb_launch_ex(jb_fwd_large_kernel<D, MODE>, dim3(grid), dim3(FL_WARPS * 32), smem, s,
+                        (ka.a.g.flags & JB_FLAG_PDL) != 0, map, ka);
+}
+
+template <int MODE>
+static cudaError_t fl_launch_d(const CUtensorMap& map, const FlKernelArgs& ka, cudaStream_t s) {
+    switch (ka.a.g.d) {
+    case 16: return fl_launch_t<16, MODE>(map, ka, s);
+    case 24: return fl_launch_t<24, MODE>(map, ka, s);
+    default: return fl_launch_t<32, MODE>(map, ka, s);
+    }
+}
+
+cudaError_t jb_launch_fwd_large(const JbFwdArgs& a_in, int mode, cudaStream_t s) {
+    FlKernelArgs ka;
+    ka.a = a_in;
+    ka.a.slots_always_big = 1;
+    const JbGeom& g = ka.a.g;
+    const int side = g.d * g.bs;
+    CUtensorMap map;
+    memset(&map, 0, sizeof(map));
+    const bool aligned = ((uintptr_t)ka.a.planes & 15) == 0 && (ka.a.row_pitch & 15) == 0 &&
+                         (ka.a.n_planes == 1 || (ka.a.plane_stride & 15) == 0);
+    ka.use_tma = 0;
+    if (!(g.flags & JB_FLAG_NO_TMA) && aligned)
+        ka.use_tma = jb_make_plane_tensor_map(&map, ka.a.planes, g.W, g.H, ka.a.n_planes, ka.a.row_pitch, ka.a.plane_stride,
+                                              FL_TILE_ROW, side) ? 1 : 0;
+    if (mode == 0) {
+        cudaError_t e = fl_launch_d<0>(map, ka, s);
+        if (e != cudaSuccess) return e;
+        return jb_launch_gather(ka.a, s);
+    }
+    return fl_launch_d<1>(map, ka, s);
+}

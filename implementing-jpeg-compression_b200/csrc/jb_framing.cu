@@ -138,9 +138,8 @@ __global__ void __launch_bounds__(1024) jb_frame_prep_kernel(JbFrameArgs f) {
     __shared__ unsigned s_warp[33];
     unsigned carry = 0, wcarry = 0;
     bool bad = false;
-    if (threadIdx.x == 0) { f.big_list[0] = 0u; *f.ticket = 0u; }
-    // first kernel of the decompress call: reset the status block (word 1 = "no bad code yet")
-    if (threadIdx.x < JB_STATUS_WORDS) f.status[threadIdx.x] = threadIdx.x == 1 ? ~0ull : 0ull;
+    if (threadIdx.x == 0) f.big_list[0] = 0u;
+    // (status words and chunk ticket live in the workspace's control block, which is clean when a call starts)
     __syncthreads();
     for (int base = 0; base < f.n_planes; base += 1024) {
         int s = base + threadIdx.x;
@@ -149,6 +148,7 @@ __global__ void __launch_bounds__(1024) jb_frame_prep_kernel(JbFrameArgs f) {
             unsigned long long len = f.plane_len[s];
             if (len > 0x1FFFFFF0ull) { bad = true; len = 0; }           // bit positions are 32-bit
             nt = (unsigned)((len + f.tile_bytes - 1) / f.tile_bytes);
+            if (len > f.in_bytes || f.plane_off[s] > f.in_bytes - len) { bad = true; nt = 0; }     // reaches beyond the input buffer
             f.fallback[s] = f.force_serial ? 1u : 0u;
             if (nt > JB_REACH_SMALL_CAP) f.big_list[1 + atomicAdd(f.big_list, 1u)] = (unsigned)s;
         }
@@ -598,7 +598,6 @@ __global__ void __launch_bounds__(JB_FRAME_THREADS) jb_frame_emit_kernel(JbFrame
 
 // ---- F4: serial fallback, one warp per marked stream ------------------------------------------------------
 // The warp stages the stream through shared memory 4 KB at a time (coalesced); lane 0 walks it.
-#define JB_SERIAL_WORDS 1024
 __device__ __forceinline__ void jb_serial_stream(const JbFrameArgs& f, int s, uint32_t* sw, int lane) {
     const uint32_t len = (uint32_t)f.plane_len[s];
     const uint8_t* stream = f.in + f.plane_off[s];

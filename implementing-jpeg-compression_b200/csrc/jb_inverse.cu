@@ -40,6 +40,14 @@ __host__ __device__ inline JbInvSmemLayout jb_inv_smem_layout(int d, bool dft) {
 
 size_t jb_inv_generic_smem_bytes(int d, bool dft) { return jb_inv_smem_layout(d, dft).total; }
 
+// end of a decompress call whose last transform kernel has no epilogue of its own (everything but the fused 8x8 kernel)
+__global__ void jb_dec_finish_kernel(JbInvArgs a) { jb_dec_publish_and_clean(a); }
+
+cudaError_t jb_launch_dec_finish(const JbInvArgs& a, cudaStream_t s) {
+    jb_dec_finish_kernel<<<1, 1, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(JB_INV_GENERIC_THREADS)
 jb_inv_generic_kernel(const JbInvArgs a) {
@@ -60,8 +68,8 @@ jb_inv_generic_kernel(const JbInvArgs a) {
     const unsigned chunk = blockIdx.x;
     if (chunk >= a.n_chunks) return;
     const int plane = chunk / g.cpp;
-    const int blk0 = (chunk % g.cpp) * JB_CHUNK;
-    const int nvalid = jb_min(JB_CHUNK, g.nblocks - blk0);
+    const int blk0 = (chunk % g.cpp) * g.chunk;
+    const int nvalid = jb_min(g.chunk, g.nblocks - blk0);
 
     if (MODE != 1) {
         for (int i = tid; i < n; i += JB_INV_GENERIC_THREADS) {

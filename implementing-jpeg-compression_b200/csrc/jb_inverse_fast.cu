@@ -122,6 +122,10 @@ jb_inv_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FiKernelArgs 
     FiRowsSmem& wr = *(FiRowsSmem*)(smem_raw + 128 + (size_t)warp * sizeof(FiRowsSmem));           // row variant
     uint32_t* const w_coef = ROWS ? wr.coef : ws.coef;
     float* const w_scr = ROWS ? wr.scr : ws.scr;
+    jb_pdl_trigger();
+    // the tables are constant once built (JB_FLAG_REUSE_TABLES): their loads may overlap the kernel before this one
+    const bool tables_const = (g.flags & JB_FLAG_REUSE_TABLES) != 0;
+    if (!tables_const) jb_pdl_wait();
     for (int i = threadIdx.x; i < 64; i += blockDim.x) s_izz[i] = (uint8_t)a.t.izz[i];
     __syncthreads();
 
@@ -134,6 +138,7 @@ jb_inv_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FiKernelArgs 
         const float sc = DFT ? (1.0f / 64.0f) : ((li == 0 ? 0.125f : 0.25f) * (v == 0 ? 0.125f : 0.25f));
         dq[v] = a.t.dqmult[li * 8 + v] * sc;
     }
+    if (tables_const) jb_pdl_wait();                                   // from here on: data the kernels before this one wrote
 
     // Chunks are claimed from a device-wide counter, one ahead (the claim of the next chunk travels while this one
     // is processed): with a fixed deal the slowest SM finished 36 % later than the fastest (ncu, sm__cycles_active
@@ -347,6 +352,7 @@ jb_inv_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FiKernelArgs 
         if (lane == 0) ff_bulk_wait_read<0>();
         __syncwarp();
     }
+    jb_dec_epilogue(a);                                       // end of the call (jb_inverse.cuh)
 }
 
 bool jb_inv_fast_eligible(const JbGeom& g) { return g.d == 8 && g.bs == 4; }
@@ -366,8 +372,8 @@ static cudaError_t jb_inv_fast_launch_t(const CUtensorMap& map, const FiKernelAr
     unsigned want = (ka.a.n_chunks + NWARPS - 1) / NWARPS;
     unsigned grid = want < (unsigned)(sms * per_sm) ? want : (unsigned)(sms * per_sm);
     if (grid == 0) return cudaSuccess;
-    jb_inv_fast_kernel<DFT, MODE, ROWS><<<grid, NWARPS * 32, smem, s>>>(map, ka);
-    return cudaGetLastError();
+    return jb_launch_ex(jb_inv_fast_kernel<DFT, MODE, ROWS>, dim3(grid), dim3(NWARPS * 32), smem, s,
+                        (ka.a.g.flags & JB_FLAG_PDL) != 0, map, ka);
 }
 
 template <bool ROWS>

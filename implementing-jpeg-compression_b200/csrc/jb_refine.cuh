@@ -43,11 +43,11 @@ static __device__ __noinline__ void jb_pf_pass8(const JbC64* c, JbC64* ch) {
     s = jb_csub(a4, a6); ch[3] = jb_cadd(s, a7); ch[7] = jb_csub(s, a7);
 }
 
-// X: the d x d box sums of the block (exact integers, as int or float); returns the value the reference hands to
+// X: the d x d box sums of the block (exact integers, as int or float; anything indexable by i * d + j); returns the value the reference hands to
 // np.round for coefficient (u, v).  A64 / B64: the fp64 transform matrices of jb_tables.cu; recip: qrecip[u*d+v].
 // (Inlined into a small __noinline__ wrapper per kernel file, so that the hot kernels see a call with few operands.)
-template <typename XT>
-__device__ __forceinline__ double jb_refine_f64(const XT* X, int u, int v, int d, int bs, int transform, int qmode,
+template <typename XA>
+__device__ __forceinline__ double jb_refine_f64(XA X, int u, int v, int d, int bs, int transform, int qmode,
                                              const double* A64, const double* B64, double recip) {
     const double bs2 = (double)(bs * bs);          // np.mean: exact integer sum / count (subsampling.py:9-11)
     double y;

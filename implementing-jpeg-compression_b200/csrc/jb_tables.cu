@@ -37,7 +37,8 @@ int jb_make_geom(const jb_params* p, JbGeom* g) {
     if (nb > 0x3FFFFFFF) return JB_ERR_UNSUPPORTED;
     g->nblocks = (int)nb;
     g->maxblk = jb_max_block_bytes(g->n);
-    g->cpp = jb_ceil_div(g->nblocks, JB_CHUNK);
+    g->chunk = jb_chunk_blocks(g->d);
+    g->cpp = jb_ceil_div(g->nblocks, g->chunk);
     g->transform = p->transform; g->qmode = p->qmode; g->qparam = p->qparam; g->flags = p->flags;
     return JB_OK;
 }

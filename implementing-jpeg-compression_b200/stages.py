@@ -62,7 +62,7 @@ def pack_coefficients(coeffs, dct_size):
     return CompressedPlanes(out, offsets, status, n).to_bytes_list()
 
 
-def unpack_streams(streams, blocks_per_plane, dct_size):
+def unpack_streams(streams, blocks_per_plane, dct_size, flags=0):
     lib = _lib.load()
     dev = _require_cuda()
     streams = [bytes(s) for s in streams]
@@ -77,7 +77,7 @@ def unpack_streams(streams, blocks_per_plane, dct_size):
     ws_bytes = lib.jb_stage_unpack_workspace_bytes(n, blocks_per_plane, dct_size, len(blob))
     ws = _workspace.get("inv", ws_bytes, dev)
     d_offs, d_lens = torch.from_numpy(offs).to(dev), torch.from_numpy(lens).to(dev)
-    rc = lib.jb_stage_unpack(_ptr(data), len(blob), _ptr(d_offs), _ptr(d_lens), n, blocks_per_plane, dct_size,
+    rc = lib.jb_stage_unpack(_ptr(data), len(blob), _ptr(d_offs), _ptr(d_lens), n, blocks_per_plane, dct_size, int(flags),
                              _ptr(coeffs), _ptr(status), _ptr(ws), ws.numel(), _stream_ptr())
     _raise_for_code(rc)
     check_status(status)

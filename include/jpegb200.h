@@ -83,6 +83,8 @@ typedef struct jb_params {
 #define JB_FLAG_NO_TMA        2  /* specialised kernels stage tiles with plain loads/stores */
 #define JB_FLAG_NO_REFINE     4  /* skip the float64 re-evaluation of near-tie coefficients */
 #define JB_FLAG_SERIAL_FRAMING 8 /* decoder: find block boundaries with the serial fallback walk only */
+#define JB_FLAG_PDL 128          /* launch the kernels of the call with programmatic dependent launch: their prologues
+                                   overlap the tail of the kernel before them on the stream (results unchanged) */
 #define JB_FLAG_TILE_DECODER 64  /* decoder, 8x8 / block_size 4 kernel: store 32-row x 128-byte tiles (TMA tensor stores,
                                    or plain stores with JB_FLAG_NO_TMA) instead of whole chunk rows; kept for comparison */
 #define JB_FLAG_REUSE_TABLES  16 /* the caller promises that this workspace was last used by a COMPLETED-OR-QUEUED call of
@@ -157,7 +159,8 @@ int jb_decompress_planes(const uint8_t* d_in, size_t in_bytes,
 
 /* Which block-boundary discovery a jb_decompress_planes call with these sizes runs (the container stores no
  * index, rle_byte_stream.py:74-88 reads sequentially; see csrc/jb_framing.cu): JB_FRAMING_STITCH = batches of
- * short streams, one CTA per stream; JB_FRAMING_CHAIN = long streams, several kernels and CTAs per stream.
+ * short streams, tile walks + one CTA per stream; JB_FRAMING_CHAIN = long streams (gigapixel planes), tile walks
+ * chained over several kernels and CTAs per stream.
  * Host only; lets a test assert which path it exercised.  Negative: an error code. */
 #define JB_FRAMING_STITCH 0
 #define JB_FRAMING_CHAIN  1
@@ -180,10 +183,10 @@ int jb_stage_pack(const int32_t* d_coeffs, int n_planes, int blocks_per_plane, i
 size_t jb_stage_pack_workspace_bytes(int n_planes, int blocks_per_plane, int dct_size);
 
 /* Stages 8-7 inverted (RleBytestream.invert + RunLengthEncoding.invert): int16 zigzag
- * coefficients, n_planes * blocks_per_plane * d*d. */
+ * coefficients, n_planes * blocks_per_plane * d*d.  flags: JB_FLAG_SERIAL_FRAMING or 0. */
 int jb_stage_unpack(const uint8_t* d_in, size_t in_bytes,
                     const uint64_t* d_plane_off, const uint64_t* d_plane_len, int n_planes,
-                    int blocks_per_plane, int dct_size, int16_t* d_coeffs, uint64_t* d_status,
+                    int blocks_per_plane, int dct_size, int flags, int16_t* d_coeffs, uint64_t* d_status,
                     void* d_ws, size_t ws_bytes, void* stream);
 size_t jb_stage_unpack_workspace_bytes(int n_planes, int blocks_per_plane, int dct_size, size_t in_bytes);
 

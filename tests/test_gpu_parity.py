@@ -147,7 +147,12 @@ def test_pack_unpack_random_coefficients(jb, n, density, bits):
     assert np.array_equal(back, zz)
 
 
-def test_framing_stream_lengths_around_the_walk_warp_boundaries(jb):
+# framing variants of the decoder: 0 = the parallel tile walk, JB_FLAG_SERIAL_FRAMING = 8 the single-thread walk
+FRAMING = [pytest.param(0, id="tile_walk"), pytest.param(8, id="serial_walk")]
+
+
+@pytest.mark.parametrize("framing", FRAMING)
+def test_framing_stream_lengths_around_the_walk_warp_boundaries(jb, framing):
     """The walk gives every stream whole warps of 32 tiles (256 bytes each here): streams whose tile counts sit
     on and around 32 and 64, a one-tile stream and an all-EOB stream in one batch, decoded block for block."""
     n_blocks, n = 400, 64
@@ -176,7 +181,7 @@ def test_framing_stream_lengths_around_the_walk_warp_boundaries(jb):
     tiles = [-(-len(x) // 256) for x in streams]
     assert {32, 64} & set(tiles) and min(tiles) <= 2 and max(tiles) >= 80, tiles
     assert len({t % 32 for t in tiles}) >= 6, tiles
-    back = jb.stages.unpack_streams(streams, n_blocks, 8)
+    back = jb.stages.unpack_streams(streams, n_blocks, 8, flags=framing)
     assert np.array_equal(back, zz)
     assert jb.stages.pack_coefficients(zz, 8) == streams
 
@@ -213,7 +218,8 @@ def test_one_long_stream_among_short_ones(jb):
     assert torch.equal(out, planes)                          # 'none' on 8-bit data with block_size 1 is lossless
 
 
-def test_framing_with_many_false_block_starts(jb):
+@pytest.mark.parametrize("framing", FRAMING)
+def test_framing_with_many_false_block_starts(jb, framing):
     """Streams full of 0x00 bytes inside amplitude fields: most candidate offsets are false."""
     rng = np.random.default_rng(77)
     zz = np.zeros((2, 3000, 64), dtype=np.int64)
@@ -224,29 +230,76 @@ def test_framing_with_many_false_block_starts(jb):
     streams = [rp.pack_blocks(zz[p]) for p in range(2)]
     frac_zero = np.mean(np.frombuffer(streams[0], dtype=np.uint8) == 0)
     assert frac_zero > 0.25
-    back = jb.stages.unpack_streams(streams, 3000, 8)
+    back = jb.stages.unpack_streams(streams, 3000, 8, flags=framing)
     assert np.array_equal(back, zz)
 
 
-def test_zero_heavy_streams_every_byte_a_candidate(jb):
+@pytest.mark.parametrize("framing", FRAMING)
+def test_framing_windows_halo_and_stream_alignment(jb, framing):
+    """Streams that start at any byte alignment, with dense (long) blocks next to sparse ones, lengths and offsets
+    of every residue mod 4, and nonzero padding bits, which the reference's decoder skips without looking
+    (rle_byte_stream.py:80-82)."""
+    rng = np.random.default_rng(31)
+    n_blocks, n = 900, 64
+    planes = []
+    for i in range(7):
+        dens = [0.9, 0.05, 0.5, 1.0, 0.2, 0.7, 0.02][i]
+        vals = rng.integers(1, 1 << [14, 3, 9, 12, 6, 14, 2][i], (n_blocks, n)) * (rng.integers(0, 2, (n_blocks, n)) * 2 - 1)
+        planes.append(np.where(rng.random((n_blocks, n)) < dens, vals, 0).astype(np.int64))
+    zz = np.stack(planes)
+    streams = [rp.pack_blocks(z) for z in zz]
+    assert max(len(x) for x in streams) > 3 * 16384 and len({len(x) % 4 for x in streams}) >= 3
+    assert len({sum(len(x) for x in streams[:i]) % 4 for i in range(7)}) >= 3          # start alignments
+    back = jb.stages.unpack_streams(streams, n_blocks, 8, flags=framing)
+    assert np.array_equal(back, zz)
+    # padding bits set to 1 behind EOBs that do not end on a byte boundary: the reference's reader skips them
+    # unseen, so such a stream is valid; here it takes the serial walk
+    small = zz[1][:40]
+    parts, touched = [], 0
+    for blk in small:
+        enc = bytearray(rp.pack_blocks(blk[None]))
+        nz = np.nonzero(blk)[0]
+        bits, prev = 8, -1
+        for pos in nz:
+            bits += 8 * ((pos - prev - 1) // 15) + 8 + int(abs(int(blk[pos]))).bit_length() + 1
+            prev = pos
+        pad = len(enc) * 8 - bits
+        assert 0 <= pad < 8
+        if pad:
+            enc[-1] |= (1 << pad) - 1
+            touched += 1
+        parts.append(bytes(enc))
+    assert touched > 10
+    got = jb.stages.unpack_streams([b"".join(parts)], 40, 8, flags=framing)
+    assert np.array_equal(got[0], small)
+
+
+@pytest.mark.parametrize("framing", FRAMING)
+def test_zero_heavy_streams_every_byte_a_candidate(jb, framing):
     # an all-black plane packs to one 0x00 per block: every byte is a block start
     cfg, ocfg = _cfgs(jb, (600, 800, 1, 8, "DCT", "qtable", None))
     a = np.zeros((600, 800), dtype=np.int64)
     s = jb.compress_band(a, cfg)
     assert s == b"\0" * (75 * 100)
-    assert np.array_equal(jb.decompress_band(s, cfg), a)
+    assert np.array_equal(jb.decompress_band(s, cfg, flags=framing), a)
 
 
-def test_malformed_streams_are_rejected(jb):
+@pytest.mark.parametrize("framing", FRAMING)
+def test_malformed_streams_are_rejected(jb, framing):
     cfg, ocfg = _cfgs(jb, (64, 64, 4, 8, "DCT", "qtable", None))
     a = synth_plane(64, 64, 1)
     good = jb.compress_band(a, cfg)
+    assert np.array_equal(jb.decompress_band(good, cfg, flags=framing), jb.decompress_band(good, cfg))
     with pytest.raises(jb.BadStreamError):
-        jb.decompress_band(good[:-1], cfg)              # truncated
+        jb.decompress_band(good[:-1], cfg, flags=framing)              # truncated
     with pytest.raises(jb.BadStreamError):
-        jb.decompress_band(good + b"\0", cfg)           # one block too many
+        jb.decompress_band(good + b"\0", cfg, flags=framing)           # one block too many
     with pytest.raises(jb.BadStreamError):
-        jb.decompress_band(b"\x50" + good[1:], cfg)     # (5, 0, 0) is not a code
+        jb.decompress_band(b"\x50" + good[1:], cfg, flags=framing)     # (5, 0, 0) is not a code
+    with pytest.raises(jb.BadStreamError):
+        jb.decompress_band(b"", cfg, flags=framing)                    # nothing at all
+    # an error in one call leaves the workspace usable: the next call on good data succeeds
+    assert np.array_equal(jb.decompress_band(good, cfg, flags=framing), jb.decompress_band(good, cfg))
     with pytest.raises(jb.BadQuantizationError):
         jb.Configuration(width=8, height=8, dct_size=4, quantization=jb.QuantizationMethod("qtable"))
     with pytest.raises(jb.EmptyArrayError):
@@ -506,3 +559,43 @@ def test_band_sharded_gigapixel_frame_concatenates(jb):
         assert np.array_equal(jb.decompress_bands(band, sub), whole_dec[:, r0:r1])
     assert jb.sharding.concat_band_streams(parts) == whole
     assert whole[1] == rp.compress_band(planes[1].astype(np.int64), ocfg)
+
+
+def test_programmatic_dependent_launch_gives_the_same_results(jb):
+    """JB_FLAG_PDL (128): the kernels of a call -- and of the calls queued behind each other -- are launched with
+    programmatic stream serialization; their prologues overlap the predecessor's tail and they wait before touching
+    its data.  Same streams and pixels as without it, also when calls follow each other back to back on one
+    stream, through a CUDA graph, and with the table reuse that moves the table loads in front of the wait."""
+    import torch
+    h, w, n = 272, 480, 12
+    cfg, ocfg = _cfgs(jb, (h, w, 4, 8, "DCT", "qtable", None))
+    planes = torch.from_numpy(np.stack([synth_plane(h, w, 700 + i) for i in range(n)]).astype(np.uint8)).cuda()
+    ref = jb.BatchCodec(cfg, n)
+    comp = ref.compress_device(planes)
+    want_streams = comp.to_bytes_list()
+    want_pixels, st = ref.decompress_device(comp, comp.total_bytes())
+    jb.check_status(st)
+    want_pixels = want_pixels.clone()
+    bc = jb.BatchCodec(cfg, n, flags=jb._lib.JB_FLAG_PDL)
+    for rep in range(4):                                   # the first call builds tables, the later ones reuse them
+        c2 = bc.compress_device(planes)
+        out, st = bc.decompress_device(c2, comp.total_bytes())
+    jb.check_status(st)
+    assert c2.to_bytes_list() == want_streams
+    assert torch.equal(out, want_pixels)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        bc.compress_device(planes)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        c3 = bc.compress_device(planes)
+        out3, st3 = bc.decompress_device(c3, comp.total_bytes())
+    for rep in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    jb.check_status(st3)
+    assert c3.to_bytes_list() == want_streams
+    assert torch.equal(out3, want_pixels)

@@ -59,6 +59,9 @@ def validate(args):
         raise SystemExit("usage: jb_compress.py infile outfile [options]  |  jb_compress.py --batch IMAGE... --outdir DIR")
 
 
+BATCH_PIXEL_BUDGET = 256 * 1024 * 1024       # source pixels per device batch of --batch (0.75 GB of pinned RGB)
+
+
 def main(argv=None):
     args = build_parser().parse_args(argv)
     validate(args)
@@ -79,16 +82,25 @@ def main(argv=None):
         return 0
 
     os.makedirs(args.outdir, exist_ok=True)
+    stems = [os.path.splitext(os.path.basename(path))[0] for path in args.batch]
+    clash = sorted({x for x in stems if stems.count(x) > 1})
+    if clash:                                      # a/x.png and b/x.jpg would both become x.jb
+        raise SystemExit("--batch: these inputs would overwrite each other's output: %s" % ", ".join(clash))
     groups = {}                                    # images of one size share a device batch
     for path in args.batch:
-        im = Image.open(path)
-        groups.setdefault((im.width, im.height), []).append((path, im))
-    for members in groups.values():
-        blobs = jb.compress_images_rgb([im for _, im in members], config_for(members[0][1]))
-        for (path, _), blob in zip(members, blobs):
-            stem = os.path.splitext(os.path.basename(path))[0]
-            with open(os.path.join(args.outdir, stem + ".jb"), "wb") as f:
-                f.write(blob)
+        with Image.open(path) as im:               # (the header only: sizes; the pixels are read per sub-batch below)
+            groups.setdefault((im.width, im.height), []).append(path)
+    for (w, h), paths in groups.items():
+        per_batch = max(1, BATCH_PIXEL_BUDGET // (w * h))       # bounds the pinned staging buffer
+        for i in range(0, len(paths), per_batch):
+            part = paths[i:i + per_batch]
+            images = [Image.open(path) for path in part]
+            blobs = jb.compress_images_rgb(images, config_for(images[0]))
+            for path, im, blob in zip(part, images, blobs):
+                im.close()
+                stem = os.path.splitext(os.path.basename(path))[0]
+                with open(os.path.join(args.outdir, stem + ".jb"), "wb") as f:
+                    f.write(blob)
     return 0
 
 

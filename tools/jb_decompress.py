@@ -39,6 +39,10 @@ def main(argv=None):
         restore(args.infile, args.outfile)
         return 0
     os.makedirs(args.outdir, exist_ok=True)
+    stems = [os.path.splitext(os.path.basename(path))[0] for path in args.batch]
+    clash = sorted({x for x in stems if stems.count(x) > 1})
+    if clash:
+        raise SystemExit("--batch: these inputs would overwrite each other's output: %s" % ", ".join(clash))
     for path in args.batch:
         stem = os.path.splitext(os.path.basename(path))[0]
         restore(path, os.path.join(args.outdir, stem + ".png"))
