@@ -5,7 +5,7 @@
 // WARP of a persistent grid (one CTA of FL_WARPS warps per SM); the warp takes its blocks through every stage on
 // its own, so nothing in the kernel is CTA-wide after the table preload:
 //   * the (d bs) x (d bs) source tile of a block arrives in the warp's shared-memory slot by TMA (one elected lane,
-//     box 128 bytes x d bs rows, mbarrier completion); the load of the NEXT block is issued as soon as the box sums
+//     box 144 bytes x d bs rows from the 16-byte boundary at or before the block, mbarrier completion); the load of the NEXT block is issued as soon as the box sums
 //     have consumed the tile, so it overlaps the arithmetic.  Edge blocks (padding.py:8-12, dct_padding.py:8-9
 //     replicate, TMA would zero-fill) and unaligned planes are filled by the warp with clamped loads;
 //   * box sums (subsampling.py:9-11 without the division): lane j sums the bs x bs bytes of sample (i, j) with
@@ -36,7 +36,9 @@
 
 #define FL_WARPS 9
 #define FL_BLOCK_BUF_WORDS 96          // 384 bytes of packed output per block in shared memory; longer blocks: serial path
-#define FL_TILE_ROW 128                // bytes per tile row in shared memory (= TMA box width)
+#define FL_TILE_ROW 144                // bytes per tile row in shared memory = TMA box width: a tile row of up to 128 bytes
+                                       // plus up to 15 bytes in front of it -- the box has to start on a 16-byte
+                                       // boundary of the plane row (block columns are d bs bytes apart: 120 for config 3)
 #define FL_BIG_CAP 8                   // amplitudes beyond the 15-bit size field remembered per block (for the error report)
 
 struct FlLayout {
@@ -191,7 +193,7 @@ jb_fwd_large_kernel(const __grid_constant__ CUtensorMap tmap, const FlKernelArgs
         if (lane == 0) {
             if (dirty) ff_fence_proxy_async();
             ff_mbar_expect_tx(bar, (uint32_t)(side * FL_TILE_ROW));
-            ff_tma_load_3d(tile, &tmap, bx * side, by * side, plane, bar);
+            ff_tma_load_3d(tile, &tmap, (bx * side) & ~15, by * side, plane, bar);      // (16-byte aligned start)
         }
     };
     uint32_t phase = 0;
@@ -221,10 +223,12 @@ jb_fwd_large_kernel(const __grid_constant__ CUtensorMap tmap, const FlKernelArgs
         for (int gi = 0; gi < nvalid; ++gi) {
             const int blk = blk0 + gi;
             const int by = blk / hb, bx = blk - by * hb;
-            // ---- the tile of this block ----
+            // ---- the tile of this block; xoff: where the block's first column sits in the tile rows ----
+            int xoff = 0;
             if (in_flight) {
                 while (!ff_mbar_try_wait(bar, phase)) { }
                 phase ^= 1u;
+                xoff = (bx * side) & 15;
             } else {
                 // edge block, or no TMA: the reference's two-level edge replication, byte by byte
                 for (int idx = lane; idx < side * side; idx += 32) {
@@ -239,7 +243,7 @@ jb_fwd_large_kernel(const __grid_constant__ CUtensorMap tmap, const FlKernelArgs
             // ---- box sums -> Xe, Xo.  Lane j < D sums sample (i, j): bs rows x bs bytes from byte bs j, under byte masks ----
             {
                 const int j = lane < D ? lane : D - 1;
-                const int x0 = j * bs;
+                const int x0 = xoff + j * bs;
                 const int w0 = x0 >> 2, o0 = x0 & 3;
                 // masks of the up to three words a bs-byte run (bs <= 8) touches
                 const int nb0 = jb_min(4 - o0, bs);                               // bytes of the run in word 0
