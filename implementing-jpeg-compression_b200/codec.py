@@ -486,6 +486,36 @@ class BatchCodec:
     def compress_device(self, planes=None):
         return self._compress(self.d_planes if planes is None else planes, self.d_streams)
 
+    def capture_graphs(self):
+        """Capture the two device-resident calls on this object's own buffers (``d_planes`` -> ``d_streams`` ->
+        ``d_decoded``) into CUDA graphs, once; returns ``(compress_graph, decompress_graph, comp, status)``.
+
+        For single frames the calls are launch bound: three kernels each way whose launches from Python cost more
+        than they run.  Replaying ``compress_graph`` re-compresses whatever ``d_planes`` holds; ``decompress_graph``
+        decodes the streams the last compress replay left (their byte count may not exceed the count of the
+        capturing call -- it sizes the framing launch -- so capture with representative content)."""
+        if getattr(self, "_graphs", None) is not None:
+            return self._graphs
+        with torch.cuda.device(self.device):
+            comp = self.compress_device()                      # builds tables, sizes the decompress workspace
+            total = comp.total_bytes()
+            _, status = self.decompress_device(comp, total + (total >> 3) + 4096)
+            check_status(status)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                      # warm the allocator pools of the capture stream
+                c2 = self.compress_device()
+                self.decompress_device(c2, total + (total >> 3) + 4096)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g_c, g_d = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_c):
+                comp_g = self.compress_device()
+            with torch.cuda.graph(g_d, pool=g_c.pool()):
+                _, status_g = self.decompress_device(comp_g, total + (total >> 3) + 4096)
+        self._graphs = (g_c, g_d, comp_g, status_g)
+        return self._graphs
+
     def decompress_device(self, comp, total_bytes):
         lengths = comp.offsets[1:] - comp.offsets[:-1]
         return self._decompress(comp.data, comp.offsets[:-1], lengths, self.n_planes, int(total_bytes), self.d_decoded)

@@ -40,13 +40,14 @@
                                        // plus up to 15 bytes in front of it -- the box has to start on a 16-byte
                                        // boundary of the plane row (block columns are d bs bytes apart: 120 for config 3)
 #define FL_BIG_CAP 8                   // amplitudes beyond the 15-bit size field remembered per block (for the error report)
+#define FL_RQ_CAP 60                   // near-tie coefficients of a block queued for the warp's float64 re-evaluation
 
 struct FlLayout {
     int h;                  // d / 2
     int xs;                 // floats per row of Xe / Xo (and of the half matrix)
     int ts;                 // floats per row of Te / To
     size_t ch, qm, thr, zz;                         // CTA-wide tables
-    size_t warp0, tile, xe, te, crow, obuf, big, bar, warp_bytes, total;
+    size_t warp0, tile, xe, te, crow, obuf, big, rq, bar, warp_bytes, total;
 };
 
 __host__ __device__ inline FlLayout fl_layout(int d, int side) {
@@ -68,6 +69,7 @@ __host__ __device__ inline FlLayout fl_layout(int d, int side) {
     L.crow = w; w += jb_align_up((size_t)n * 2, 16);
     L.obuf = w; w += (size_t)(FL_BLOCK_BUF_WORDS + 2) * 4;
     L.big = w;  w += (size_t)(1 + 2 * FL_BIG_CAP) * 4;
+    L.rq = w;   w += 4 + (size_t)FL_RQ_CAP * 2 + 4;
     w = jb_align_up(w, 16);
     L.bar = w;  w += 16;
     L.warp_bytes = jb_align_up(w, 128);
@@ -149,6 +151,8 @@ jb_fwd_large_kernel(const __grid_constant__ CUtensorMap tmap, const FlKernelArgs
     uint32_t* obuf = (uint32_t*)(wbase + L.obuf);
     unsigned long long* bar = (unsigned long long*)(wbase + L.bar);
     int* big = (int*)(wbase + L.big);                    // [0] = count, then (zigzag position, amplitude) pairs
+    int* rq_count = (int*)(wbase + L.rq);                // near-tie coefficients of the current block: count, then natural indices
+    uint16_t* rq = (uint16_t*)(wbase + L.rq + 4);
 
     jb_pdl_trigger();
     const bool tables_const = (g.flags & JB_FLAG_REUSE_TABLES) != 0;
@@ -168,6 +172,7 @@ jb_fwd_large_kernel(const __grid_constant__ CUtensorMap tmap, const FlKernelArgs
     }
     if (lane == 0) {
         big[0] = 0;
+        *rq_count = 0;
         ff_mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -382,8 +387,13 @@ jb_fwd_large_kernel(const __grid_constant__ CUtensorMap tmap, const FlKernelArgs
                         const float tt = val + 12582912.0f;             // 1.5 * 2^23: rounds half-even to an integer
                         int qi = __float_as_int(tt) - 0x4B400000;
                         const float dd = fabsf(val - (tt - 12582912.0f));
-                        if (refine_on && fmaf(fabsf(val), 2.4e-7f, dd) > sThr[idx])
-                            qi = (int)rint(fl_refine<D>(sXe, idx, (bs << 8) | g.qmode, a.t.fA64, a.t.qrecip[idx]));
+                        if (refine_on && fmaf(fabsf(val), 2.4e-7f, dd) > sThr[idx]) {
+                            // within the fp32 error bound of a rounding tie: queued for the warp's float64 re-evaluation
+                            // below (a lane on its own would take ~30 times as long while 31 lanes wait for it)
+                            const int slot = atomicAdd(rq_count, 1);
+                            if (slot < FL_RQ_CAP) rq[slot] = (uint16_t)idx;
+                            else qi = (int)rint(fl_refine<D>(sXe, idx, (bs << 8) | g.qmode, a.t.fA64, a.t.qrecip[idx]));
+                        }
                         const int zp = sZz[idx];
                         if (MODE == 1) {
                             a.coeffs_out[((size_t)plane * g.nblocks + blk) * n + zp] = (int16_t)max(-32767, min(32767, qi));
@@ -400,8 +410,54 @@ jb_fwd_large_kernel(const __grid_constant__ CUtensorMap tmap, const FlKernelArgs
                     }
                 }
             }
-            if (MODE == 1) { __syncwarp(); continue; }
             __syncwarp();
+            // ---- float64 re-evaluation of the queued coefficients, the whole warp on one coefficient at a time, in the
+            //      reference's order (jb_refine.cuh): lane i sums row i against C[v] (ascending j, separate multiply and
+            //      add), then the 24 row results are combined against C[u] in ascending i ----
+            {
+                const int nreq = jb_min(*rq_count, FL_RQ_CAP);
+                if (nreq > 0) {
+                    const JbBoxMean mean(bs);
+                    const double* A64 = a.t.fA64;
+                    const int li = lane < D ? lane : D - 1;
+                    for (int t = 0; t < nreq; ++t) {
+                        const int idx = rq[t];
+                        const int u = idx / D, v = idx - u * D;
+                        double m = 0.0;
+                        for (int j = 0; j < D; ++j) {
+                            const int jj = j < H ? j : D - 1 - j;
+                            const float e = sXe[li * L.xs + jj], o = sXo[li * L.xs + jj];
+                            const double x = mean((double)((j < H ? e + o : e - o) * 0.5f));
+                            const double term = __dmul_rn(x, A64[v * D + j]);
+                            m = j == 0 ? term : __dadd_rn(m, term);
+                        }
+                        double y64 = 0.0;
+                        for (int i = 0; i < D; ++i) {
+                            const double term = __dmul_rn(__shfl_sync(0xffffffffu, m, i), A64[u * D + i]);
+                            y64 = i == 0 ? term : __dadd_rn(y64, term);
+                        }
+                        const double recip = a.t.qrecip[idx];
+                        const double f64 = g.qmode == JB_Q_QTABLE ? __dmul_rn(y64, recip) : g.qmode == JB_Q_DIVIDE ? __ddiv_rn(y64, recip) : y64;
+                        if (lane == 0) {
+                            int qi = (int)rint(f64);
+                            const int zp = sZz[idx];
+                            if (MODE == 1) {
+                                a.coeffs_out[((size_t)plane * g.nblocks + blk) * n + zp] = (int16_t)max(-32767, min(32767, qi));
+                            } else {
+                                if (qi > JB_MAX_AMP || qi < -JB_MAX_AMP) {
+                                    const int kk = atomicAdd(big, 1);
+                                    if (kk < FL_BIG_CAP) { big[1 + 2 * kk] = zp; big[2 + 2 * kk] = qi; }
+                                    qi = qi > 0 ? 32767 : -32767;
+                                }
+                                crow[zp] = (int16_t)qi;
+                            }
+                        }
+                    }
+                }
+                if (lane == 0) *rq_count = 0;
+                __syncwarp();
+            }
+            if (MODE == 1) continue;
             // ---- non-zero bitmap (zigzag order): lane w keeps word w ----
             uint32_t mybits = 0;
             #pragma unroll

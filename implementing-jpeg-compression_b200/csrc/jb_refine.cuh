@@ -15,15 +15,25 @@
 
 struct JbC64 { double r, i; };
 
+// sum / (bs * bs) as the reference's np.mean rounds it
+struct JbBoxMean {
+    double k;
+    bool pow2;
+    __device__ __forceinline__ explicit JbBoxMean(int bs) {
+        const int c = bs * bs;
+        pow2 = (c & (c - 1)) == 0;
+        k = pow2 ? 1.0 / (double)c : (double)c;
+    }
+    __device__ __forceinline__ double operator()(double sum) const { return pow2 ? __dmul_rn(sum, k) : __ddiv_rn(sum, k); }
+};
+
 __device__ __forceinline__ JbC64 jb_cadd(JbC64 a, JbC64 b) { return {__dadd_rn(a.r, b.r), __dadd_rn(a.i, b.i)}; }
 __device__ __forceinline__ JbC64 jb_csub(JbC64 a, JbC64 b) { return {__dsub_rn(a.r, b.r), __dsub_rn(a.i, b.i)}; }
 __device__ __forceinline__ JbC64 jb_rot90(JbC64 a) { return {a.i, -a.r}; }                       // forward: times -i
 
 // pocketfft (C++, as built into numpy >= 2.0) cfftp::pass8<fwd = true> with ido = l1 = 1, the whole plan of a
 // length-8 transform: PM / PMINPLACE / ROTX90 / ROTX45 / ROTX135 in its order, hsqt2 = sqrt(1/2) rounded.
-// (Not inlined, operands through memory: this path runs for a few coefficients in a thousand, and kept out of
-// line it costs the calling kernels no registers.)
-static __device__ __noinline__ void jb_pf_pass8(const JbC64* c, JbC64* ch) {
+__device__ __forceinline__ void jb_pf_pass8_body(const JbC64* c, JbC64* ch) {
     const double h = 0.70710678118654752440;
     JbC64 a0, a1, a2, a3, a4, a5, a6, a7, s, t;
     a1 = jb_cadd(c[1], c[5]); a5 = jb_csub(c[1], c[5]);
@@ -42,6 +52,34 @@ static __device__ __noinline__ void jb_pf_pass8(const JbC64* c, JbC64* ch) {
     s = jb_cadd(a4, a6); ch[1] = jb_cadd(s, a5); ch[5] = jb_csub(s, a5);
     s = jb_csub(a4, a6); ch[3] = jb_cadd(s, a7); ch[7] = jb_csub(s, a7);
 }
+// (Not inlined, operands through memory: the single-lane path runs for a few coefficients in a thousand, and kept
+// out of line it costs the calling kernels no registers.)
+static __device__ __noinline__ void jb_pf_pass8(const JbC64* c, JbC64* ch) { jb_pf_pass8_body(c, ch); }
+
+// The same transform of one 8 x 8 block by a whole warp: lanes 0..7 (and their copies 8..31) take one row each through
+// the radix-8 pass in registers, the eight values of column v meet by shuffles, and a second pass down that column gives
+// Re F[u][v].  X: the 64 box sums of the block (block_size 4: mean = sum / 16, exact).  Every lane of the warp must call;
+// every lane gets the value.  ~300 instructions, where a lane on its own needs nine passes through local memory.
+static __device__ __noinline__ double jb_pf_fft2_8x8_warp(const float* X, int u, int v) {
+    const int i = threadIdx.x & 7;
+    JbC64 c[8], ch[8];
+    #pragma unroll
+    for (int j = 0; j < 8; ++j) { c[j].r = __dmul_rn((double)X[i * 8 + j], 0.0625); c[j].i = 0.0; }
+    jb_pf_pass8_body(c, ch);
+    JbC64 pick = ch[0];
+    #pragma unroll
+    for (int k = 1; k < 8; ++k) if (k == v) pick = ch[k];
+    #pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        c[r].r = __shfl_sync(0xffffffffu, pick.r, r);
+        c[r].i = __shfl_sync(0xffffffffu, pick.i, r);
+    }
+    jb_pf_pass8_body(c, ch);
+    double y = ch[0].r;
+    #pragma unroll
+    for (int k = 1; k < 8; ++k) if (k == u) y = ch[k].r;
+    return y;
+}
 
 // X: the d x d box sums of the block (exact integers, as int or float; anything indexable by i * d + j); returns the value the reference hands to
 // np.round for coefficient (u, v).  A64 / B64: the fp64 transform matrices of jb_tables.cu; recip: qrecip[u*d+v].
@@ -49,14 +87,16 @@ static __device__ __noinline__ void jb_pf_pass8(const JbC64* c, JbC64* ch) {
 template <typename XA>
 __device__ __forceinline__ double jb_refine_f64(XA X, int u, int v, int d, int bs, int transform, int qmode,
                                              const double* A64, const double* B64, double recip) {
-    const double bs2 = (double)(bs * bs);          // np.mean: exact integer sum / count (subsampling.py:9-11)
+    // np.mean: exact integer sum / count (subsampling.py:9-11).  A power-of-two count divides exactly, so the
+    // (slow) fp64 division can be a multiplication by the exact reciprocal with the same result.
+    const JbBoxMean mean(bs);
     double y;
     if (transform == JB_TRANSFORM_DFT && d == 8) {
         JbC64 col[8];
         for (int i = 0; i < 8; ++i) {
             JbC64 c[8], ch[8];
             #pragma unroll
-            for (int j = 0; j < 8; ++j) { c[j].r = __ddiv_rn((double)X[i * 8 + j], bs2); c[j].i = 0.0; }
+            for (int j = 0; j < 8; ++j) { c[j].r = mean((double)X[i * 8 + j]); c[j].i = 0.0; }
             jb_pf_pass8(c, ch);
             JbC64 pick = ch[0];
             #pragma unroll
@@ -73,7 +113,7 @@ __device__ __forceinline__ double jb_refine_f64(XA X, int u, int v, int d, int b
         for (int i = 0; i < d; ++i) {
             double mc = 0.0, ms = 0.0;
             for (int j = 0; j < d; ++j) {
-                const double x = __ddiv_rn((double)X[i * d + j], bs2);
+                const double x = mean((double)X[i * d + j]);
                 mc = __dadd_rn(mc, __dmul_rn(A64[v * d + j], x));
                 ms = __dadd_rn(ms, __dmul_rn(B64[v * d + j], x));
             }
@@ -82,8 +122,8 @@ __device__ __forceinline__ double jb_refine_f64(XA X, int u, int v, int d, int b
     } else {
         y = 0.0;
         for (int i = 0; i < d; ++i) {
-            double m = __dmul_rn(__ddiv_rn((double)X[i * d], bs2), A64[v * d]);
-            for (int j = 1; j < d; ++j) m = __dadd_rn(m, __dmul_rn(__ddiv_rn((double)X[i * d + j], bs2), A64[v * d + j]));
+            double m = __dmul_rn(mean((double)X[i * d]), A64[v * d]);
+            for (int j = 1; j < d; ++j) m = __dadd_rn(m, __dmul_rn(mean((double)X[i * d + j]), A64[v * d + j]));
             const double term = __dmul_rn(m, A64[u * d + i]);
             y = i == 0 ? term : __dadd_rn(y, term);
         }
