@@ -356,39 +356,41 @@ def run_ours(args, rank, world, local_rank):
                     raise RuntimeError("step graph replay differs from the direct calls")
                 run_step = g_s.replay
                 launch_mode = "cuda graph (one per step: compress + decompress)"
-                if args.streams == 2:
-                    # Consecutive steps are independent batches: a second codec object (own buffers, own workspaces)
-                    # on a second CUDA stream takes every other step, so the head of one step overlaps the tail of
+                if args.streams >= 2:
+                    # Consecutive steps are independent batches: further codec objects (own buffers, own workspaces),
+                    # each on its own CUDA stream, take the steps in turn, so the head of one step overlaps the tail of
                     # the step before it.  Every step still compresses and decompresses this rank's whole batch.
-                    bc2 = jb.BatchCodec(cfg, n_planes, device=device, flags=bc.flags)
-                    bc2.d_planes.copy_(bc.d_planes)
-                    comp2 = bc2.compress_device()
-                    if comp2.total_bytes() != total_bytes:
-                        raise RuntimeError("second codec disagrees on the stream size")
-                    out2, st2 = bc2.decompress_device(comp2, total_bytes)
-                    jb.check_status(st2)
-                    side.wait_stream(torch.cuda.current_stream())
-                    with torch.cuda.stream(side):
-                        bc2.compress_device(); bc2.decompress_device(comp2, total_bytes)
-                    torch.cuda.current_stream().wait_stream(side)
-                    torch.cuda.synchronize()
-                    g_s2 = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g_s2):
-                        comp_s2 = bc2.compress_device()
-                        out_s2, status_s2 = bc2.decompress_device(comp_s2, total_bytes)
-                    g_s2.replay()
-                    torch.cuda.synchronize()
-                    jb.check_status(comp_s2.status); jb.check_status(status_s2)
-                    if not torch.equal(out_s2, out_s):
-                        raise RuntimeError("second codec decodes differently")
-                    s_a, s_b = torch.cuda.Stream(), torch.cuda.Stream()
+                    graphs, streams_, keep = [g_s], [torch.cuda.Stream()], []
+                    for extra in range(args.streams - 1):
+                        bcx = jb.BatchCodec(cfg, n_planes, device=device, flags=bc.flags)
+                        bcx.d_planes.copy_(bc.d_planes)
+                        compx = bcx.compress_device()
+                        if compx.total_bytes() != total_bytes:
+                            raise RuntimeError("another codec object disagrees on the stream size")
+                        _, stx = bcx.decompress_device(compx, total_bytes)
+                        jb.check_status(stx)
+                        side.wait_stream(torch.cuda.current_stream())
+                        with torch.cuda.stream(side):
+                            bcx.compress_device(); bcx.decompress_device(compx, total_bytes)
+                        torch.cuda.current_stream().wait_stream(side)
+                        torch.cuda.synchronize()
+                        g_x = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g_x):
+                            comp_x = bcx.compress_device()
+                            out_x, status_x = bcx.decompress_device(comp_x, total_bytes)
+                        g_x.replay()
+                        torch.cuda.synchronize()
+                        jb.check_status(comp_x.status); jb.check_status(status_x)
+                        if not torch.equal(out_x, out_s):
+                            raise RuntimeError("another codec object decodes differently")
+                        graphs.append(g_x); streams_.append(torch.cuda.Stream()); keep.append((bcx, comp_x, out_x, status_x))
 
-                    def run_pair(step, _ga=g_s, _gb=g_s2, _sa=s_a, _sb=s_b):
-                        with torch.cuda.stream(_sa if step % 2 == 0 else _sb):
-                            (_ga if step % 2 == 0 else _gb).replay()
-                    two_streams = (s_a, s_b, run_pair)
-                    launch_mode = ("cuda graph (one per step: compress + decompress); steps alternate between two codec "
-                                   "objects on two CUDA streams")
+                    def run_turn(step, _g=graphs, _s=streams_):
+                        with torch.cuda.stream(_s[step % len(_s)]):
+                            _g[step % len(_g)].replay()
+                    two_streams = (streams_, run_turn, keep)
+                    launch_mode = ("cuda graph (one per step: compress + decompress); steps take turns on %d codec objects, "
+                                   "each on its own CUDA stream" % len(graphs))
         except Exception as exc:                          # noqa: BLE001 -- report and fall back to direct launches
             launch_mode = "direct (graph capture failed: %s)" % str(exc).splitlines()[0][:120]
             run_c, run_d, run_step, two_streams = direct_c, direct_d, None, None
@@ -417,11 +419,13 @@ def run_ours(args, rank, world, local_rank):
                 for step in range(count):
                     run_step()
                 return
-            s_a, s_b, run_pair = two_streams
-            s_a.wait_stream(cur); s_b.wait_stream(cur)
+            streams_, run_turn, _keep = two_streams
+            for st in streams_:
+                st.wait_stream(cur)
             for step in range(count):
-                run_pair(step)
-            cur.wait_stream(s_a); cur.wait_stream(s_b)
+                run_turn(step)
+            for st in streams_:
+                cur.wait_stream(st)
         run_steps(Wm)
         barrier()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
@@ -540,7 +544,7 @@ def run_ours(args, rank, world, local_rank):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
             "compress_mps": mp_total / (t_c * 1e-3), "decompress_mps": mp_total / (t_d * 1e-3),
             "ms_compress": t_c, "ms_decompress": t_d, "ms_per_step_two_graphs": t_split, "stream_bytes": stream_total,
-            "pdl": bool(args.pdl), "streams": 2 if two_streams is not None else 1,
+            "pdl": bool(args.pdl), "streams": len(two_streams[0]) if two_streams is not None else 1,
             "decoder_serial_fallback_streams_rank0": serial_streams, "launch": launch_mode,
             "bytes_per_pixel": stream_total / (N_IMAGES * H * W),
             # achieved = algorithmic bytes of one launch / the fused kernel's own duration (CUDA events recorded by the
@@ -657,8 +661,8 @@ def main():
                     help="launch the kernels without programmatic dependent launch (JB_FLAG_PDL is the default)")
     ap.add_argument("--call-graphs", dest="step_graph", action="store_false",
                     help="time one CUDA graph per library call instead of one per step (compress + decompress)")
-    ap.add_argument("--streams", type=int, default=2, choices=[1, 2],
-                    help="2: consecutive steps alternate between two codec objects on two CUDA streams (default); 1: one stream")
+    ap.add_argument("--streams", type=int, default=2, choices=[1, 2, 3, 4],
+                    help="n > 1: consecutive steps take turns on n codec objects, each on its own CUDA stream (default 2); 1: one stream")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
     args = ap.parse_args()

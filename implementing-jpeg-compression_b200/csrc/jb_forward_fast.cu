@@ -226,9 +226,14 @@ jb_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfKernelArgs 
     if (tables_const) jb_pdl_wait();                           // from here on: data the kernels before this one wrote
     const int P = jb_ctrl_parity(a);                           // which set of the control block this call uses
     unsigned* const ticket = jb_ctrl_ticket(a, P);
+    // The first chunk of every warp is dealt statically, CTA-major (warp w of CTA b: chunk b + gridDim w): a small input
+    // (one 4K frame: 765 chunks) then spreads over all SMs instead of filling the first few; the chunks behind that first
+    // round are claimed from the ticket counter.
+    const unsigned static_chunks = gridDim.x * FF_WARPS;
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.ctrl[1] = (unsigned)P;        // the parity, for the kernels behind this one
     auto claim = [&]() -> unsigned {
         unsigned c = 0;
-        if (lane == 0) { c = atomicAdd(ticket, 1u); jb_ctrl_note_first(a, P, c); }
+        if (lane == 0) c = static_chunks + atomicAdd(ticket, 1u);
         return __shfl_sync(0xffffffffu, c, 0);
     };
 
@@ -238,7 +243,7 @@ jb_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfKernelArgs 
     // Chunk-level state only moves at chunk boundaries; per tile only (bx, by, kind) do.
     FfCursor ck, nk;
     {
-        const unsigned first = claim();
+        const unsigned first = blockIdx.x + gridDim.x * (unsigned)warp;
         if (first >= a.n_chunks) return;
         ff_cursor_set(ck, first, g);
     }
@@ -563,7 +568,7 @@ static cudaError_t jb_fwd_fast_launch_t(const CUtensorMap& map, const FfKernelAr
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jb_fwd_fast_kernel<DFT, MODE>, FF_WARPS * 32, smem);
     if (per_sm < 1) per_sm = 1;
-    unsigned want = (ka.a.n_chunks + FF_WARPS - 1) / FF_WARPS;
+    unsigned want = ka.a.n_chunks;                              // (warps without a chunk leave at once)
     unsigned grid = want < (unsigned)(sms * per_sm) ? want : (unsigned)(sms * per_sm);
     if (grid == 0) return cudaSuccess;
     return jb_launch_ex(jb_fwd_fast_kernel<DFT, MODE>, dim3(grid), dim3(FF_WARPS * 32), smem, s,

@@ -127,14 +127,15 @@ __device__ __noinline__ unsigned fl_pack_serial(const int16_t* c, const uint32_t
     return bw.finish();
 }
 
-template <int D, int MODE>
+// BS: block_size as a compile-time constant (5: config 3) for fully unrolled box sums, or 0: any block_size at run time.
+template <int D, int MODE, int BS>
 __global__ void __launch_bounds__(FL_WARPS * 32, 1)
 jb_fwd_large_kernel(const __grid_constant__ CUtensorMap tmap, const FlKernelArgs ka) {
     extern __shared__ __align__(128) unsigned char smem[];
     const JbFwdArgs& a = ka.a;
     const JbGeom& g = a.g;
     constexpr int n = D * D, H = D / 2, RT = D / 8, KT = D / 4, NW = n / 32;
-    const int bs = g.bs, side = D * bs;
+    const int bs = BS ? BS : g.bs, side = D * bs;
     const FlLayout L = fl_layout(D, side);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* sCH = (float*)(smem + L.ch);
@@ -186,9 +187,13 @@ jb_fwd_large_kernel(const __grid_constant__ CUtensorMap tmap, const FlKernelArgs
     const int hb = g.hb;
     const int rg = lane >> 2, kg = lane & 3, kpar = kg >> 1, khalf = kg & 1;
 
+    // first chunk of every warp dealt statically, CTA-major, so that a single frame spreads over all SMs; the rest
+    // from the ticket counter (as in jb_forward_fast.cu)
+    const unsigned static_chunks = gridDim.x * (blockDim.x >> 5);
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.ctrl[1] = (unsigned)P;
     auto claim = [&]() -> unsigned {
         unsigned c = 0;
-        if (lane == 0) { c = atomicAdd(ticket, 1u); jb_ctrl_note_first(a, P, c); }
+        if (lane == 0) c = static_chunks + atomicAdd(ticket, 1u);
         return __shfl_sync(0xffffffffu, c, 0);
     };
     // a block whose whole tile lies inside the image can come by TMA
@@ -203,7 +208,7 @@ jb_fwd_large_kernel(const __grid_constant__ CUtensorMap tmap, const FlKernelArgs
     };
     uint32_t phase = 0;
 
-    unsigned chunk = claim();
+    unsigned chunk = blockIdx.x + gridDim.x * (unsigned)warp;
     // (plane, blk0, nvalid) of the chunk, and the state of the tile slot: has the load of the chunk's first block
     // been issued already (by the previous chunk's last block)?
     bool first_in_flight = false;
@@ -259,19 +264,46 @@ jb_fwd_large_kernel(const __grid_constant__ CUtensorMap tmap, const FlKernelArgs
                 const uint32_t m2 = nb2 <= 0 ? 0u : (0x01010101u >> (8 * (4 - nb2)));
                 const uint32_t* t32 = (const uint32_t*)tile + w0;
                 const int partner = D - 1 - lane;                                  // (lanes < D)
-                #pragma unroll 2
-                for (int i = 0; i < D; ++i) {
-                    const uint32_t* row = t32 + (size_t)i * bs * (FL_TILE_ROW / 4);
-                    uint32_t s = 0x4B000000u;                  // bit pattern of 2^23: exact int -> float without a conversion
-                    for (int k = 0; k < bs; ++k) {
-                        s = __dp4a(row[0], m0, s);
-                        s = __dp4a(row[1], m1, s);
-                        if (m2) s = __dp4a(row[2], m2, s);
-                        row += FL_TILE_ROW / 4;
+                constexpr int RW = FL_TILE_ROW / 4;                                // words per tile row
+                if (BS > 0 && BS <= 5) {
+                    // compile-time block_size whose runs touch two words at most: everything unrolled, four sample rows
+                    // (8 BS independent loads, 4 accumulator chains) in flight at a time
+                    #pragma unroll
+                    for (int i0 = 0; i0 < D; i0 += 4) {
+                        uint32_t acc[4];
+                        #pragma unroll
+                        for (int ii = 0; ii < 4; ++ii) {
+                            const uint32_t* row = t32 + (i0 + ii) * BS * RW;
+                            uint32_t sa = 0x4B000000u, sb = 0u;    // 0x4B000000 + s is the bit pattern of 2^23 + s: exact int -> float
+                            #pragma unroll
+                            for (int k = 0; k < BS; ++k) {
+                                sa = __dp4a(row[k * RW], m0, sa);
+                                sb = __dp4a(row[k * RW + 1], m1, sb);
+                            }
+                            acc[ii] = sa + sb;
+                        }
+                        #pragma unroll
+                        for (int ii = 0; ii < 4; ++ii) {
+                            const float f = __uint_as_float(acc[ii]) - 8388608.0f;
+                            const float p = __shfl_sync(0xffffffffu, f, partner & 31);
+                            if (lane < H) { sXe[(i0 + ii) * L.xs + lane] = f + p; sXo[(i0 + ii) * L.xs + lane] = f - p; }
+                        }
                     }
-                    const float f = __uint_as_float(s) - 8388608.0f;
-                    const float p = __shfl_sync(0xffffffffu, f, partner & 31);
-                    if (lane < H) { sXe[i * L.xs + lane] = f + p; sXo[i * L.xs + lane] = f - p; }
+                } else {
+                    #pragma unroll 2
+                    for (int i = 0; i < D; ++i) {
+                        const uint32_t* row = t32 + (size_t)i * bs * RW;
+                        uint32_t sacc = 0x4B000000u;
+                        for (int k = 0; k < bs; ++k) {
+                            sacc = __dp4a(row[0], m0, sacc);
+                            sacc = __dp4a(row[1], m1, sacc);
+                            if (m2) sacc = __dp4a(row[2], m2, sacc);
+                            row += RW;
+                        }
+                        const float f = __uint_as_float(sacc) - 8388608.0f;
+                        const float p = __shfl_sync(0xffffffffu, f, partner & 31);
+                        if (lane < H) { sXe[i * L.xs + lane] = f + p; sXo[i * L.xs + lane] = f - p; }
+                    }
                 }
             }
             __syncwarp();
@@ -376,36 +408,53 @@ jb_fwd_large_kernel(const __grid_constant__ CUtensorMap tmap, const FlKernelArgs
                         }
                     }
                 }
+                // quantise all RT x KT outputs straight through (no branches); the rare cases -- a value within the fp32
+                // error bound of a rounding tie, an amplitude beyond the 15-bit size field -- are collected in bit masks
+                // and dealt with behind the loop
+                unsigned nearmask = 0, bigmask = 0;
+                int16_t* const cout = MODE == 1 ? a.coeffs_out + ((size_t)plane * g.nblocks + blk) * n : crow;
                 #pragma unroll
                 for (int r = 0; r < RT; ++r) {
                     const int u = 2 * (ug * RT + r) + upar;
                     #pragma unroll
                     for (int q = 0; q < KT; ++q) {
-                        const int k = kg * KT + q;
-                        const int idx = u * D + k;
+                        const int idx = u * D + kg * KT + q;
                         const float val = y[r][q] * sQm[idx];
                         const float tt = val + 12582912.0f;             // 1.5 * 2^23: rounds half-even to an integer
-                        int qi = __float_as_int(tt) - 0x4B400000;
+                        const int qi = __float_as_int(tt) - 0x4B400000;
                         const float dd = fabsf(val - (tt - 12582912.0f));
-                        if (refine_on && fmaf(fabsf(val), 2.4e-7f, dd) > sThr[idx]) {
-                            // within the fp32 error bound of a rounding tie: queued for the warp's float64 re-evaluation
-                            // below (a lane on its own would take ~30 times as long while 31 lanes wait for it)
+                        if (fmaf(fabsf(val), 2.4e-7f, dd) > sThr[idx]) nearmask |= 1u << (r * KT + q);
+                        if (qi > JB_MAX_AMP || qi < -JB_MAX_AMP) bigmask |= 1u << (r * KT + q);
+                        cout[sZz[idx]] = (int16_t)max(-32767, min(32767, qi));
+                        if (bigmask >> (r * KT + q) & 1u) y[r][q] = __int_as_float(qi);       // (kept for the report below)
+                    }
+                }
+                if (!refine_on) nearmask = 0;
+                if (nearmask | bigmask) {
+                    for (unsigned mm = nearmask | bigmask; mm; mm &= mm - 1u) {
+                        const int t = __ffs((int)mm) - 1, r = t / KT, q = t - r * KT;
+                        const int idx = (2 * (ug * RT + r) + upar) * D + kg * KT + q;
+                        if (nearmask >> t & 1u) {
+                            // queued for the warp's float64 re-evaluation below (a lane on its own would take ~30 times as
+                            // long while 31 lanes wait for it)
                             const int slot = atomicAdd(rq_count, 1);
-                            if (slot < FL_RQ_CAP) rq[slot] = (uint16_t)idx;
-                            else qi = (int)rint(fl_refine<D>(sXe, idx, (bs << 8) | g.qmode, a.t.fA64, a.t.qrecip[idx]));
-                        }
-                        const int zp = sZz[idx];
-                        if (MODE == 1) {
-                            a.coeffs_out[((size_t)plane * g.nblocks + blk) * n + zp] = (int16_t)max(-32767, min(32767, qi));
-                        } else {
-                            if (qi > JB_MAX_AMP || qi < -JB_MAX_AMP) {
-                                // BadRleCodeError in the reference (util.py:170-171): remember the true amplitude for the
-                                // report the run-length stage makes, store a saturated value
+                            if (slot < FL_RQ_CAP) { rq[slot] = (uint16_t)idx; continue; }
+                            const int qi = (int)rint(fl_refine<D>(sXe, idx, (bs << 8) | g.qmode, a.t.fA64, a.t.qrecip[idx]));
+                            cout[sZz[idx]] = (int16_t)max(-32767, min(32767, qi));
+                            if (MODE != 1 && (qi > JB_MAX_AMP || qi < -JB_MAX_AMP)) {
                                 const int kk = atomicAdd(big, 1);
-                                if (kk < FL_BIG_CAP) { big[1 + 2 * kk] = zp; big[2 + 2 * kk] = qi; }
-                                qi = qi > 0 ? 32767 : -32767;
+                                if (kk < FL_BIG_CAP) { big[1 + 2 * kk] = sZz[idx]; big[2 + 2 * kk] = qi; }
                             }
-                            crow[zp] = (int16_t)qi;
+                        } else if (MODE != 1) {
+                            // BadRleCodeError in the reference (util.py:170-171): remember the true amplitude for the report
+                            // the run-length stage makes (the stored value is saturated)
+                            int qi = 0;
+                            #pragma unroll
+                            for (int rr = 0; rr < RT; ++rr)
+                                #pragma unroll
+                                for (int qq = 0; qq < KT; ++qq) if (rr * KT + qq == t) qi = __float_as_int(y[rr][qq]);
+                            const int kk = atomicAdd(big, 1);
+                            if (kk < FL_BIG_CAP) { big[1 + 2 * kk] = sZz[idx]; big[2 + 2 * kk] = qi; }
                         }
                     }
                 }
@@ -465,83 +514,92 @@ jb_fwd_large_kernel(const __grid_constant__ CUtensorMap tmap, const FlKernelArgs
                 const uint32_t m = __ballot_sync(0xffffffffu, crow[w * 32 + lane] != 0);
                 if (lane == w) mybits = m;
             }
-            // ---- run-length codes of the whole warp: lane w codes the non-zeros of its 32 positions ----
-            // previous non-zero position before word w: the highest set bit of the nearest non-empty lower word
-            int last_here = mybits ? lane * 32 + 31 - __clz((int)mybits) : -1;
-            int prev_before = -1;
-            {
-                int run_max = last_here;                                   // inclusive max-scan over lanes
-                #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int v = __shfl_up_sync(0xffffffffu, run_max, o);
-                    if (lane >= o) run_max = max(run_max, v);
+            // ---- run-length codes by the whole warp, 32 zigzag positions at a time (empty words cost nothing): lane l
+            //      of non-empty word w looks at position 32 w + l; the previous non-zero is the nearest set bit below it
+            //      (or the last one of the words before), a warp scan of the code lengths gives the bit offsets, and the
+            //      codes are OR-ed into the block's bytes in shared memory ----
+            for (int i = lane; i < FL_BLOCK_BUF_WORDS + 2; i += 32) obuf[i] = 0u;
+            __syncwarp();
+            unsigned bitpos = 0;                       // bits emitted so far (warp-uniform)
+            int prev = -1;                             // last non-zero position of the words before (warp-uniform)
+            bool any_bad = false, overflow = false;
+            for (uint32_t wleft = __ballot_sync(0xffffffffu, mybits != 0); wleft; wleft &= wleft - 1u) {
+                const int w = __ffs((int)wleft) - 1;
+                const uint32_t word = __shfl_sync(0xffffffffu, mybits, w);
+                const int p = w * 32 + lane;
+                const bool nz = (word >> lane) & 1u;
+                const uint32_t below = word & ((1u << lane) - 1u);
+                const int pv = below ? w * 32 + 31 - __clz((int)below) : prev;
+                const int amp = nz ? (int)crow[p] : 0;
+                const uint32_t mag = (uint32_t)(amp < 0 ? -amp : amp);
+                int run = p - pv - 1;
+                const bool bad = nz && mag > (uint32_t)JB_MAX_AMP;        // BadRleCodeError: nothing is emitted (as in the reference)
+                const int size = 33 - __clz((int)(mag | 1u));             // bit length + 1
+                const unsigned nzrl = (unsigned)(run / JB_MAX_RUN);
+                const unsigned len = (nz && !bad) ? 8u * nzrl + 8u + (unsigned)size : 0u;
+                unsigned total;
+                unsigned off = bitpos + jb_warp_excl_scan(len, lane, &total);
+                if (bitpos + total + 8u > FL_BLOCK_BUF_WORDS * 32u) { overflow = true; break; }      // (warp-uniform)
+                if (bad) {
+                    long long true_amp = amp;
+                    const int nb = jb_min(big[0], FL_BIG_CAP);
+                    for (int k = 0; k < nb; ++k)
+                        if (big[1 + 2 * k] == p) true_amp = big[2 + 2 * k];
+                    jb_report_bad_code(jb_ctrl_status(a, P), (unsigned long long)plane * g.nblocks + blk, p, run % JB_MAX_RUN, true_amp);
                 }
-                prev_before = __shfl_up_sync(0xffffffffu, run_max, 1);
-                if (lane == 0) prev_before = -1;
-            }
-            // pass 1: bits of my codes
-            unsigned mybitlen = 0;
-            bool bad_amp = false;
-            {
-                int prev = prev_before;
-                for (uint32_t m = mybits; m; m &= m - 1u) {
-                    const int p = lane * 32 + __ffs((int)m) - 1;
-                    const int amp = crow[p];
-                    const uint32_t mag = (uint32_t)(amp < 0 ? -amp : amp);
-                    const int run = p - prev - 1;
-                    prev = p;
-                    if (mag > (uint32_t)JB_MAX_AMP) {                          // nothing is emitted (as in the reference)
-                        long long true_amp = amp;
-                        const int nb = jb_min(big[0], FL_BIG_CAP);
-                        for (int k = 0; k < nb; ++k)
-                            if (big[1 + 2 * k] == p) true_amp = big[2 + 2 * k];
-                        jb_report_bad_code(jb_ctrl_status(a, P), (unsigned long long)plane * g.nblocks + blk, p, run % JB_MAX_RUN, true_amp);
-                        bad_amp = true;
-                        continue;
+                if (len) {
+                    for (unsigned z = 0; z < nzrl; ++z) {                       // (15, 0): the byte 0xF0
+                        atomicOr(obuf + (off >> 5), 0xF0000000u >> (off & 31u));
+                        if ((off & 31u) > 24u) atomicOr(obuf + (off >> 5) + 1, 0xF0000000u << (32u - (off & 31u)));
+                        off += 8u;
                     }
-                    mybitlen += 8u * (unsigned)(run / JB_MAX_RUN) + 8u + (unsigned)(33 - __clz((int)mag));
-                }
-            }
-            unsigned total_bits;
-            unsigned bitoff = jb_warp_excl_scan(mybitlen, lane, &total_bits);
-            total_bits += 8u;                                                   // EOB
-            const unsigned blen = (total_bits + 7u) >> 3;
-            const bool any_bad = __any_sync(0xffffffffu, bad_amp);
-            uint8_t* dst = slot + chunk_bytes;
-            if (blen <= FL_BLOCK_BUF_WORDS * 4u) {
-                for (int i = lane; i < FL_BLOCK_BUF_WORDS + 2; i += 32) obuf[i] = 0u;
-                __syncwarp();
-                int prev = prev_before;
-                for (uint32_t m = mybits; m; m &= m - 1u) {
-                    const int p = lane * 32 + __ffs((int)m) - 1;
-                    const int amp = crow[p];
-                    const uint32_t mag = (uint32_t)(amp < 0 ? -amp : amp);
-                    int run = p - prev - 1;
-                    prev = p;
-                    if (mag > (uint32_t)JB_MAX_AMP) continue;
-                    while (run >= JB_MAX_RUN) {                               // (15, 0): the byte 0xF0
-                        atomicOr(obuf + (bitoff >> 5), 0xF0000000u >> (bitoff & 31u));
-                        if ((bitoff & 31u) > 24u) atomicOr(obuf + (bitoff >> 5) + 1, 0xF0000000u << (32u - (bitoff & 31u)));
-                        bitoff += 8u;
-                        run -= JB_MAX_RUN;
-                    }
-                    const int size = 33 - __clz((int)mag);
+                    run -= (int)nzrl * JB_MAX_RUN;
                     const uint32_t code = ((((uint32_t)run << 4) | (uint32_t)size) << size) | ((amp > 0 ? 1u : 0u) << (size - 1)) | mag;
-                    const unsigned len = 8u + (unsigned)size;
-                    const unsigned long long v64 = (unsigned long long)code << (64u - len - (bitoff & 31u));
-                    atomicOr(obuf + (bitoff >> 5), (uint32_t)(v64 >> 32));
-                    if ((uint32_t)v64) atomicOr(obuf + (bitoff >> 5) + 1, (uint32_t)v64);
-                    bitoff += len;
+                    const unsigned cl = 8u + (unsigned)size;
+                    const unsigned long long v64 = (unsigned long long)code << (64u - cl - (off & 31u));
+                    atomicOr(obuf + (off >> 5), (uint32_t)(v64 >> 32));
+                    if ((uint32_t)v64) atomicOr(obuf + (off >> 5) + 1, (uint32_t)v64);
                 }
+                any_bad = any_bad || __any_sync(0xffffffffu, bad);
+                bitpos += total;
+                prev = w * 32 + 31 - __clz((int)word);
+            }
+            uint8_t* dst = slot + chunk_bytes;
+            unsigned blen;
+            if (!overflow) {
+                blen = (bitpos + 8u + 7u) >> 3;                                 // + EOB, padded to the byte
                 __syncwarp();
                 // bytes of the block -> the chunk's slot (big-endian words = stream order)
                 for (unsigned i = lane; i < blen; i += 32) dst[i] = (uint8_t)(obuf[i >> 2] >> (24u - 8u * (i & 3u)));
             } else {
-                // a block longer than the shared-memory buffer: lane 0 packs it serially, straight to the slot
+                // a block longer than the shared-memory buffer: lane 0 packs it serially, straight to the slot (amplitudes
+                // that do not fit are skipped there as well; they are reported by the code above only up to the overflow,
+                // so report the rest here)
                 __shared__ uint32_t s_mask[FL_WARPS][32];
                 if (lane < NW) s_mask[warp][lane] = mybits;
                 __syncwarp();
-                if (lane == 0) fl_pack_serial(crow, s_mask[warp], NW, dst);
+                unsigned bl = 0;
+                if (lane == 0) {
+                    bl = fl_pack_serial(crow, s_mask[warp], NW, dst);
+                    int pr = -1;
+                    for (int wi = 0; wi < NW; ++wi)
+                        for (uint32_t m = s_mask[warp][wi]; m; m &= m - 1u) {
+                            const int p = wi * 32 + __ffs((int)m) - 1;
+                            const int amp = crow[p];
+                            if (amp > JB_MAX_AMP || amp < -JB_MAX_AMP) {
+                                long long true_amp = amp;
+                                const int nb = jb_min(big[0], FL_BIG_CAP);
+                                for (int k = 0; k < nb; ++k)
+                                    if (big[1 + 2 * k] == p) true_amp = big[2 + 2 * k];
+                                jb_report_bad_code(jb_ctrl_status(a, P), (unsigned long long)plane * g.nblocks + blk, p,
+                                                   (p - pr - 1) % JB_MAX_RUN, true_amp);
+                                any_bad = true;
+                            }
+                            pr = p;
+                        }
+                }
+                blen = __shfl_sync(0xffffffffu, bl, 0);
+                any_bad = __any_sync(0xffffffffu, any_bad);
             }
             chunk_bytes += blen;
             if (any_bad && lane == 0) big[0] = 0;
@@ -554,27 +612,27 @@ jb_fwd_large_kernel(const __grid_constant__ CUtensorMap tmap, const FlKernelArgs
 }
 
 // ---- host side ----------------------------------------------------------------------------------
-template <int D, int MODE>
+template <int D, int MODE, int BS>
 static cudaError_t fl_launch_t(const CUtensorMap& map, const FlKernelArgs& ka, cudaStream_t s) {
     const size_t smem = fl_layout(D, D * ka.a.g.bs).total;
-    cudaError_t e = cudaFuncSetAttribute(jb_fwd_large_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(jb_fwd_large_kernel<D, MODE, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const unsigned want = (ka.a.n_chunks + FL_WARPS - 1) / FL_WARPS;
+    const unsigned want = ka.a.n_chunks;
     const unsigned grid = want < (unsigned)sms ? want : (unsigned)sms;
     if (grid == 0) return cudaSuccess;
-    return jb_launch_ex(jb_fwd_large_kernel<D, MODE>, dim3(grid), dim3(FL_WARPS * 32), smem, s,
+    return jb_launch_ex(jb_fwd_large_kernel<D, MODE, BS>, dim3(grid), dim3(FL_WARPS * 32), smem, s,
                         (ka.a.g.flags & JB_FLAG_PDL) != 0, map, ka);
 }
 
 template <int MODE>
 static cudaError_t fl_launch_d(const CUtensorMap& map, const FlKernelArgs& ka, cudaStream_t s) {
     switch (ka.a.g.d) {
-    case 16: return fl_launch_t<16, MODE>(map, ka, s);
-    case 24: return fl_launch_t<24, MODE>(map, ka, s);
-    default: return fl_launch_t<32, MODE>(map, ka, s);
+    case 16: return fl_launch_t<16, MODE, 0>(map, ka, s);
+    case 24: return ka.a.g.bs == 5 ? fl_launch_t<24, MODE, 5>(map, ka, s) : fl_launch_t<24, MODE, 0>(map, ka, s);
+    default: return fl_launch_t<32, MODE, 0>(map, ka, s);
     }
 }
 

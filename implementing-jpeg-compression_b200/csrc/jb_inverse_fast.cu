@@ -149,10 +149,11 @@ jb_inv_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FiKernelArgs 
     auto claim = [&](unsigned prev) -> unsigned {
         if (a.ticket == nullptr) return prev + total_warps;
         unsigned c = 0;
-        if (lane == 0) c = atomicAdd(a.ticket, 1u);
+        if (lane == 0) c = total_warps + atomicAdd(a.ticket, 1u);
         return __shfl_sync(0xffffffffu, c, 0);
     };
-    unsigned next_chunk = a.ticket ? claim(0) : blockIdx.x * NWARPS + warp;
+    // (first chunk dealt statically, CTA-major: a single frame spreads over all SMs; the rest from the counter)
+    unsigned next_chunk = blockIdx.x + gridDim.x * (unsigned)warp;
     while (next_chunk < a.n_chunks) {
         const unsigned chunk = next_chunk;
         next_chunk = claim(chunk);
@@ -369,7 +370,7 @@ static cudaError_t jb_inv_fast_launch_t(const CUtensorMap& map, const FiKernelAr
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jb_inv_fast_kernel<DFT, MODE, ROWS>, NWARPS * 32, smem);
     if (per_sm < 1) per_sm = 1;
-    unsigned want = (ka.a.n_chunks + NWARPS - 1) / NWARPS;
+    unsigned want = ka.a.n_chunks;
     unsigned grid = want < (unsigned)(sms * per_sm) ? want : (unsigned)(sms * per_sm);
     if (grid == 0) return cudaSuccess;
     return jb_launch_ex(jb_inv_fast_kernel<DFT, MODE, ROWS>, dim3(grid), dim3(NWARPS * 32), smem, s,

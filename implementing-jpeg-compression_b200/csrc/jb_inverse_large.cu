@@ -155,10 +155,11 @@ jb_inv_large_kernel(const JbInvArgs a) {
     auto claim = [&](unsigned prev) -> unsigned {
         if (a.ticket == nullptr) return prev + total_warps;
         unsigned c = 0;
-        if (lane == 0) c = atomicAdd(a.ticket, 1u);
+        if (lane == 0) c = total_warps + atomicAdd(a.ticket, 1u);
         return __shfl_sync(0xffffffffu, c, 0);
     };
-    unsigned next_chunk = a.ticket ? claim(0) : blockIdx.x * NWARPS + warp;
+    // (first chunk dealt statically, CTA-major: a single frame spreads over all SMs; the rest from the counter)
+    unsigned next_chunk = blockIdx.x + gridDim.x * (unsigned)warp;
     while (next_chunk < a.n_chunks) {
         const unsigned chunk = next_chunk;
         next_chunk = claim(chunk);
@@ -340,7 +341,7 @@ static cudaError_t il_launch_t(const JbInvArgs& a, cudaStream_t s) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const unsigned want = (a.n_chunks + L.warps - 1) / L.warps;
+    const unsigned want = a.n_chunks;
     const unsigned grid = want < (unsigned)sms ? want : (unsigned)sms;
     if (grid == 0) return cudaSuccess;
     return jb_launch_ex(jb_inv_large_kernel<D, MODE>, dim3(grid), dim3(L.warps * 32), L.total, s,

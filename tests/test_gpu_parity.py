@@ -599,3 +599,56 @@ def test_programmatic_dependent_launch_gives_the_same_results(jb):
     jb.check_status(st3)
     assert c3.to_bytes_list() == want_streams
     assert torch.equal(out3, want_pixels)
+
+
+@pytest.mark.parametrize("h,w,bs,d,tr,qn,qp,pitch_extra", [
+    (97, 161, 4, 8, "DCT", "qtable", None, 15), (97, 161, 4, 8, "DCT", "qtable", None, 2), (128, 256, 4, 8, "DFT", "qtable", None, 32),
+    (240, 250, 5, 24, "DCT", "divide", 1000, 6), (360, 1024, 5, 24, "DCT", "divide", 40, 16), (50, 60, 1, 32, "DCT", "divide", 50, 4),
+    (33, 31, 3, 5, "DFT", "divide", 7, 1), (64, 64, 2, 16, "DCT", "divide", 20, 0)])
+def test_no_write_outside_the_callers_buffers(jb, h, w, bs, d, tr, qn, qp, pitch_extra):
+    """The sanitizer substitute (compute-sanitizer is not available on the GPU pool): every buffer the library
+    writes -- streams, offsets, status, workspaces, decoded planes -- sits inside a larger allocation pre-filled with
+    0xA5, with 256-byte guard bands on both sides; the decoded planes are given a row pitch wider than the image, so
+    that the bytes between the rows are guards too.  After compress + decompress all guards must be intact, and the
+    part of the stream buffer behind the last stream byte as well."""
+    import ctypes
+    import torch
+    cfg, ocfg = _cfgs(jb, (h, w, bs, d, tr, qn, qp))
+    n = 3
+    lib = jb._lib.load()
+    p = cfg.c_params()
+    G = 256
+
+    def guarded(nbytes):
+        buf = torch.full((nbytes + 2 * G,), 0xA5, dtype=torch.uint8, device="cuda")
+        return buf, buf[G:G + nbytes]
+
+    def intact(buf, nbytes):
+        return bool((buf[:G] == 0xA5).all()) and bool((buf[G + nbytes:] == 0xA5).all())
+
+    planes = torch.from_numpy(np.stack([synth_plane(h, w, 900 + i) for i in range(n)]).astype(np.uint8)).cuda()
+    cap = int(lib.jb_max_stream_bytes(ctypes.byref(p), n))
+    out_buf, out = guarded(cap)
+    ws_bytes = int(lib.jb_compress_workspace_bytes(ctypes.byref(p), n))
+    ws_buf, ws = guarded(ws_bytes)
+    comp = jb.compress_planes(planes, cfg, out=out, ws=ws)
+    total = comp.total_bytes()
+    want = jb.compress_planes(planes, cfg).to_bytes_list()
+    assert comp.to_bytes_list() == want
+    assert intact(out_buf, cap) and intact(ws_buf, ws_bytes)
+    assert bool((out[total:] == 0xA5).all()), "compress wrote behind the last stream byte"
+    # decode into planes with a wider pitch, inside a guarded allocation
+    pitch = w + pitch_extra
+    dec_bytes = n * h * pitch
+    dec_buf, dec_flat = guarded(dec_bytes)
+    dec = torch.as_strided(dec_flat, (n, h, w), (h * pitch, pitch, 1))
+    ws2_bytes = int(lib.jb_decompress_workspace_bytes(ctypes.byref(p), n, total))
+    ws2_buf, ws2 = guarded(ws2_bytes)
+    lens = comp.offsets[1:] - comp.offsets[:-1]
+    got, status = jb.decompress_planes(comp.data, comp.offsets[:-1], lens, cfg, n, in_bytes=total, out=dec, ws=ws2)
+    jb.check_status(status)
+    assert np.array_equal(got.cpu().numpy(), jb.decompress_bands(want, cfg))
+    assert intact(dec_buf, dec_bytes) and intact(ws2_buf, ws2_bytes)
+    if pitch_extra:
+        gaps = torch.as_strided(dec_flat, (n, h, pitch_extra), (h * pitch, pitch, 1), storage_offset=dec_flat.storage_offset() + w)
+        assert bool((gaps == 0xA5).all()), "decompress wrote between the rows"
