@@ -322,6 +322,7 @@ def run_ours(args, rank, world, local_rank):
     run_c, run_d = direct_c, direct_d
     run_step = None
     two_streams = None
+    launches_per_step, launches_source = 7, "known chain (3 compress + 4 decompress kernels): no graph was captured"
     if not args.no_graph:
         try:
             side = torch.cuda.Stream()
@@ -346,9 +347,13 @@ def run_ours(args, rank, world, local_rank):
             if args.step_graph:
                 # the step's two calls in ONE graph: no graph-launch gap between compress and decompress
                 g_s = torch.cuda.CUDAGraph()
+                lib_ = jb._lib.load()
+                n_before = lib_.jb_debug_launch_count()
                 with torch.cuda.graph(g_s, pool=g_c.pool()):
                     comp_s = bc.compress_device()
                     out_s, status_s = bc.decompress_device(comp_s, total_bytes)
+                launches_per_step = int(lib_.jb_debug_launch_count() - n_before)
+                launches_source = "jb_debug_launch_count() across the capture of the step's CUDA graph"
                 g_s.replay()
                 torch.cuda.synchronize()
                 jb.check_status(comp_s.status); jb.check_status(status_s)
@@ -446,6 +451,9 @@ def run_ours(args, rank, world, local_rank):
             e.record()                                       # creates the handle
     torch.cuda.synchronize()
     lib = jb._lib.load()
+    # (without programmatic dependent launch here: a kernel that may start under the tail of its predecessor would have
+    # the wait for it counted into its own duration)
+    flags_saved, bc.flags = bc.flags, bc.flags & ~jb._lib.JB_FLAG_PDL
     try:
         for quad in kev:
             if lib.jb_debug_kernel_events(*[e.cuda_event for e in quad]) != 0:
@@ -453,6 +461,7 @@ def run_ours(args, rank, world, local_rank):
             direct_c(); direct_d()
     finally:
         lib.jb_debug_kernel_events(None, None, None, None)
+        bc.flags = flags_saved
     barrier()
     tk_c = max_over_ranks(sum(q[0].elapsed_time(q[1]) for q in kev) / K)      # ms per launch, fused forward kernel
     tk_d = max_over_ranks(sum(q[2].elapsed_time(q[3]) for q in kev) / K)      # fused inverse kernel
@@ -536,6 +545,7 @@ def run_ours(args, rank, world, local_rank):
         a_d = total_bytes + n_planes * H * W
         ach_c = a_c / (t_c * 1e-3) / 1e9
         ach_d = a_d / (t_d * 1e-3) / 1e9
+        traffic = measured_traffic(n_img)
         os.sched_setaffinity(0, all_cores)              # the CPU leg uses every core again
         cpu = None if args.no_cpu else cpu_baseline_with_parity(bc, comp, n_img)
         line = {
@@ -555,29 +565,55 @@ def run_ours(args, rank, world, local_rank):
                          "unit": "GB/s", "frac": a_c / (tk_c * 1e-3) / 1e9 / peak,
                          "frac_of_nominal_8000": a_c / (tk_c * 1e-3) / 1e9 / 8000.0,
                          "whole_call_ms": t_c, "whole_call_achieved": ach_c, "whole_call_frac": ach_c / peak,
-                         # dram__bytes_read+write of one launch from `ncu --set full` at 1024 images on one GPU
-                         # (profiles/r1_ncu_full_v11_jb_fwd_fast.txt: 6.419 GB + 0.129 GB), scaled to this rank's share
-                         "traffic": 6.549e9 * n_img / 1024.0, "traffic_source": "profiles/r1_ncu_full_v11_jb_fwd_fast.txt",
+                         # dram__bytes_read + dram__bytes_write of one launch from `ncu --set full` (profiles/r2_traffic.json,
+                         # recorded per image together with the build id of the kernels it was measured on; null when the
+                         # sources have changed since), scaled to this rank's images
+                         "traffic": traffic["fwd"], "traffic_source": traffic["source"],
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": a_c},
             "roofline_decompress": {"bound": "hbm", "kernel": "jb_inv_fast_kernel (fused decompress)", "kernel_ms": tk_d,
                                     "achieved": a_d / (tk_d * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                     "frac": a_d / (tk_d * 1e-3) / 1e9 / peak,
                                     "frac_of_nominal_8000": a_d / (tk_d * 1e-3) / 1e9 / 8000.0,
                                     "whole_call_ms": t_d, "whole_call_achieved": ach_d, "whole_call_frac": ach_d / peak,
-                                    "traffic": 6.458e9 * n_img / 1024.0,
-                                    "traffic_source": "profiles/r1_ncu_full_v12_jb_inv_fast.txt (0.146 GB read + 6.313 GB written)",
+                                    "traffic": traffic["inv"], "traffic_source": traffic["source"],
                                     "algorithmic_bytes_per_launch": a_d},
             "cpu_baseline": cpu,
             "e2e": e2e,
-# per step: compress = init, fused kernel, 2 scan kernels, gather (5); decompress = framing prep, walk,
-            # stitch and the fused kernel (4); the table builders run once per codec object, outside the timed region
-            "gpu_launches": K * 9,
+            # kernels of ours inside the timed region: K steps x the kernel nodes of the step's CUDA graph (counted from
+            # the graph's own DOT dump at capture time); per step: fused compress kernel, scan, gather; framing prep,
+            # walk, stitch; fused decompress kernel.  The table builders run once per codec object, before it.
+            "gpu_launches": K * launches_per_step, "gpu_launches_per_step": launches_per_step,
+            "gpu_launches_source": launches_source,
             "clocks": clocks,
         }
         emit_json_line(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def library_build_id():
+    """sha256 over the kernel sources (tools/sass_summary.py): ties a profile to the code it was measured on."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import sass_summary
+    return sass_summary.build_id()
+
+
+def measured_traffic(n_img):
+    """DRAM bytes of one launch of the two fused kernels, from profiles/r2_traffic.json (`ncu --set full`), scaled to
+    n_img images; null values when the file is missing or belongs to other kernel sources."""
+    path = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    out = {"fwd": None, "inv": None, "source": "profiles/r2_traffic.json missing"}
+    try:
+        rec = json.load(open(path))
+    except (OSError, ValueError):
+        return out
+    bid = library_build_id()
+    if rec.get("build_id") != bid:
+        out["source"] = "profiles/r2_traffic.json is for build %s, this is %s: not used" % (rec.get("build_id"), bid)
+        return out
+    return {"fwd": rec["fwd_dram_bytes_per_image"] * n_img, "inv": rec["inv_dram_bytes_per_image"] * n_img,
+            "source": "profiles/r2_traffic.json (%s; build %s)" % (rec.get("how", "ncu --set full"), bid)}
 
 
 def cpu_baseline_with_parity(bc, comp, n_img):
@@ -661,8 +697,8 @@ def main():
                     help="launch the kernels without programmatic dependent launch (JB_FLAG_PDL is the default)")
     ap.add_argument("--call-graphs", dest="step_graph", action="store_false",
                     help="time one CUDA graph per library call instead of one per step (compress + decompress)")
-    ap.add_argument("--streams", type=int, default=2, choices=[1, 2, 3, 4],
-                    help="n > 1: consecutive steps take turns on n codec objects, each on its own CUDA stream (default 2); 1: one stream")
+    ap.add_argument("--streams", type=int, default=3, choices=[1, 2, 3, 4],
+                    help="n > 1: consecutive steps take turns on n codec objects, each on its own CUDA stream (default 3); 1: one stream")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
     args = ap.parse_args()

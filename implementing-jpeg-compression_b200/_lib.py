@@ -65,6 +65,7 @@ SYMBOLS = {
     "jb_containers_max_bytes": (_SZ, [_I, _I, _SZ]),
     "jb_pack_containers": (_I, [_P, _P, _I, ctypes.c_char_p, _I, _P, _SZ, _P, _P, _P]),
     "jb_debug_kernel_events": (_I, [_P, _P, _P, _P]),
+    "jb_debug_launch_count": (ctypes.c_ulonglong, []),
 }
 
 _lib = None

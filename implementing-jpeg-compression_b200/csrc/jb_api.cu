@@ -1,5 +1,6 @@
 // jb_api.cu -- the extern "C" surface declared in include/jpegb200.h.
 #include <string.h>
+#include <atomic>
 
 #include "jb_common.cuh"
 #include "jb_forward.cuh"
@@ -90,7 +91,7 @@ __global__ void jb_init_kernel(unsigned long long* status, unsigned* ticket) {
 }
 
 static int jb_reset_status(uint64_t* d_status, unsigned* d_ticket, cudaStream_t s) {
-    jb_init_kernel<<<1, 64, 0, s>>>((unsigned long long*)d_status, d_ticket);
+    JB_LAUNCH((jb_init_kernel), 1, 64, 0, s, (unsigned long long*)d_status, d_ticket);
     JB_CUDA_TRY(cudaGetLastError());
     return JB_OK;
 }
@@ -182,7 +183,11 @@ extern "C" int jb_stage_pack(const int32_t* d_coeffs, int n_planes, int blocks_p
                              d_coeffs, d_ws, ws_bytes, (cudaStream_t)stream);
 }
 
-// ---- measurement hook ------------------------------------------------------------------------------
+// ---- measurement hooks -----------------------------------------------------------------------------
+static std::atomic<unsigned long long> g_jb_launches{0};
+void jb_note_launches(unsigned n) { g_jb_launches.fetch_add(n, std::memory_order_relaxed); }
+extern "C" unsigned long long jb_debug_launch_count(void) { return g_jb_launches.load(std::memory_order_relaxed); }
+
 static cudaEvent_t g_prof_ev[4] = {nullptr, nullptr, nullptr, nullptr};
 
 extern "C" int jb_debug_kernel_events(void* fwd_begin, void* fwd_end, void* inv_begin, void* inv_end) {

@@ -178,11 +178,11 @@ static int jc_launch(bool forward, const uint8_t* src, uint8_t* dst, size_t imag
             return JB_ERR_CUDA;
         const long long want = (total + JC_FWD_THREADS - 1) / JC_FWD_THREADS;
         const long long cap = (long long)sms * 2;
-        jb_rgb_to_ycc_kernel<<<(unsigned)(want < cap ? want : cap), JC_FWD_THREADS, JC_FWD_SMEM, s>>>(a);
+        JB_LAUNCH((jb_rgb_to_ycc_kernel), (unsigned)(want < cap ? want : cap), JC_FWD_THREADS, JC_FWD_SMEM, s, a);
     } else {
         const long long want = (total + JC_THREADS - 1) / JC_THREADS;
         const long long cap = (long long)sms * 8 * 4;    // grid-stride beyond a few waves
-        jb_ycc_to_rgb_kernel<<<(unsigned)(want < cap ? want : cap), JC_THREADS, 0, s>>>(a);
+        JB_LAUNCH((jb_ycc_to_rgb_kernel), (unsigned)(want < cap ? want : cap), JC_THREADS, 0, s, a);
     }
     return cudaGetLastError() == cudaSuccess ? JB_OK : JB_ERR_CUDA;
 }
@@ -291,6 +291,6 @@ extern "C" int jb_pack_containers(const uint8_t* d_streams, const uint64_t* d_pl
     memcpy(a.header, header, (size_t)header_len);
     cudaStream_t s = (cudaStream_t)stream;
     if (cudaMemsetAsync(d_status, 0, sizeof(uint64_t), s) != cudaSuccess) return JB_ERR_CUDA;
-    jb_pack_containers_kernel<<<n_images, 256, 0, s>>>(a);
+    JB_LAUNCH((jb_pack_containers_kernel), n_images, 256, 0, s, a);
     return cudaGetLastError() == cudaSuccess ? JB_OK : JB_ERR_CUDA;
 }

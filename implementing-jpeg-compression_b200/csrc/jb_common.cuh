@@ -163,6 +163,12 @@ cudaError_t jb_launch_init_ctrl(unsigned* ctrl, unsigned long long* seg, size_t 
 __device__ __forceinline__ void jb_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void jb_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// Every kernel launch of the library goes through JB_LAUNCH or jb_launch_ex and is counted (process-wide, relaxed
+// atomic): jb_debug_launch_count() lets the benchmark report how many kernels a call really launches.
+void jb_note_launches(unsigned n);
+#define JB_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    do { kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); jb_note_launches(1u); } while (0)
+
 #ifdef __CUDACC__
 template <typename... KArgs, typename... Args>
 static inline cudaError_t jb_launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
@@ -175,6 +181,7 @@ static inline cudaError_t jb_launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
+    jb_note_launches(1u);
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 #endif

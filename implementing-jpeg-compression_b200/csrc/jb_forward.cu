@@ -369,7 +369,7 @@ cudaError_t jb_launch_init_ctrl(unsigned* ctrl, unsigned long long* seg, size_t 
     size_t blocks = (n_seg_words + 255) / 256;
     if (blocks < 1) blocks = 1;
     if (blocks > 1024) blocks = 1024;
-    jb_init_ctrl_kernel<<<(unsigned)blocks, 256, 0, s>>>(ctrl, seg, n_seg_words);
+    JB_LAUNCH((jb_init_ctrl_kernel), (unsigned)blocks, 256, 0, s, ctrl, seg, n_seg_words);
     return cudaGetLastError();
 }
 
@@ -385,7 +385,7 @@ cudaError_t jb_launch_gather(const JbFwdArgs& a, cudaStream_t s) {
 }
 
 cudaError_t jb_launch_finish(const JbFwdArgs& a, cudaStream_t s) {
-    jb_finish_kernel<<<1, 1, 0, s>>>(a);
+    JB_LAUNCH((jb_finish_kernel), 1, 1, 0, s, a);
     return cudaGetLastError();
 }
 
@@ -398,18 +398,18 @@ cudaError_t jb_launch_fwd_generic(const JbFwdArgs& a, int mode, cudaStream_t s) 
     case 0:
         e = cudaFuncSetAttribute(jb_fwd_generic_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        jb_fwd_generic_kernel<0><<<a.n_chunks, JB_GENERIC_THREADS, smem, s>>>(a);
+        JB_LAUNCH((jb_fwd_generic_kernel<0>), a.n_chunks, JB_GENERIC_THREADS, smem, s, a);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         return jb_launch_gather(a, s);
     case 1:
         e = cudaFuncSetAttribute(jb_fwd_generic_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        jb_fwd_generic_kernel<1><<<a.n_chunks, JB_GENERIC_THREADS, smem, s>>>(a);
+        JB_LAUNCH((jb_fwd_generic_kernel<1>), a.n_chunks, JB_GENERIC_THREADS, smem, s, a);
         break;
     default:
         e = cudaFuncSetAttribute(jb_fwd_generic_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        jb_fwd_generic_kernel<2><<<a.n_chunks, JB_GENERIC_THREADS, smem, s>>>(a);
+        JB_LAUNCH((jb_fwd_generic_kernel<2>), a.n_chunks, JB_GENERIC_THREADS, smem, s, a);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         return jb_launch_gather(a, s);
     }

@@ -136,9 +136,11 @@ __device__ __forceinline__ int jb_stream_of_tile(const unsigned* tile_first, int
 #define JB_REACH_SMALL_CAP 4096u
 __global__ void __launch_bounds__(1024) jb_frame_prep_kernel(JbFrameArgs f) {
     __shared__ unsigned s_warp[33];
+    __shared__ unsigned s_big[32][3];
+    __shared__ int s_nbig;
     unsigned carry = 0, wcarry = 0;
     bool bad = false;
-    if (threadIdx.x == 0) f.big_list[0] = 0u;
+    if (threadIdx.x == 0) { f.big_list[0] = 0u; s_nbig = 0; }
     // (status words and chunk ticket live in the workspace's control block, which is clean when a call starts)
     __syncthreads();
     for (int base = 0; base < f.n_planes; base += 1024) {
@@ -161,9 +163,27 @@ __global__ void __launch_bounds__(1024) jb_frame_prep_kernel(JbFrameArgs f) {
         if (s < f.n_planes) {
             f.warp_first[s] = wcarry + ex;
             const unsigned wmax = f.max_tiles / 32u + (unsigned)f.n_planes + 1u;            // capacity of warp_stream
-            for (unsigned j = 0, w = wcarry + ex; j < ((nt + 31u) >> 5) && w < wmax; ++j, ++w) f.warp_stream[w] = (unsigned)s;
+            const unsigned nw = (nt + 31u) >> 5;
+            int slot = -1;
+            if (nw > 64u) slot = atomicAdd(&s_nbig, 1);          // a long stream: the whole CTA fills its range below
+            if (slot >= 0 && slot < 32) {
+                s_big[slot][0] = (unsigned)s; s_big[slot][1] = wcarry + ex; s_big[slot][2] = nw;
+            } else {
+                for (unsigned j = 0, w = wcarry + ex; j < nw && w < wmax; ++j, ++w) f.warp_stream[w] = (unsigned)s;
+            }
         }
         wcarry += total;
+        __syncthreads();
+        {
+            const unsigned wmax = f.max_tiles / 32u + (unsigned)f.n_planes + 1u;
+            const int nbig = s_nbig < 32 ? s_nbig : 32;
+            for (int b = 0; b < nbig; ++b)
+                for (unsigned j = threadIdx.x; j < s_big[b][2] && s_big[b][1] + j < wmax; j += blockDim.x)
+                    f.warp_stream[s_big[b][1] + j] = s_big[b][0];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_nbig = 0;
+        __syncthreads();
     }
     if (__syncthreads_or(bad ? 1 : 0)) carry = 0xFFFFFFFFu;
     if (threadIdx.x == 0) {
@@ -415,24 +435,40 @@ __device__ __forceinline__ void jb_reach_stream(const JbFrameArgs& f, int s, uin
     const unsigned nt = f.tile_first[s + 1] - t0;
     const uint32_t len = (uint32_t)f.plane_len[s];
     const unsigned T = f.tile_bytes;
-    for (unsigned t = tid; t < nt; t += blockDim.x) {
-        const uint32_t ex = f.tile_exit[t0 + t];
-        uint16_t nx = 0xFFFFu;
-        if (ex != JB_POS_INVALID && ex < len) { const unsigned k = ex / T; if (k > t && k < nt) nx = (uint16_t)k; }
-        J[0][t] = nx;
-        R[t] = t == 0 ? 1 : 0;
-        f.tile_entry[t0 + t] = t == 0 ? 0u : JB_POS_INVALID;
+    // (tile sizes are powers of two; the loops take four tiles per thread and pass so that their global loads overlap:
+    // a long stream is 16 K tiles for one CTA, and a loop of dependent L2 round trips was most of this kernel)
+    const unsigned tsh = (unsigned)__ffs((int)T) - 1u;
+    const unsigned bd = blockDim.x;
+    for (unsigned base = tid; base < nt; base += 4u * bd) {
+        uint32_t ex[4];
+        #pragma unroll
+        for (int k = 0; k < 4; ++k) ex[k] = base + k * bd < nt ? __ldg(f.tile_exit + t0 + base + k * bd) : JB_POS_INVALID;
+        #pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const unsigned t = base + k * bd;
+            if (t >= nt) break;
+            uint16_t nx = 0xFFFFu;
+            if (ex[k] != JB_POS_INVALID && ex[k] < len) { const unsigned kk = ex[k] >> tsh; if (kk > t && kk < nt) nx = (uint16_t)kk; }
+            J[0][t] = nx;
+            R[t] = t == 0 ? 1 : 0;
+            f.tile_entry[t0 + t] = t == 0 ? 0u : JB_POS_INVALID;
+        }
     }
     __syncthreads();
     int cur = 0;
     for (unsigned span = 1; span < nt; span <<= 1) {
-        for (unsigned t = tid; t < nt; t += blockDim.x) {
-            const uint16_t j = J[cur][t];
-            if (j != 0xFFFFu) {
-                if (R[t]) R[j] = 1;                          // marks only tiles that are on the chain
-                J[cur ^ 1][t] = J[cur][j];
-            } else {
-                J[cur ^ 1][t] = 0xFFFFu;
+        for (unsigned base = tid; base < nt; base += 4u * bd) {
+            uint16_t j[4], jj[4];
+            #pragma unroll
+            for (int k = 0; k < 4; ++k) j[k] = base + k * bd < nt ? J[cur][base + k * bd] : (uint16_t)0xFFFFu;
+            #pragma unroll
+            for (int k = 0; k < 4; ++k) jj[k] = j[k] != 0xFFFFu ? J[cur][j[k]] : (uint16_t)0xFFFFu;
+            #pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const unsigned t = base + k * bd;
+                if (t >= nt) break;
+                if (j[k] != 0xFFFFu && R[t]) R[j[k]] = 1;        // marks only tiles that are on the chain
+                J[cur ^ 1][t] = jj[k];
             }
         }
         __syncthreads();
@@ -440,12 +476,21 @@ __device__ __forceinline__ void jb_reach_stream(const JbFrameArgs& f, int s, uin
     }
     // entries of the tiles on the chain, and the end of the chain
     int bad = 0, ends = 0;
-    for (unsigned t = tid; t < nt; t += blockDim.x) {
-        if (!R[t]) continue;
-        const uint32_t ex = f.tile_exit[t0 + t];
-        if (ex == len) ++ends;
-        else if (ex == JB_POS_INVALID || ex > len || ex / T <= t || ex / T >= nt) bad = 1;
-        else f.tile_entry[t0 + ex / T] = ex;
+    for (unsigned base = tid; base < nt; base += 4u * bd) {
+        uint32_t ex[4];
+        #pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const unsigned t = base + k * bd;
+            ex[k] = (t < nt && R[t]) ? __ldg(f.tile_exit + t0 + t) : 0xFFFFFFFEu;          // 0xFFFFFFFE: not on the chain
+        }
+        #pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const unsigned t = base + k * bd;
+            if (ex[k] == 0xFFFFFFFEu) continue;
+            if (ex[k] == len) ++ends;
+            else if (ex[k] == JB_POS_INVALID || ex[k] > len || (ex[k] >> tsh) <= t || (ex[k] >> tsh) >= nt) bad = 1;
+            else f.tile_entry[t0 + (ex[k] >> tsh)] = ex[k];
+        }
     }
     bad = __syncthreads_or(bad);
     const int total_ends = __syncthreads_count(ends);
@@ -532,12 +577,19 @@ __device__ __forceinline__ void jb_scan_stream(const JbFrameArgs& f, int s, unsi
     const unsigned t0 = f.tile_first[s];
     const unsigned nt = f.tile_first[s + 1] - t0;
     unsigned carry = 0;
-    for (unsigned b = 0; b < nt; b += blockDim.x) {
-        const unsigned t = b + tid;
-        const unsigned hops = t < nt ? f.tile_hops[t0 + t] : 0u;
+    // four consecutive tiles per thread and pass: a quarter of the block scans (and of the dependent L2 round trips)
+    for (unsigned b = 0; b < nt; b += 4u * blockDim.x) {
+        const unsigned t = b + 4u * (unsigned)tid;
+        unsigned h[4];
+        #pragma unroll
+        for (int k = 0; k < 4; ++k) h[k] = t + k < nt ? f.tile_hops[t0 + t + k] : 0u;
         unsigned total;
-        const unsigned ex = jb_block_excl_scan(hops, s_warp, &total);
-        if (t < nt) f.tile_base[t0 + t] = carry + ex;
+        unsigned ex = carry + jb_block_excl_scan(h[0] + h[1] + h[2] + h[3], s_warp, &total);
+        #pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (t + k < nt) f.tile_base[t0 + t + k] = ex;
+            ex += h[k];
+        }
         carry += total;
     }
     if (tid == 0) {
@@ -672,7 +724,7 @@ cudaError_t jb_launch_framing(const JbFrameArgs& f_in, cudaStream_t s) {
     cudaError_t e;
     JbFrameArgs f = f_in;
     const unsigned grid = (f.max_tiles + JB_FRAME_THREADS - 1) / JB_FRAME_THREADS;
-    jb_frame_prep_kernel<<<1, 1024, 0, s>>>(f);
+    JB_LAUNCH((jb_frame_prep_kernel), 1, 1024, 0, s, f);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     // region of one warp of the walk: 32 tiles, the byte before them, JB_WALK_HALO bytes behind them, misalignment and
     // two words of zero slack; then 32 bitmaps.  The block size that puts most warps on an SM.
@@ -693,9 +745,9 @@ cudaError_t jb_launch_framing(const JbFrameArgs& f_in, cudaStream_t s) {
         const size_t walk_blocks = (walk_warps * 32u + wthreads - 1) / wthreads;
         e = cudaFuncSetAttribute(jb_frame_walk_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        jb_frame_walk_smem_kernel<<<(unsigned)walk_blocks, wthreads, smem, s>>>(f, region_words, warp_words);
+        JB_LAUNCH((jb_frame_walk_smem_kernel), (unsigned)walk_blocks, wthreads, smem, s, f, region_words, warp_words);
     } else {
-        jb_frame_walk_kernel<<<(f.max_tiles + JB_WALK_THREADS - 1) / JB_WALK_THREADS, JB_WALK_THREADS, 0, s>>>(f);
+        JB_LAUNCH((jb_frame_walk_kernel), (f.max_tiles + JB_WALK_THREADS - 1) / JB_WALK_THREADS, JB_WALK_THREADS, 0, s, f);
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (!jb_framing_is_chain(f.max_tiles, f.n_planes)) {
@@ -711,20 +763,20 @@ cudaError_t jb_launch_framing(const JbFrameArgs& f_in, cudaStream_t s) {
         size_t smem = 5 * (size_t)cap;
         if (smem < (JB_SERIAL_WORDS + 8) * 4) smem = (JB_SERIAL_WORDS + 8) * 4;
         f.stitch_cap = cap;
-        jb_frame_stitch_kernel<<<f.n_planes, small ? JB_STITCH_THREADS / 2 : JB_STITCH_THREADS, smem, s>>>(f);
+        JB_LAUNCH((jb_frame_stitch_kernel), f.n_planes, small ? JB_STITCH_THREADS / 2 : JB_STITCH_THREADS, smem, s, f);
         return cudaGetLastError();
     }
     {   // chain of tiles: streams of up to 4096 tiles (1 MB) in 20 KB of shared memory, longer ones in 200 KB
         const size_t sm_small = 5 * 4096, sm_big = 5 * 40000;
-        jb_frame_reach_kernel<JB_REACH_SMALL_CAP, 0><<<f.n_planes, JB_FRAME_THREADS, sm_small, s>>>(f);
+        JB_LAUNCH((jb_frame_reach_kernel<JB_REACH_SMALL_CAP, 0>), f.n_planes, JB_FRAME_THREADS, sm_small, s, f);
         e = cudaFuncSetAttribute(jb_frame_reach_kernel<40000, JB_REACH_SMALL_CAP + 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_big);
         if (e != cudaSuccess) return e;
-        jb_frame_reach_kernel<40000, JB_REACH_SMALL_CAP + 1><<<f.n_planes < 32 ? f.n_planes : 32, 1024, sm_big, s>>>(f);
+        JB_LAUNCH((jb_frame_reach_kernel<40000, JB_REACH_SMALL_CAP + 1>), f.n_planes < 32 ? f.n_planes : 32, 1024, sm_big, s, f);
     }
-    jb_frame_link_kernel<<<grid, JB_FRAME_THREADS, 0, s>>>(f);
+    JB_LAUNCH((jb_frame_link_kernel), grid, JB_FRAME_THREADS, 0, s, f);
     // a few long streams: wide CTAs; many short streams: narrow ones
-    jb_frame_scan_kernel<<<f.n_planes, (f.max_tiles / (unsigned)f.n_planes > 2048u) ? 1024 : JB_FRAME_THREADS, 0, s>>>(f);
-    jb_frame_emit_kernel<<<grid, JB_FRAME_THREADS, 0, s>>>(f);
-    jb_frame_serial_kernel<<<f.n_planes, 32, 0, s>>>(f);
+    JB_LAUNCH((jb_frame_scan_kernel), f.n_planes, (f.max_tiles / (unsigned)f.n_planes > 2048u) ? 1024 : JB_FRAME_THREADS, 0, s, f);
+    JB_LAUNCH((jb_frame_emit_kernel), grid, JB_FRAME_THREADS, 0, s, f);
+    JB_LAUNCH((jb_frame_serial_kernel), f.n_planes, 32, 0, s, f);
     return cudaGetLastError();
 }

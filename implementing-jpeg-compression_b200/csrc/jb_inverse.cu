@@ -44,7 +44,7 @@ size_t jb_inv_generic_smem_bytes(int d, bool dft) { return jb_inv_smem_layout(d,
 __global__ void jb_dec_finish_kernel(JbInvArgs a) { jb_dec_publish_and_clean(a); }
 
 cudaError_t jb_launch_dec_finish(const JbInvArgs& a, cudaStream_t s) {
-    jb_dec_finish_kernel<<<1, 1, 0, s>>>(a);
+    JB_LAUNCH((jb_dec_finish_kernel), 1, 1, 0, s, a);
     return cudaGetLastError();
 }
 
@@ -89,7 +89,9 @@ jb_inv_generic_kernel(const JbInvArgs a) {
             const unsigned start = a.block_start[(size_t)plane * g.nblocks + blk0 + tid];
             const unsigned limit = len > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned)len;
             int16_t* row = (int16_t*)(sCoef + tid * L.coefW);
-            int rc = (start < limit)
+            // (a stream must lie inside the caller's buffer: device-supplied offsets are not trusted)
+            const bool inside = a.plane_off[plane] <= a.in_bytes && len <= a.in_bytes - a.plane_off[plane];
+            int rc = (inside && start < limit)
                 ? jb_decode_block<int16_t, uint16_t>(stream, start, limit, n, row,
                                                      MODE == 1 ? (const uint16_t*)nullptr : a.t.izz)
                 : JB_PARSE_BAD;
@@ -184,17 +186,17 @@ cudaError_t jb_launch_inv_generic(const JbInvArgs& a, int mode, cudaStream_t s) 
     case 0:
         e = cudaFuncSetAttribute(jb_inv_generic_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        jb_inv_generic_kernel<0><<<a.n_chunks, JB_INV_GENERIC_THREADS, smem, s>>>(a);
+        JB_LAUNCH((jb_inv_generic_kernel<0>), a.n_chunks, JB_INV_GENERIC_THREADS, smem, s, a);
         break;
     case 1:
         e = cudaFuncSetAttribute(jb_inv_generic_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        jb_inv_generic_kernel<1><<<a.n_chunks, JB_INV_GENERIC_THREADS, smem, s>>>(a);
+        JB_LAUNCH((jb_inv_generic_kernel<1>), a.n_chunks, JB_INV_GENERIC_THREADS, smem, s, a);
         break;
     default:
         e = cudaFuncSetAttribute(jb_inv_generic_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        jb_inv_generic_kernel<2><<<a.n_chunks, JB_INV_GENERIC_THREADS, smem, s>>>(a);
+        JB_LAUNCH((jb_inv_generic_kernel<2>), a.n_chunks, JB_INV_GENERIC_THREADS, smem, s, a);
         break;
     }
     return cudaGetLastError();

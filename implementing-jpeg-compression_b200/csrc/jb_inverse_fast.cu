@@ -182,7 +182,8 @@ jb_inv_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FiKernelArgs 
             c_end = __shfl_sync(0xffffffffu, c_end, 0);
             const unsigned long long addr0 = (unsigned long long)(uintptr_t)(stream + c_start);
             const unsigned mis = (unsigned)(addr0 & 3ull);
-            const bool ok = c_start <= c_end && c_end <= len;
+            // (a stream must lie inside the caller's buffer: device-supplied offsets are not trusted)
+            const bool ok = c_start <= c_end && c_end <= len && a.plane_off[plane] <= a.in_bytes && len <= a.in_bytes - a.plane_off[plane];
             const uint32_t* wsrc = (const uint32_t*)(uintptr_t)(addr0 - mis);
             const unsigned nwords = ok ? (((c_end - c_start) + mis + 3u) >> 2) : 0u;
             const bool staged = nwords <= STAGE_WORDS;

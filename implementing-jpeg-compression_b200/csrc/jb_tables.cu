@@ -151,6 +151,6 @@ cudaError_t jb_launch_build_tables(const JbGeom& g, const JbTables& t, cudaStrea
             for (int m = 0; m < g.d; ++m) hm.a[k * g.d + m] = cos(PI / g.d * (m + 0.5) * k);     // transforms.py:9-10
         hm_d = g.d;
     }
-    jb_build_tables_kernel<<<1, 256, 0, s>>>(g, t, hm);
+    JB_LAUNCH((jb_build_tables_kernel), 1, 256, 0, s, g, t, hm);
     return cudaGetLastError();
 }

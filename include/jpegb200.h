@@ -228,6 +228,11 @@ int jb_pack_containers(const uint8_t* d_streams, const uint64_t* d_plane_off, in
  * calls into a CUDA graph while it is armed.  The reference has no counterpart. */
 int jb_debug_kernel_events(void* fwd_begin, void* fwd_end, void* inv_begin, void* inv_end);
 
+/* Kernels this library has launched in this process so far (every launch is counted, also while a CUDA graph is being
+ * captured): the difference across a call -- or across the capture of a graph -- is the number of kernels it consists
+ * of.  bench.py's gpu_launches comes from it. */
+unsigned long long jb_debug_launch_count(void);
+
 #ifdef __cplusplus
 }
 #endif

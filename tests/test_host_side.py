@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_library_loads_and_exports_every_declared_symbol():
     lib = jb._lib.load()
     header = open(os.path.join(ROOT, "include", "jpegb200.h")).read()
-    declared = set(re.findall(r"^(?:int|size_t|const char\*)\s+(jb_[a-z_]+)\s*\(", header, flags=re.M))
+    declared = set(re.findall(r"^(?:int|size_t|const char\*|unsigned long long)\s+(jb_[a-z_0-9]+)\s*\(", header, flags=re.M))
     assert declared == set(jb._lib.SYMBOLS), declared ^ set(jb._lib.SYMBOLS)
     for name in declared:
         assert hasattr(lib, name)
