@@ -454,9 +454,19 @@ __device__ __forceinline__ void jb_reach_stream(const JbFrameArgs& f, int s, uin
             f.tile_entry[t0 + t] = t == 0 ? 0u : JB_POS_INVALID;
         }
     }
+    // The usual stream: every walk leaves its tile for the next one (a block longer than a whole tile is what it takes
+    // to skip one), i.e. every tile is on the chain -- seen in one parallel pass.  Pointer doubling (log2(tiles) rounds
+    // by one CTA: 60 us for the 16 K tiles of a gigapixel plane) is for the streams where that does not hold.
     __syncthreads();
+    int plain = 1;
+    for (unsigned t = tid; t + 1u < nt; t += bd) plain &= J[0][t] == (uint16_t)(t + 1u);
+    plain = __syncthreads_and(plain);
+    if (plain) {
+        for (unsigned t = tid; t < nt; t += bd) R[t] = 1;
+        __syncthreads();
+    }
     int cur = 0;
-    for (unsigned span = 1; span < nt; span <<= 1) {
+    for (unsigned span = 1; span < nt && !plain; span <<= 1) {
         for (unsigned base = tid; base < nt; base += 4u * bd) {
             uint16_t j[4], jj[4];
             #pragma unroll

@@ -90,8 +90,9 @@ typedef struct jb_params {
 #define JB_FLAG_REUSE_TABLES  16 /* the caller promises that this workspace was last used by a COMPLETED-OR-QUEUED call of
                                    the same direction with identical jb_params and n_planes (on the same stream, or
                                    ordered before this one) and has not been written since: the launches that build the
-                                   tables and clean the control block are skipped -- a compress call is then two
-                                   launches, the fused transform kernel and the gather */
+                                   tables and clean the control block are skipped -- a compress call is then three
+                                   launches (fused transform kernel, scan, gather), a decompress call four (framing prep,
+                                   walk, stitch, fused inverse kernel) */
 
 /* Derived sizes (pipeline/run_length_encoding.py:80-88, pipeline/dct_padding.py:11-21). */
 typedef struct jb_geometry {
@@ -100,7 +101,7 @@ typedef struct jb_geometry {
     int32_t vb, hb;            /* blocks down / across                             */
     int32_t blocks_per_plane;  /* vb * hb                                          */
     int32_t max_block_bytes;   /* ceil((23 d^2 + 8) / 8): worst case of one block  */
-    int32_t chunks_per_plane;  /* ceil(blocks_per_plane / 32): scheduling unit     */
+    int32_t chunks_per_plane;  /* scheduling units: ceil(blocks_per_plane / 32), / 8 for dct_size >= 16 */
     int32_t reserved;
 } jb_geometry;
 
