@@ -57,9 +57,12 @@ bool jb_inv_large_eligible(const JbGeom& g) {
     return g.d * g.bs <= 128 && il_layout(g.d).warps >= 4;
 }
 
-// word-based block decoder over global memory, any n (same logic as fi_decode_block of jb_inverse_fast.cu)
+// word-based block decoder over global memory, any n (same logic as fi_decode_block of jb_inverse_fast.cu); also
+// reports the largest row / column (natural order) that holds a coefficient: umax, vmax (-1: the block is empty)
+template <int D>
 __device__ __forceinline__ int il_decode_block(const uint8_t* stream, uint32_t start, uint32_t len, int n,
-                                               int16_t* row, const uint16_t* izz) {
+                                               int16_t* row, const uint16_t* izz, int& umax, int& vmax) {
+    umax = vmax = -1;
     const uintptr_t a0 = (uintptr_t)(stream + start);
     const uint32_t mis = (uint32_t)(a0 & 3);
     const uint32_t* words = (const uint32_t*)(a0 - mis);
@@ -89,7 +92,10 @@ __device__ __forceinline__ int il_decode_block(const uint8_t* stream, uint32_t s
         nb -= 8 + (int)size; used += 8u + size;
         if (used > bitlimit) return 1;
         const int mag = (int)(raw & ((1u << (size - 1)) - 1u));
-        row[izz[count]] = (int16_t)((raw >> (size - 1)) ? mag : -mag);
+        const int nat = izz[count];
+        row[nat] = (int16_t)((raw >> (size - 1)) ? mag : -mag);
+        umax = max(umax, nat / D);
+        vmax = max(vmax, nat % D);
         ++count;
     }
 }
@@ -173,6 +179,7 @@ jb_inv_large_kernel(const JbInvArgs a) {
             for (int i = lane; i < JB_CHUNK_LARGE * n / 8; i += 32) z[i] = make_uint4(0, 0, 0, 0);
         }
         __syncwarp();
+        int my_umax = D - 1, my_vmax = D - 1;                   // of the block this lane decoded (lane < nvalid)
         if (MODE == 2) {
             for (int gi = 0; gi < nvalid; ++gi)
                 for (int zp = lane; zp < n; zp += 32)
@@ -182,19 +189,25 @@ jb_inv_large_kernel(const JbInvArgs a) {
             const unsigned start = a.block_start[(size_t)plane * g.nblocks + blk0 + lane];
             int rc = 1;
             if (len <= 0xFFFFFFFFull && start < (unsigned)len && a.plane_off[plane] + len <= a.in_bytes)
-                rc = il_decode_block(a.in + a.plane_off[plane], start, (unsigned)len, n, coef + lane * n, sIzz);
-            if (rc) jb_set_error(a.status, JB_ERR_BAD_STREAM);
+                rc = il_decode_block<D>(a.in + a.plane_off[plane], start, (unsigned)len, n, coef + lane * n, sIzz, my_umax, my_vmax);
+            if (rc) { jb_set_error(a.status, JB_ERR_BAD_STREAM); my_umax = my_vmax = D - 1; }
         }
         __syncwarp();
 
         for (int gi = 0; gi < nvalid; ++gi) {
+            // A heavily quantised block keeps its coefficients in the low-frequency corner (config 3: divide 1000, zigzag
+            // positions 0..~10): rows u >= ulim and columns k >= klim (multiples of 8 around the decoder's umax / vmax) hold
+            // zeros, so the sums below stop there -- a third of the multiply-adds for an 8 x 8 corner of a 24 x 24 block.
+            // Whatever earlier blocks left outside that corner of sY / sP is never read.
+            const int ulim = jb_min(D, (__shfl_sync(0xffffffffu, my_umax, gi) + 8) & ~7);
+            const int klim = jb_min(D, (__shfl_sync(0xffffffffu, my_vmax, gi) + 8) & ~7);
+            const int mlim = klim >> 1, mulim = ulim >> 1;          // in pairs (even, odd): multiples of 4
             // ---- dequantise (integer coefficient * quantiser step: exact in fp32), split by frequency parity ----
             {
                 const int16_t* row = coef + gi * n;
-                for (int idx = lane; idx < n; idx += 32) {
-                    const int u = idx / D, k = idx - u * D;
-                    sY[(k & 1) * (D * H) + u * H + (k >> 1)] = (float)row[idx] * sDq[idx];
-                }
+                if (lane < klim)
+                    for (int u = 0; u < ulim; ++u)
+                        sY[(lane & 1) * (D * H) + u * H + (lane >> 1)] = (float)row[u * D + lane] * sDq[u * D + lane];
             }
             __syncwarp();
             // ---- along the rows: Pe / Po[u][c] = sum_m Y[u][2m + par] B[c][2m + par], c < H; lane tile RT rows x KT samples ----
@@ -209,6 +222,7 @@ jb_inv_large_kernel(const JbInvArgs a) {
                     for (int q = 0; q < KT; ++q) acc[r][q] = 0.f;
                 #pragma unroll
                 for (int m = 0; m < H; m += 4) {
+                    if (m >= mlim) break;                               // (warp-uniform)
                     float4 y4[RT], b4[KT];
                     #pragma unroll
                     for (int r = 0; r < RT; ++r) y4[r] = *(const float4*)(ybase + r * H + m);
@@ -251,6 +265,7 @@ jb_inv_large_kernel(const JbInvArgs a) {
                     for (int q = 0; q < KT; ++q) acc[r][q] = 0.f;
                 #pragma unroll
                 for (int mu = 0; mu < H; mu += 4) {
+                    if (mu >= mulim) break;                             // (warp-uniform)
                     float4 b4[RT];
                     #pragma unroll
                     for (int r = 0; r < RT; ++r) b4[r] = *(const float4*)(bbase + r * H + mu);
