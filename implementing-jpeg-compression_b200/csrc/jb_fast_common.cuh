@@ -101,19 +101,29 @@ __device__ __forceinline__ void ff_idct8(const float (&z)[8], float (&x)[8]) {
 //   Re F[u][v] = CT(cos col v)[u] - ST(sin col v)[u],  Re F[u][8-v] = CT + ST.
 // The partner column sits 4 lanes-of-c away, i.e. lane ^ 16 in the (c * 4 + b) lane layout.
 __device__ __forceinline__ void ff_dft_column_stage(const float (&col)[8], int c, float (&y)[8]) {
-    float t[8], mine[8];
+    float t[8];
     ff_rdft8(col, t);
-    if (c < 5) {
-        mine[0] = t[0]; mine[1] = t[1]; mine[2] = t[2]; mine[3] = t[3]; mine[4] = t[4];
-        mine[5] = t[3]; mine[6] = t[2]; mine[7] = t[1];
-    } else {
-        mine[0] = 0.f; mine[1] = t[5]; mine[2] = t[6]; mine[3] = t[7]; mine[4] = 0.f;
-        mine[5] = -t[7]; mine[6] = -t[6]; mine[7] = -t[5];
-    }
+    // A cos lane holds CT[u] = t[min(u, 8 - u)], a sin lane ST[u] = (0, t5, t6, t7, 0, -t7, -t6, -t5): five distinct
+    // values each, so five exchanges do.  With (A, S) = (cos part, sin part) of this lane's output column:
+    //   y[k] = A[k] + f S[k], y[8-k] = A[k] - f S[k] (k = 1..3), y[0] = A[0], y[4] = A[4];
+    //   f = -1 on the cos lanes 1..3 (column v = c), +1 on the sin lanes (column 8 - v), 0 for c = 0 and c = 4 (no sin part).
+    const bool sin_lane = c >= 5;
+    const float f = sin_lane ? 1.f : ((c & 3) ? -1.f : 0.f);
+    float m[5], o[5];
+    m[0] = sin_lane ? 0.f : t[0];
+    m[1] = sin_lane ? t[5] : t[1];
+    m[2] = sin_lane ? t[6] : t[2];
+    m[3] = sin_lane ? t[7] : t[3];
+    m[4] = sin_lane ? 0.f : t[4];
     #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        const float other = __shfl_xor_sync(0xffffffffu, mine[u], 16);
-        y[u] = (c == 0 || c == 4) ? mine[u] : (c < 4 ? mine[u] - other : other + mine[u]);
+    for (int k = 0; k < 5; ++k) o[k] = __shfl_xor_sync(0xffffffffu, m[k], 16);
+    y[0] = sin_lane ? o[0] : m[0];
+    y[4] = sin_lane ? o[4] : m[4];
+    #pragma unroll
+    for (int k = 1; k < 4; ++k) {
+        const float A = sin_lane ? o[k] : m[k], S = sin_lane ? m[k] : o[k];
+        y[k] = fmaf(f, S, A);
+        y[8 - k] = fmaf(-f, S, A);
     }
 }
 

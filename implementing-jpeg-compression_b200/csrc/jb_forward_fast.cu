@@ -131,19 +131,29 @@ struct FfKernelArgs {
     int aligned;        // plane base / pitch / stride are multiples of 16 bytes
 };
 
-// Pack one block (64 int16 coefficients in zigzag order, row of FF_COEF_W words) with any writer.
+// Non-zero mask of one block's 64 int16 coefficients (zigzag order, row of FF_COEF_W words): per pair of 128-bit
+// loads, min(halfword, 1) packed two to a word (VIMNMX.U16x2), the eight words added at even bit positions, and the
+// high halfwords folded down between them.
+__device__ __forceinline__ void ff_block_mask(const uint32_t* rowp, uint32_t& lo, uint32_t& hi) {
+    uint32_t m16[4];
+    #pragma unroll
+    for (int q8 = 0; q8 < 4; ++q8) {
+        const uint4 w0 = *(const uint4*)(rowp + 8 * q8), w1 = *(const uint4*)(rowp + 8 * q8 + 4);
+        const uint32_t one = 0x00010001u;
+        uint32_t m = __vminu2(w0.x, one) + (__vminu2(w0.y, one) << 2) + (__vminu2(w0.z, one) << 4) + (__vminu2(w0.w, one) << 6)
+                   + (__vminu2(w1.x, one) << 8) + (__vminu2(w1.y, one) << 10) + (__vminu2(w1.z, one) << 12) + (__vminu2(w1.w, one) << 14);
+        m16[q8] = (m | (m >> 15)) & 0xFFFFu;
+    }
+    lo = m16[0] | (m16[1] << 16);
+    hi = m16[2] | (m16[3] << 16);
+}
+
+// Pack one block with any writer; amplitudes that do not fit their size field (BadRleCodeError in the reference) are
+// skipped and the first of them reported.
 template <typename Writer>
 __device__ __forceinline__ void ff_pack_block(const uint32_t* rowp, Writer& bw, int& bad_pos, int& bad_run) {
-    uint32_t lo = 0, hi = 0;
-    #pragma unroll
-    for (int q4 = 0; q4 < 8; ++q4) {
-        const uint4 w = *(const uint4*)(rowp + 4 * q4);
-        const uint32_t m = ((w.x & 0xFFFFu) ? 1u : 0u) | ((w.x >> 16) ? 2u : 0u)
-                         | ((w.y & 0xFFFFu) ? 4u : 0u) | ((w.y >> 16) ? 8u : 0u)
-                         | ((w.z & 0xFFFFu) ? 16u : 0u) | ((w.z >> 16) ? 32u : 0u)
-                         | ((w.w & 0xFFFFu) ? 64u : 0u) | ((w.w >> 16) ? 128u : 0u);
-        if (q4 < 4) lo |= m << (8 * q4); else hi |= m << (8 * (q4 - 4));
-    }
+    uint32_t lo, hi;
+    ff_block_mask(rowp, lo, hi);
     const int16_t* c16 = (const int16_t*)rowp;
     int prev = -1, bad_prev = 0;
     bad_pos = -1;
@@ -170,6 +180,51 @@ __device__ __forceinline__ void ff_pack_block(const uint32_t* rowp, Writer& bw, 
     }
     bad_run = bad_pos >= 0 ? (bad_pos - bad_prev - 1) % JB_MAX_RUN : 0;
     bw.put(0u, 8);
+}
+
+// The common case of the above -- every amplitude of the chunk fits (the quantiser stage counted none that does not) --
+// into a staging row of FF_STAGE_W words: the run of the loop per non-zero coefficient is what the kernel spends a
+// fifth of its instructions on, so it is kept branch-free.  Pending bits sit left-aligned in `acc`; every code stores
+// the word it lands in (again, if the word is not full yet); words beyond FF_STAGE_CAP fall on the row's spare last
+// word and are only counted.  Returns the block's length in bytes.
+__device__ __forceinline__ unsigned ff_pack_block_fit(const uint32_t* rowp, uint32_t* out) {
+    uint32_t lo, hi;
+    ff_block_mask(rowp, lo, hi);
+    const int16_t* c16 = (const int16_t*)rowp;
+    uint32_t acc = 0;
+    int nacc = 0, nw = 0;
+    auto put = [&](uint32_t vl, int k) {                         // vl: the k <= 23 bits, left-aligned
+        const uint32_t word = acc | (vl >> nacc);
+        const uint32_t rest = __funnelshift_r(0u, vl, nacc);     // vl << (32 - nacc); 0 for nacc == 0
+        out[jb_min(nw, FF_STAGE_CAP)] = jb_bswap32(word);
+        const int t = nacc + k;
+        acc = t >= 32 ? rest : word;
+        nw += t >> 5;
+        nacc = t & 31;
+    };
+    int off = 0;                                                 // run = off + b: minus the position behind the previous non-zero
+    #pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        uint32_t m = half ? hi : lo;
+        const int16_t* cb = c16 + 32 * half;
+        while (m) {
+            const int b = __ffs((int)m) - 1;
+            m &= m - 1;
+            const int amp = cb[b];
+            int run = off + b;
+            off = ~b;                                            // -(b + 1)
+            #pragma unroll 1
+            while (run >= JB_MAX_RUN) { put(0xF0000000u, 8); run -= JB_MAX_RUN; }     // (rare: at most three times)
+            const uint32_t mag = (uint32_t)(amp < 0 ? -amp : amp);
+            const int sz1 = 32 - __clz((int)mag);                // bit length = size - 1
+            const uint32_t head = ((uint32_t)run << 5) | ((uint32_t)(sz1 + 1) << 1) | (amp > 0 ? 1u : 0u);
+            put((head << 23) | (mag << (23 - sz1)), 9 + sz1);
+        }
+        off += 32;
+    }
+    put(0u, 8);
+    out[jb_min(nw, FF_STAGE_CAP)] = jb_bswap32(acc);
+    return ((unsigned)nw * 32u + (unsigned)nacc + 7u) >> 3;
 }
 
 // ---- the kernel -------------------------------------------------------------------------------
@@ -206,18 +261,14 @@ jb_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfKernelArgs 
         const uint32_t z = a.t.zz[u * 8 + v];
         if (u < 4) zzlo |= z << (8 * u); else zzhi |= z << (8 * (u - 4));
     }
-    // near-tie threshold: |frac - .5| < tolY[u][v] * qm[u] (+ relative term), tolY = row(u) * col(v) factor
-    float tol_row[8];
-    float tol_col;
-    {
-        // qtol[u*8+v] = tolY[u][v] * |qmult| + 1e-7 with tolY separable in (u, v): recover the two factors
-        // from the table itself so that the bound stays the one jb_tables.cu derived
-        #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const float m0 = fabsf(a.t.qmult[u * 8 + v]);
-            tol_row[u] = m0 > 0.f ? (a.t.qtol[u * 8 + v] - 1e-7f) / m0 : 0.f;     // = tolY[u][v]
-        }
-        tol_col = 1.0f;
+    // near a tie  <=>  |frac - .5| < tol + 2.4e-7 |val|, tol = qtol[u][v] the bound jb_tables.cu derived for the fp32 path:
+    // thr[u] = .5 - tol, compared with |val - rint(val)| + 2.4e-7 |val|
+    float thr[8];
+    #pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const float m0 = fabsf(a.t.qmult[u * 8 + v]);
+        const float tol = m0 > 0.f ? (a.t.qtol[u * 8 + v] - 1e-7f) / m0 * m0 : 0.f;
+        thr[u] = 0.5f - 1e-7f - tol;
     }
     const bool refine_on = !(g.flags & JB_FLAG_NO_REFINE);
     const bool aligned = ka.aligned != 0;
@@ -363,9 +414,8 @@ jb_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfKernelArgs 
                 const float t = val + 12582912.0f;          // 1.5 * 2^23: rounds half-even to an integer
                 const float dd = val - (t - 12582912.0f);
                 qi[u] = __float_as_int(t) - 0x4B400000;
-                // near a tie  <=>  |frac - .5| < tol + 2.4e-7 |val|   (tol = tolY * |qm| + 1e-7)
                 const float e = fmaf(fabsf(val), 2.4e-7f, fabsf(dd));
-                if (e > 0.5f - 1e-7f - tol_row[u] * fabsf(qm[u]) * tol_col) nearmask |= 1u << u;
+                if (e > thr[u]) nearmask |= 1u << u;
             }
             if (refine_on && __any_sync(0xffffffffu, nearmask != 0)) {
                 // the box sums go back to shared memory only now: nearly every iteration skips this
@@ -460,7 +510,10 @@ jb_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfKernelArgs 
             uint32_t* stage = (uint32_t*)ws.tile[slot];
             dirty = true;
             unsigned len = 0;
-            if (lane < ck.nvalid) {
+            if (ws.nbig == 0) {
+                // (no amplitude of this chunk is too large for its size field: the lean packer)
+                if (lane < ck.nvalid) len = ff_pack_block_fit(ws.coef + lane * FF_COEF_W, stage + lane * FF_STAGE_W);
+            } else if (lane < ck.nvalid) {
                 JbBitWriter bw;
                 bw.init(stage + lane * FF_STAGE_W, FF_STAGE_CAP);
                 int bad_pos, bad_run;
@@ -491,8 +544,25 @@ jb_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfKernelArgs 
                 // write the chunk with 128-bit stores; the slot is 16-byte aligned
                 __syncwarp();
                 uint8_t* cbuf = (uint8_t*)ws.coef;
-                const uint8_t* sb = (const uint8_t*)(stage + lane * FF_STAGE_W);
-                for (unsigned j = 0; j < len; ++j) cbuf[excl + j] = sb[j];
+                // lane t moves its row to byte `excl`: single bytes up to the first word boundary of the destination,
+                // then whole words funnelled out of pairs of source words, then the last bytes (the neighbours' rows
+                // share the first and the last word)
+                const uint32_t* sw = stage + lane * FF_STAGE_W;
+                const uint8_t* sb = (const uint8_t*)sw;
+                unsigned j = 0, d = excl;
+                while ((d & 3u) && j < len) cbuf[d++] = sb[j++];
+                if (j < len) {
+                    const unsigned nfull = (len - j) >> 2, sh = 8u * j;          // (j < 4 here)
+                    uint32_t* dw = (uint32_t*)(cbuf + d);
+                    uint32_t cur = sw[0];
+                    for (unsigned k = 0; k < nfull; ++k) {
+                        const uint32_t nxt = sw[k + 1];                          // (at most word FF_STAGE_CAP of the row)
+                        dw[k] = __funnelshift_r(cur, nxt, sh);
+                        cur = nxt;
+                    }
+                    j += 4u * nfull; d += 4u * nfull;
+                    while (j < len) cbuf[d++] = sb[j++];
+                }
                 __syncwarp();
                 const uint4* c16 = (const uint4*)cbuf;
                 for (unsigned i = lane; i < (total + 15u) >> 4; i += 32) ((uint4*)slot)[i] = c16[i];

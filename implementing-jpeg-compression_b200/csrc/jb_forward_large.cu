@@ -27,6 +27,7 @@
 // No tensor-core variant: after the half-length trick the contraction is ~1 MAC per source byte; ncu
 // (profiles/) shows the FMA pipe far from saturated -- SURVEY.md section 7.2.
 #include <cuda.h>
+#include <type_traits>
 #include <string.h>
 
 #include "jb_common.cuh"
@@ -265,7 +266,50 @@ jb_fwd_large_kernel(const __grid_constant__ CUtensorMap tmap, const FlKernelArgs
                 const uint32_t* t32 = (const uint32_t*)tile + w0;
                 const int partner = D - 1 - lane;                                  // (lanes < D)
                 constexpr int RW = FL_TILE_ROW / 4;                                // words per tile row
-                if (BS > 0 && BS <= 5) {
+                if constexpr (BS == 5 && D == 24) {
+                    // config 3 (side 120, so xoff is 0 or 8): lane i < D sums sample row i -- tile rows 5 i .. 5 i + 4, each
+                    // eight 128-bit loads and 24 x 2 dot products under compile-time byte masks into 24 accumulators --
+                    // and forms the even / odd sums of its row without leaving its registers.  Rows are 144 bytes apart:
+                    // the eight lanes of a load phase fall on distinct bank groups.
+                    if (lane < D) {
+                        uint32_t acc[D];
+                        #pragma unroll
+                        for (int jj = 0; jj < D; ++jj) acc[jj] = 0x4B000000u;     // bit pattern of 2^23: exact int -> float below
+                        const uint4* rows = (const uint4*)(tile + (size_t)(5 * lane) * FL_TILE_ROW);
+                        auto sum_rows = [&](auto xw_tag) {
+                            constexpr int XW = decltype(xw_tag)::value;          // xoff in words
+                            #pragma unroll
+                            for (int k = 0; k < 5; ++k) {
+                                uint32_t w[32];
+                                #pragma unroll
+                                for (int c = 0; c < 8; ++c) {
+                                    const uint4 v = rows[k * (FL_TILE_ROW / 16) + c];
+                                    w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
+                                }
+                                #pragma unroll
+                                for (int jj = 0; jj < D; ++jj) {
+                                    const int b0 = 4 * XW + 5 * jj, wi = b0 >> 2, o = b0 & 3;
+                                    acc[jj] = __dp4a(w[wi], 0x01010101u << (8 * o), acc[jj]);               // bytes o..3
+                                    acc[jj] = __dp4a(w[wi + 1], 0x01010101u >> (8 * (3 - o)), acc[jj]);     // bytes 0..o
+                                }
+                            }
+                        };
+                        if (xoff == 0) sum_rows(std::integral_constant<int, 0>()); else sum_rows(std::integral_constant<int, 2>());
+                        float e[H], od[H];
+                        #pragma unroll
+                        for (int jj = 0; jj < H; ++jj) {
+                            const float f = __uint_as_float(acc[jj]) - 8388608.0f, p = __uint_as_float(acc[D - 1 - jj]) - 8388608.0f;
+                            e[jj] = f + p; od[jj] = f - p;
+                        }
+                        float4* de = (float4*)(sXe + lane * L.xs);
+                        float4* dd = (float4*)(sXo + lane * L.xs);
+                        #pragma unroll
+                        for (int q4 = 0; q4 < H / 4; ++q4) {
+                            de[q4] = make_float4(e[4 * q4], e[4 * q4 + 1], e[4 * q4 + 2], e[4 * q4 + 3]);
+                            dd[q4] = make_float4(od[4 * q4], od[4 * q4 + 1], od[4 * q4 + 2], od[4 * q4 + 3]);
+                        }
+                    }
+                } else if (BS > 0 && BS <= 5) {
                     // compile-time block_size whose runs touch two words at most: everything unrolled, four sample rows
                     // (8 BS independent loads, 4 accumulator chains) in flight at a time
                     #pragma unroll
