@@ -457,21 +457,40 @@ jb_fwd_large_kernel(const __grid_constant__ CUtensorMap tmap, const FlKernelArgs
                 // and dealt with behind the loop
                 unsigned nearmask = 0, bigmask = 0;
                 int16_t* const cout = MODE == 1 ? a.coeffs_out + ((size_t)plane * g.nblocks + blk) * n : crow;
+                float vmax = 0.f;
                 #pragma unroll
                 for (int r = 0; r < RT; ++r) {
                     const int u = 2 * (ug * RT + r) + upar;
+                    const int idx0 = u * D + kg * KT;                   // (even: 8-byte aligned table rows)
                     #pragma unroll
-                    for (int q = 0; q < KT; ++q) {
-                        const int idx = u * D + kg * KT + q;
-                        const float val = y[r][q] * sQm[idx];
-                        const float tt = val + 12582912.0f;             // 1.5 * 2^23: rounds half-even to an integer
-                        const int qi = __float_as_int(tt) - 0x4B400000;
-                        const float dd = fabsf(val - (tt - 12582912.0f));
-                        if (fmaf(fabsf(val), 2.4e-7f, dd) > sThr[idx]) nearmask |= 1u << (r * KT + q);
-                        if (qi > JB_MAX_AMP || qi < -JB_MAX_AMP) bigmask |= 1u << (r * KT + q);
-                        cout[sZz[idx]] = (int16_t)max(-32767, min(32767, qi));
-                        if (bigmask >> (r * KT + q) & 1u) y[r][q] = __int_as_float(qi);       // (kept for the report below)
+                    for (int q = 0; q < KT; q += 2) {
+                        const float2 qm2 = *(const float2*)(sQm + idx0 + q), th2 = *(const float2*)(sThr + idx0 + q);
+                        const uint32_t zz2 = *(const uint32_t*)(sZz + idx0 + q);
+                        #pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const float val = y[r][q + h] * (h ? qm2.y : qm2.x);
+                            vmax = fmaxf(vmax, fabsf(val));
+                            const float tt = val + 12582912.0f;         // 1.5 * 2^23: rounds half-even to an integer
+                            const int qi = __float_as_int(tt) - 0x4B400000;
+                            const float dd = fabsf(val - (tt - 12582912.0f));
+                            if (fmaf(fabsf(val), 2.4e-7f, dd) > (h ? th2.y : th2.x)) nearmask |= 1u << (r * KT + q + h);
+                            cout[h ? zz2 >> 16 : zz2 & 0xFFFFu] = (int16_t)qi;
+                            y[r][q + h] = __int_as_float(qi);           // (kept for the rare case below)
+                        }
                     }
+                }
+                if (vmax > (float)JB_MAX_AMP - 0.75f) {
+                    // some amplitude may not fit the 15-bit size field: store it saturated, and see below
+                    #pragma unroll
+                    for (int r = 0; r < RT; ++r)
+                        #pragma unroll
+                        for (int q = 0; q < KT; ++q) {
+                            const int qi = __float_as_int(y[r][q]);
+                            if (qi > JB_MAX_AMP || qi < -JB_MAX_AMP) {
+                                bigmask |= 1u << (r * KT + q);
+                                cout[sZz[(2 * (ug * RT + r) + upar) * D + kg * KT + q]] = (int16_t)max(-32767, min(32767, qi));
+                            }
+                        }
                 }
                 if (!refine_on) nearmask = 0;
                 if (nearmask | bigmask) {

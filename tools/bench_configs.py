@@ -169,6 +169,12 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "config3":
         run("3b: 3840x2160 bs5 d24 divide 1000, batch of 8", 2160, 3840, 5, 24, "DCT", "divide", 1000, 8, steps=2, warmup=1)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "single":
+        # the single-image configurations only (launch lists of the latency-bound cases)
+        run("1: 512x512 defaults, single image", 512, 512, 4, 8, "DCT", "qtable", None, 1, steps=2, warmup=1)
+        run("2: 3840x2160 DCT qtable, single image", 2160, 3840, 4, 8, "DCT", "qtable", None, 1, steps=2, warmup=1)
+        run("3: 3840x2160 bs5 d24 divide 1000, single image", 2160, 3840, 5, 24, "DCT", "divide", 1000, 1, steps=2, warmup=1)
+        return
     out.append(run("1: 512x512 defaults, single image", 512, 512, 4, 8, "DCT", "qtable", None, 1, check_planes=3))
     out.append(run("1b: 512x512 defaults, batch of 1024", 512, 512, 4, 8, "DCT", "qtable", None, 1024))
     out.append(run("2: 3840x2160 DCT qtable, single image", 2160, 3840, 4, 8, "DCT", "qtable", None, 1))
