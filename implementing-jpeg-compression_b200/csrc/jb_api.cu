@@ -268,6 +268,7 @@ static int jb_inverse_common(int mode, const uint8_t* d_in, size_t in_bytes, con
         f.pdl = (g.flags & JB_FLAG_PDL) ? 1 : 0;
         f.tile_first = (unsigned*)(ws + L.tile_first);
         f.fallback = (unsigned*)(ws + L.fallback);
+        f.notplain = (unsigned*)(ws + L.notplain);
         f.big_list = (unsigned*)(ws + L.big_list);
         f.block_start = (unsigned*)(ws + L.block_start);
         f.tile_exit = (unsigned*)(ws + L.tile_exit);

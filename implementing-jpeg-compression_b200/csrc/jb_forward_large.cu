@@ -35,7 +35,7 @@
 #include "jb_forward.cuh"
 #include "jb_refine.cuh"
 
-#define FL_WARPS 9
+#define FL_WARPS 10                    // at most; fewer when the per-warp buffers of a geometry do not fit (fl_layout)
 #define FL_BLOCK_BUF_WORDS 96          // 384 bytes of packed output per block in shared memory; longer blocks: serial path
 #define FL_TILE_ROW 144                // bytes per tile row in shared memory = TMA box width: a tile row of up to 128 bytes
                                        // plus up to 15 bytes in front of it -- the box has to start on a 16-byte
@@ -49,6 +49,7 @@ struct FlLayout {
     int ts;                 // floats per row of Te / To
     size_t ch, qm, thr, zz;                         // CTA-wide tables
     size_t warp0, tile, xe, te, crow, obuf, big, rq, bar, warp_bytes, total;
+    int warps;              // warps per CTA that fit the 227 KB of one SM
 };
 
 __host__ __device__ inline FlLayout fl_layout(int d, int side) {
@@ -67,14 +68,21 @@ __host__ __device__ inline FlLayout fl_layout(int d, int side) {
     L.tile = w; w += jb_align_up((size_t)side * FL_TILE_ROW, 128);
     L.xe = w;   w += jb_align_up((size_t)2 * d * L.xs * 4, 16);   // Xe rows, then Xo rows
     L.te = w;   w += jb_align_up((size_t)2 * L.h * L.ts * 4, 16); // Te rows (j < h), then To rows
-    L.crow = w; w += jb_align_up((size_t)n * 2, 16);
-    L.obuf = w; w += (size_t)(FL_BLOCK_BUF_WORDS + 2) * 4;
+    // Two buffers live inside others whose contents are dead by then: the quantised coefficients (written once the
+    // whole warp has left the column pass) in Te / To, the packed bytes of the block (built after the float64
+    // re-evaluation, the last reader of the box sums) in Xe / Xo -- the kilobyte and a half per warp is what puts a tenth
+    // warp on the SM for config 3.
+    L.crow = L.te;
+    L.obuf = L.xe;
     L.big = w;  w += (size_t)(1 + 2 * FL_BIG_CAP) * 4;
     L.rq = w;   w += 4 + (size_t)FL_RQ_CAP * 2 + 4;
     w = jb_align_up(w, 16);
     L.bar = w;  w += 16;
     L.warp_bytes = jb_align_up(w, 128);
-    L.total = L.warp0 + (size_t)FL_WARPS * L.warp_bytes;
+    const size_t budget = 227 * 1024 - FL_WARPS * 32 * 4;       // (the kernel's static shared memory)
+    L.warps = (int)((budget - L.warp0) / L.warp_bytes);
+    if (L.warps > FL_WARPS) L.warps = FL_WARPS;
+    L.total = L.warp0 + (size_t)(L.warps > 0 ? L.warps : 1) * L.warp_bytes;
     return L;
 }
 
@@ -82,7 +90,7 @@ bool jb_fwd_large_eligible(const JbGeom& g) {
     if (g.transform != JB_TRANSFORM_DCT) return false;
     if (g.d != 16 && g.d != 24 && g.d != 32) return false;
     const int side = g.d * g.bs;
-    return side <= 128 && fl_layout(g.d, side).total <= 227 * 1024;
+    return side <= 128 && fl_layout(g.d, side).warps >= 4;
 }
 
 struct FlKernelArgs {
@@ -452,6 +460,7 @@ jb_fwd_large_kernel(const __grid_constant__ CUtensorMap tmap, const FlKernelArgs
                         }
                     }
                 }
+                __syncwarp();                    // (the quantised row shares its memory with Te / To: every lane has read them)
                 // quantise all RT x KT outputs straight through (no branches); the rare cases -- a value within the fp32
                 // error bound of a rounding tie, an amplitude beyond the 15-bit size field -- are collected in bit masks
                 // and dealt with behind the loop
@@ -686,7 +695,7 @@ static cudaError_t fl_launch_t(const CUtensorMap& map, const FlKernelArgs& ka, c
     const unsigned want = ka.a.n_chunks;
     const unsigned grid = want < (unsigned)sms ? want : (unsigned)sms;
     if (grid == 0) return cudaSuccess;
-    return jb_launch_ex(jb_fwd_large_kernel<D, MODE, BS>, dim3(grid), dim3(FL_WARPS * 32), smem, s,
+    return jb_launch_ex(jb_fwd_large_kernel<D, MODE, BS>, dim3(grid), dim3(fl_layout(D, D * ka.a.g.bs).warps * 32), smem, s,
                         (ka.a.g.flags & JB_FLAG_PDL) != 0, map, ka);
 }
 

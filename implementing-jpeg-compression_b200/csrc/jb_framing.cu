@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(1024) jb_frame_prep_kernel(JbFrameArgs f) {
             nt = (unsigned)((len + f.tile_bytes - 1) / f.tile_bytes);
             if (len > f.in_bytes || f.plane_off[s] > f.in_bytes - len) { bad = true; nt = 0; }     // reaches beyond the input buffer
             f.fallback[s] = f.force_serial ? 1u : 0u;
+            f.notplain[s] = 0u;
             if (nt > JB_REACH_SMALL_CAP) f.big_list[1 + atomicAdd(f.big_list, 1u)] = (unsigned)s;
         }
         unsigned total;
@@ -199,6 +200,24 @@ __global__ void __launch_bounds__(1024) jb_frame_prep_kernel(JbFrameArgs f) {
 // ---- F1: walk ----------------------------------------------------------------------------------
 #define JB_WALK_THREADS 128
 #define JB_WALK_HALO 64           // bytes staged beyond the tile; longer blocks continue from global memory
+
+// The usual stream: every walk leaves its tile for the next one (it takes a block longer than a whole tile to skip
+// one), i.e. every tile is on the chain of tiles and its entry is the exit of the tile before it.  The walks record
+// exactly that -- entry of tile t + 1 = exit of tile t -- and raise the stream's flag where it does not hold; only then
+// does jb_reach_stream work the chain out (and rewrite every entry).  t, nt: tile index and count within the stream.
+__device__ __forceinline__ void jb_walk_note_exit(const JbFrameArgs& f, int s, unsigned tile, unsigned t, unsigned nt,
+                                                  uint32_t exit_pos, uint32_t len) {
+    const unsigned tsh = (unsigned)__ffs((int)f.tile_bytes) - 1u;
+    bool ok;
+    if (t + 1u < nt) {
+        ok = exit_pos != JB_POS_INVALID && exit_pos < len && (exit_pos >> tsh) == t + 1u;
+        if (ok) f.tile_entry[tile + 1u] = exit_pos;
+    } else {
+        ok = exit_pos == len;
+    }
+    if (t == 0u) f.tile_entry[tile] = 0u;
+    if (!ok) f.notplain[s] = 1u;
+}
 
 // any tile size: every thread reads its tile straight from global memory and keeps its bitmap there
 __global__ void __launch_bounds__(JB_WALK_THREADS) jb_frame_walk_kernel(JbFrameArgs f) {
@@ -261,6 +280,7 @@ __global__ void __launch_bounds__(JB_WALK_THREADS) jb_frame_walk_kernel(JbFrameA
         }
     }
     f.tile_exit[tile] = exit_pos;
+    jb_walk_note_exit(f, s, tile, tile - f.tile_first[s], f.tile_first[s + 1] - f.tile_first[s], exit_pos, len);
 }
 
 // A block that runs past the staged window of its walk: parse it from global memory.
@@ -415,6 +435,7 @@ __global__ void __launch_bounds__(JB_WALK_THREADS) jb_frame_walk_smem_kernel(JbF
             }
         }
         f.tile_exit[tile] = exit_pos;
+        jb_walk_note_exit(f, s, tile, t0 + (unsigned)lane, nt, exit_pos, len);
     }
     __syncwarp();
     // the warp's bitmaps are consecutive in shared and in global memory
@@ -439,6 +460,9 @@ __device__ __forceinline__ void jb_reach_stream(const JbFrameArgs& f, int s, uin
     // a long stream is 16 K tiles for one CTA, and a loop of dependent L2 round trips was most of this kernel)
     const unsigned tsh = (unsigned)__ffs((int)T) - 1u;
     const unsigned bd = blockDim.x;
+    // every walk left its tile for the next one and the last one ended at the end of the stream: the walks have written
+    // the entries already (jb_walk_note_exit)
+    if (f.notplain[s] == 0u) return;
     for (unsigned base = tid; base < nt; base += 4u * bd) {
         uint32_t ex[4];
         #pragma unroll
@@ -521,6 +545,7 @@ __global__ void __launch_bounds__(1024) jb_frame_reach_kernel(JbFrameArgs f) {
         const int s = MIN_TILES ? (int)f.big_list[1 + wi] : (int)wi;
         const unsigned nt = f.tile_first[s + 1] - f.tile_first[s];
         if (nt < MIN_TILES) continue;                            // the smaller instantiation took it
+        if (nt != 0 && f.notplain[s] == 0u) continue;            // every tile on the chain: nothing to work out, however long
         if (nt > CAP) { if (CAP >= 40000u && tid == 0) f.fallback[s] = 1u; continue; }
         if (nt == 0) { if (tid == 0) f.fallback[s] = 1u; continue; }
         jb_reach_stream(f, s, (uint16_t*)reach_smem, (uint16_t*)reach_smem + CAP, (uint8_t*)(reach_smem + 4 * (size_t)CAP));
@@ -713,8 +738,8 @@ __global__ void __launch_bounds__(JB_STITCH_THREADS) jb_frame_stitch_kernel(JbFr
     const unsigned t0 = f.tile_first[s];
     const unsigned nt = f.tile_first[s + 1] - t0;
     const unsigned cap = f.stitch_cap;
-    if (nt == 0 || nt > cap) {
-        if (tid == 0) f.fallback[s] = 1u;                     // empty (invalid) or far longer than its peers
+    if (nt == 0 || (nt > cap && f.notplain[s] != 0u)) {
+        if (tid == 0) f.fallback[s] = 1u;                     // empty (invalid), or off the usual chain and far longer than its peers
         __syncthreads();
     } else {
         jb_reach_stream(f, s, (uint16_t*)stitch_smem, (uint16_t*)stitch_smem + cap, (uint8_t*)(stitch_smem + 4 * (size_t)cap));

@@ -30,6 +30,7 @@ struct JbDecLayout {
     size_t ctrl;         // control block (jb_common.cuh): chunk ticket, finished CTAs, status words
     size_t tile_first;   // uint32 [n_planes + 1]   first tile of each stream; [n_planes] = tile count
     size_t fallback;     // uint32 [n_planes]       stream needs the serial walk
+    size_t notplain;     // uint32 [n_planes]       some walk of the stream did not leave its tile for the next one
     size_t big_list;     // uint32 [n_planes + 1]   [0] = count, then the streams with more than 4096 tiles
     size_t block_start;  // uint32 [n_planes * nblocks]  byte offset of every block inside its stream
     size_t tile_exit;    // uint32 [max_tiles]  offset where the walk leaves the tile (or invalid)
@@ -56,6 +57,7 @@ static inline JbDecLayout jb_dec_layout(int d, int n_planes, long long nblocks_p
     L.ctrl = o;        o += JB_CTRL_BYTES;
     L.tile_first = o;  o += jb_align_up(((size_t)n_planes + 1) * 4, 256);
     L.fallback = o;    o += jb_align_up((size_t)n_planes * 4, 256);
+    L.notplain = o;    o += jb_align_up((size_t)n_planes * 4, 256);
     L.big_list = o;    o += jb_align_up(((size_t)n_planes + 1) * 4, 256);
     L.block_start = o; o += jb_align_up((size_t)n_planes * (size_t)nblocks_per_plane * 4, 256);
     L.tile_exit = o;   o += jb_align_up((size_t)L.max_tiles * 4, 256);
@@ -96,6 +98,7 @@ struct JbFrameArgs {
     size_t in_bytes;       // bytes readable at `in`; a stream that reaches beyond is malformed
     unsigned* tile_first;
     unsigned* fallback;
+    unsigned* notplain;
     unsigned* big_list;
     unsigned* block_start;
     unsigned* tile_exit;

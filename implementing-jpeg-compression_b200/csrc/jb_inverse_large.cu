@@ -100,13 +100,14 @@ __device__ __forceinline__ int il_decode_block(const uint8_t* stream, uint32_t s
     }
 }
 
-template <int D, int MODE>
+// BS: block_size as a compile-time constant (5: config 3), so that the row stores unroll; 0: any block_size at run time.
+template <int D, int MODE, int BS>
 __global__ void __launch_bounds__(IL_MAX_WARPS * 32, 1)
 jb_inv_large_kernel(const JbInvArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const JbGeom& g = a.g;
     constexpr int n = D * D, H = D / 2, RT = D / 8, KT = D / 4, ROWB = JB_CHUNK_LARGE * D;     // bytes per sample row of a chunk
-    const int bs = g.bs, side = D * bs;
+    const int bs = BS ? BS : g.bs, side = D * bs;
     const IlLayout L = il_layout(D);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NWARPS = blockDim.x >> 5;
     float* sBH = (float*)(smem + L.bh);
@@ -155,7 +156,7 @@ jb_inv_large_kernel(const JbInvArgs a) {
         }
     }
     const int nvec = (JB_CHUNK_LARGE * side) >> 4;               // 16-byte vectors per pixel row of a chunk
-    const bool fast_store_ok = aligned && bs >= 3 && bs <= 8;
+    const bool fast_store_ok = aligned && bs >= 3 && bs <= 8 && a.row_pitch < (1u << 24);     // (32-bit offsets inside a chunk row)
 
     const unsigned total_warps = gridDim.x * NWARPS;
     auto claim = [&](unsigned prev) -> unsigned {
@@ -310,6 +311,7 @@ jb_inv_large_kernel(const JbInvArgs a) {
                              x0 + JB_CHUNK_LARGE * side <= g.W && y0 + side <= g.H && (x0 & 15) == 0;
         if (fast_store_ok && one_row) {
             uint8_t* base = dstp + (size_t)y0 * a.row_pitch + x0;
+            const unsigned pitch32 = (unsigned)a.row_pitch;
             #pragma unroll 1
             for (int i = 0; i < D; ++i) {
                 const uint8_t* srow = samp + i * ROWB;
@@ -324,8 +326,14 @@ jb_inv_large_kernel(const JbInvArgs a) {
                         const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
                         const uint4 o = make_uint4(__byte_perm(lo, hi, sel[q][0]), __byte_perm(lo, hi, sel[q][1]),
                                                    __byte_perm(lo, hi, sel[q][2]), __byte_perm(lo, hi, sel[q][3]));
-                        uint8_t* d = base + (size_t)i * bs * a.row_pitch + 16 * v;
-                        for (int k = 0; k < bs; ++k) *(uint4*)(d + (size_t)k * a.row_pitch) = o;
+                        // (offsets inside one chunk row of blocks fit 32 bits: side <= 128 rows of one plane row each)
+                        uint8_t* d = base + (size_t)((unsigned)(i * bs) * pitch32 + 16u * (unsigned)v);
+                        if (BS) {
+                            #pragma unroll
+                            for (int k = 0; k < BS; ++k) *(uint4*)(d + (unsigned)k * pitch32) = o;
+                        } else {
+                            for (int k = 0; k < bs; ++k) *(uint4*)(d + (unsigned)k * pitch32) = o;
+                        }
                     }
                 }
             }
@@ -348,10 +356,10 @@ jb_inv_large_kernel(const JbInvArgs a) {
     jb_dec_epilogue(a);
 }
 
-template <int D, int MODE>
+template <int D, int MODE, int BS>
 static cudaError_t il_launch_t(const JbInvArgs& a, cudaStream_t s) {
     const IlLayout L = il_layout(D);
-    cudaError_t e = cudaFuncSetAttribute(jb_inv_large_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+    cudaError_t e = cudaFuncSetAttribute(jb_inv_large_kernel<D, MODE, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -359,16 +367,16 @@ static cudaError_t il_launch_t(const JbInvArgs& a, cudaStream_t s) {
     const unsigned want = a.n_chunks;
     const unsigned grid = want < (unsigned)sms ? want : (unsigned)sms;
     if (grid == 0) return cudaSuccess;
-    return jb_launch_ex(jb_inv_large_kernel<D, MODE>, dim3(grid), dim3(L.warps * 32), L.total, s,
+    return jb_launch_ex(jb_inv_large_kernel<D, MODE, BS>, dim3(grid), dim3(L.warps * 32), L.total, s,
                         (a.g.flags & JB_FLAG_PDL) != 0, a);
 }
 
 template <int MODE>
 static cudaError_t il_launch_d(const JbInvArgs& a, cudaStream_t s) {
     switch (a.g.d) {
-    case 16: return il_launch_t<16, MODE>(a, s);
-    case 24: return il_launch_t<24, MODE>(a, s);
-    default: return il_launch_t<32, MODE>(a, s);
+    case 16: return il_launch_t<16, MODE, 0>(a, s);
+    case 24: return a.g.bs == 5 ? il_launch_t<24, MODE, 5>(a, s) : il_launch_t<24, MODE, 0>(a, s);
+    default: return il_launch_t<32, MODE, 0>(a, s);
     }
 }
 
