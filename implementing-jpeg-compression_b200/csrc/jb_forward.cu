@@ -286,13 +286,9 @@ __device__ __forceinline__ void jb_ctrl_finish(const JbFwdArgs& a, int P) {
     a.ctrl[0] = (unsigned)Q;
 }
 
-__global__ void __launch_bounds__(JB_GATHER_WARPS * 32) jb_gather_chunks_kernel(JbFwdArgs a) {
-    const int lane = threadIdx.x & 31;
-    const unsigned c = blockIdx.x * JB_GATHER_WARPS + (threadIdx.x >> 5);
-    jb_pdl_trigger();
-    jb_pdl_wait();
-    if (blockIdx.x == 0 && threadIdx.x == 0) jb_ctrl_finish(a, (int)(__ldcg(a.ctrl + 1) & 1u));
-    if (c >= a.n_chunks) return;
+// one warp: chunk c from its slot to byte `base` of the output
+__device__ __forceinline__ void jb_gather_chunk(const JbFwdArgs& a, unsigned c, int lane, unsigned long long base, bool base_known,
+                                                const unsigned* s_off) {
     // 16-byte aligned slots: the dense array of 1 KB + 32 B ones, or the worst-case sized ones
     const uint8_t* src = a.slots_always_big ? a.tmp + (size_t)c * a.chunk_cap : a.tmp_small + (size_t)c * JB_SLOT_STRIDE;
     const uint4* s16 = (const uint4*)src;
@@ -317,9 +313,9 @@ __global__ void __launch_bounds__(JB_GATHER_WARPS * 32) jb_gather_chunks_kernel(
             pn[k] = __ldg(s32 + 4 * (lane + 32 * k) + 4);
         }
     }
-    const unsigned long long base = a.seg_total[c / JB_SCAN_SEG] + a.chunk_off[c];
+    if (!base_known) base = s_off ? (unsigned long long)s_off[c] : a.seg_total[c / JB_SCAN_SEG] + a.chunk_off[c];
     if (lane == 0 && c % (unsigned)a.g.cpp == 0) a.plane_off[c / (unsigned)a.g.cpp] = base;
-    if (base + len > a.out_cap) return;                       // flagged by the scan kernel
+    if (base + len > a.out_cap) return;                       // flagged by the scan
     uint8_t* dst = a.out + base;
     // head bytes up to a 4-byte boundary of dst; then every lane moves 16 bytes per pass: one
     // 128-bit load + the following word, funnel-shifted into four aligned words; then the tail
@@ -350,6 +346,50 @@ __global__ void __launch_bounds__(JB_GATHER_WARPS * 32) jb_gather_chunks_kernel(
     if (tail0 + lane < len) dst[tail0 + lane] = src[tail0 + lane];
 }
 
+__global__ void __launch_bounds__(JB_GATHER_WARPS * 32) jb_gather_chunks_kernel(JbFwdArgs a) {
+    const int lane = threadIdx.x & 31;
+    const unsigned c = blockIdx.x * JB_GATHER_WARPS + (threadIdx.x >> 5);
+    jb_pdl_trigger();
+    jb_pdl_wait();
+    if (blockIdx.x == 0 && threadIdx.x == 0) jb_ctrl_finish(a, (int)(__ldcg(a.ctrl + 1) & 1u));
+    if (c >= a.n_chunks) return;
+    jb_gather_chunk(a, c, lane, 0ull, false, nullptr);
+}
+
+// Scan and gather in one launch for calls of a few frames (up to JB_TAIL_SMALL chunks), where a launch costs as much
+// as the work: every CTA scans all the chunk lengths for itself (a few kilobytes out of L2) and gathers its own eight
+// chunks; CTA 0 also ends the call.
+#define JB_TAIL_SMALL 2048u
+__global__ void __launch_bounds__(JB_GATHER_WARPS * 32) jb_scan_gather_small_kernel(JbFwdArgs a) {
+    __shared__ unsigned s_off[JB_TAIL_SMALL];
+    __shared__ unsigned s_warp[33];
+    const int lane = threadIdx.x & 31;
+    jb_pdl_trigger();
+    jb_pdl_wait();
+    constexpr unsigned PER = JB_TAIL_SMALL / (JB_GATHER_WARPS * 32);
+    unsigned len[PER], sum = 0;
+    #pragma unroll
+    for (unsigned k = 0; k < PER; ++k) {
+        const unsigned c = threadIdx.x * PER + k;
+        len[k] = c < a.n_chunks ? __ldcg(a.chunk_len + c) : 0u;
+        sum += len[k];
+    }
+    unsigned total;
+    unsigned ex = jb_block_excl_scan(sum, s_warp, &total);
+    #pragma unroll
+    for (unsigned k = 0; k < PER; ++k) { s_off[threadIdx.x * PER + k] = ex; ex += len[k]; }
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const int P = (int)(__ldcg(a.ctrl + 1) & 1u);
+        a.plane_off[a.n_planes] = total;
+        if (total > a.out_cap) jb_set_error(jb_ctrl_status(a, P), JB_ERR_OUT_CAPACITY);
+        jb_ctrl_finish(a, P);
+    }
+    const unsigned c = blockIdx.x * JB_GATHER_WARPS + (threadIdx.x >> 5);
+    if (c >= a.n_chunks) return;
+    jb_gather_chunk(a, c, lane, 0ull, false, s_off);
+}
+
 // calls that end without a gather pass (stage entry point: coefficients only)
 __global__ void jb_finish_kernel(JbFwdArgs a) { jb_ctrl_finish(a, (int)(__ldcg(a.ctrl + 1) & 1u)); }
 
@@ -377,6 +417,9 @@ cudaError_t jb_launch_gather(const JbFwdArgs& a, cudaStream_t s) {
     jb_prof_mark(1, s);                                // the fused forward kernel was launched just before
     if (a.n_chunks == 0) return jb_launch_finish(a, s);
     const bool pdl = (a.g.flags & JB_FLAG_PDL) != 0;
+    if (a.n_chunks <= JB_TAIL_SMALL)
+        return jb_launch_ex(jb_scan_gather_small_kernel, dim3((a.n_chunks + JB_GATHER_WARPS - 1) / JB_GATHER_WARPS),
+                            dim3(JB_GATHER_WARPS * 32), 0, s, pdl, a);
     const unsigned n_seg = (a.n_chunks + JB_SCAN_SEG - 1) / JB_SCAN_SEG;
     cudaError_t e = jb_launch_ex(jb_scan_kernel, dim3(n_seg), dim3(JB_SCAN_SEG), 0, s, pdl, a, n_seg);
     if (e != cudaSuccess) return e;

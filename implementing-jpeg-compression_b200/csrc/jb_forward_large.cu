@@ -239,9 +239,14 @@ jb_fwd_large_kernel(const __grid_constant__ CUtensorMap tmap, const FlKernelArgs
         bool in_flight = first_in_flight;
         first_in_flight = false;
 
-        for (int gi = 0; gi < nvalid; ++gi) {
+        int by = blk0 / hb, bx = blk0 - by * hb;
+        for (int gi = 0; gi < nvalid; ++gi, ++bx) {
             const int blk = blk0 + gi;
-            const int by = blk / hb, bx = blk - by * hb;
+            if (bx >= hb) { bx = 0; ++by; }
+            // the ticket of the chunk after this one is drawn a block early: the round trip of the atomic hides behind
+            // this block's box sums
+            unsigned early_ticket = 0;
+            if (gi + 1 == nvalid && lane == 0) early_ticket = static_chunks + atomicAdd(ticket, 1u);
             // ---- the tile of this block; xoff: where the block's first column sits in the tile rows ----
             int xoff = 0;
             if (in_flight) {
@@ -365,7 +370,7 @@ jb_fwd_large_kernel(const __grid_constant__ CUtensorMap tmap, const FlKernelArgs
                 int nplane = plane, nblk = blk + 1;
                 bool have = gi + 1 < nvalid;
                 if (!have) {
-                    next_chunk = claim();
+                    next_chunk = __shfl_sync(0xffffffffu, early_ticket, 0);
                     if (next_chunk < a.n_chunks) {
                         nplane = (int)(next_chunk / (unsigned)g.cpp);
                         nblk = (int)(next_chunk - (unsigned)nplane * (unsigned)g.cpp) * JB_CHUNK_LARGE;
