@@ -20,6 +20,7 @@ JB_FLAG_FORCE_GENERIC, JB_FLAG_NO_TMA, JB_FLAG_NO_REFINE, JB_FLAG_SERIAL_FRAMING
 JB_FLAG_REUSE_TABLES = 16
 JB_FLAG_TILE_DECODER = 64
 JB_FLAG_PDL = 128
+JB_F64_SAMPLES, JB_F64_TRANSFORM, JB_F64_PREROUNDING = 0, 1, 2
 JB_STATUS_WORDS = 4
 JB_MAX_DCT_SIZE = 32
 JB_MAX_BLOCK_SIZE = 255
@@ -55,6 +56,7 @@ SYMBOLS = {
     "jb_compress_planes": (_I, [_P, _SZ, _SZ, _I, _PP, _P, _SZ, _P, _P, _P, _SZ, _P]),
     "jb_decompress_planes": (_I, [_P, _SZ, _P, _P, _I, _PP, _P, _SZ, _SZ, _P, _P, _SZ, _P]),
     "jb_stage_forward_coeffs": (_I, [_P, _SZ, _SZ, _I, _PP, _P, _P, _P, _SZ, _P]),
+    "jb_stage_float64": (_I, [_P, _SZ, _SZ, _I, _PP, _I, _P, _P, _SZ, _P]),
     "jb_stage_pack": (_I, [_P, _I, _I, _I, _P, _SZ, _P, _P, _P, _SZ, _P]),
     "jb_stage_pack_workspace_bytes": (_SZ, [_I, _I, _I]),
     "jb_stage_unpack": (_I, [_P, _SZ, _P, _P, _I, _I, _I, _I, _P, _P, _P, _SZ, _P]),

@@ -54,11 +54,19 @@ extern "C" size_t jb_max_stream_bytes(const jb_params* p, int n_planes) {
 }
 
 // ---- compress ----------------------------------------------------------------------------------
+// the chunk size of this call (jb_call_chunk_blocks): geometry as the kernels of the call see it
+static JbGeom jb_geom_for_call(const JbGeom& g0, int n_planes) {
+    JbGeom g = g0;
+    g.chunk = jb_call_chunk_blocks(g.d, (long long)n_planes * g.nblocks);
+    g.cpp = (g.nblocks + g.chunk - 1) / g.chunk;
+    return g;
+}
+
 struct JbFwdWs { size_t ctrl, chunk_len, chunk_off, seg_total, tmp_small, tmp, total; unsigned chunk_cap; };
-static JbFwdWs jb_fwd_ws(int d, size_t n_chunks) {
+static JbFwdWs jb_fwd_ws(int d, int chunk, size_t n_chunks) {
     JbFwdWs w;
     size_t o = jb_align_up(jb_table_layout(d).total, 256);
-    w.chunk_cap = (unsigned)jb_align_up((size_t)jb_chunk_blocks(d) * jb_max_block_bytes(d * d) + 32, 16);
+    w.chunk_cap = (unsigned)jb_align_up((size_t)chunk * jb_max_block_bytes(d * d) + 32, 16);
     if (w.chunk_cap < 1024 + 32) w.chunk_cap = 1024 + 32;      // the gather kernel reads 1 KB ahead
     w.ctrl = o;      o += JB_CTRL_BYTES;
     w.chunk_len = o; o += jb_align_up(n_chunks * 4, 256);
@@ -73,14 +81,15 @@ static JbFwdWs jb_fwd_ws(int d, size_t n_chunks) {
 extern "C" size_t jb_compress_workspace_bytes(const jb_params* p, int n_planes) {
     JbGeom g;
     if (jb_make_geom(p, &g) != JB_OK || n_planes <= 0) return 0;
-    return jb_fwd_ws(g.d, (size_t)n_planes * g.cpp).total;
+    g = jb_geom_for_call(g, n_planes);
+    return jb_fwd_ws(g.d, g.chunk, (size_t)n_planes * g.cpp).total;
 }
 
 extern "C" size_t jb_stage_pack_workspace_bytes(int n_planes, int blocks_per_plane, int dct_size) {
     if (n_planes <= 0 || blocks_per_plane <= 0 || dct_size < 1 || dct_size > JB_MAX_DCT_SIZE) return 0;
     const size_t cb = (size_t)jb_chunk_blocks(dct_size);
     size_t cpp = ((size_t)blocks_per_plane + cb - 1) / cb;
-    return jb_fwd_ws(dct_size, (size_t)n_planes * cpp).total;
+    return jb_fwd_ws(dct_size, (int)cb, (size_t)n_planes * cpp).total;
 }
 
 // The status block of calls that do not run the self-cleaning protocol (word 1 = "no bad code yet" = all ones).
@@ -97,12 +106,13 @@ static int jb_reset_status(uint64_t* d_status, unsigned* d_ticket, cudaStream_t 
 }
 
 static int jb_forward_common(int mode, const uint8_t* d_planes, size_t plane_stride, size_t row_pitch,
-                             int n_planes, const JbGeom& g, uint8_t* d_out, size_t out_cap,
+                             int n_planes, const JbGeom& g_in, uint8_t* d_out, size_t out_cap,
                              uint64_t* d_plane_off, uint64_t* d_status, int16_t* d_coeffs_out,
                              const int32_t* d_coeffs_in, void* d_ws, size_t ws_bytes, cudaStream_t s) {
+    const JbGeom g = mode == 2 ? g_in : jb_geom_for_call(g_in, n_planes);       // (mode 2: the caller built g by hand)
     const size_t n_chunks = (size_t)n_planes * g.cpp;
     if (n_chunks > 0x7FFFFFFFull) return JB_ERR_UNSUPPORTED;
-    JbFwdWs w = jb_fwd_ws(g.d, n_chunks);
+    JbFwdWs w = jb_fwd_ws(g.d, g.chunk, n_chunks);
     if (!d_ws || ws_bytes < w.total) return JB_ERR_WORKSPACE;
     if (((uintptr_t)d_ws & 255) != 0) return JB_ERR_BAD_PARAM;
     char* ws = (char*)d_ws;
@@ -183,6 +193,26 @@ extern "C" int jb_stage_pack(const int32_t* d_coeffs, int n_planes, int blocks_p
                              d_coeffs, d_ws, ws_bytes, (cudaStream_t)stream);
 }
 
+cudaError_t jb_launch_stage_f64(const JbGeom& g, const JbTables& t, const uint8_t* d_planes, size_t plane_stride,
+                                size_t row_pitch, int n_planes, int which, double* d_out, cudaStream_t s);
+
+extern "C" int jb_stage_float64(const uint8_t* d_planes, size_t plane_stride, size_t row_pitch, int n_planes,
+                                const jb_params* p, int which, double* d_out, void* d_ws, size_t ws_bytes, void* stream) {
+    JbGeom g;
+    int rc = jb_make_geom(p, &g);
+    if (rc != JB_OK) return rc;
+    if (!d_planes || !d_out || n_planes <= 0 || n_planes > 65535) return JB_ERR_BAD_PARAM;
+    if (which != JB_F64_SAMPLES && which != JB_F64_TRANSFORM && which != JB_F64_PREROUNDING) return JB_ERR_BAD_PARAM;
+    if (row_pitch < (size_t)g.W || plane_stride < row_pitch * (size_t)(g.H - 1) + (size_t)g.W) return JB_ERR_BAD_PARAM;
+    if (!d_ws || ws_bytes < jb_table_layout(g.d).total) return JB_ERR_WORKSPACE;
+    if (((uintptr_t)d_ws & 255) != 0) return JB_ERR_BAD_PARAM;
+    cudaStream_t s = (cudaStream_t)stream;
+    const JbTables t = jb_tables_at(d_ws, g.d);
+    if (!(g.flags & JB_FLAG_REUSE_TABLES)) JB_CUDA_TRY(jb_launch_build_tables(g, t, s));
+    JB_CUDA_TRY(jb_launch_stage_f64(g, t, d_planes, plane_stride, row_pitch, n_planes, which, d_out, s));
+    return JB_OK;
+}
+
 // ---- measurement hooks -----------------------------------------------------------------------------
 static std::atomic<unsigned long long> g_jb_launches{0};
 void jb_note_launches(unsigned n) { g_jb_launches.fetch_add(n, std::memory_order_relaxed); }
@@ -223,10 +253,11 @@ extern "C" int jb_decompress_framing_path(const jb_params* p, int n_planes, size
 }
 
 static int jb_inverse_common(int mode, const uint8_t* d_in, size_t in_bytes, const uint64_t* d_plane_off,
-                             const uint64_t* d_plane_len, int n_planes, const JbGeom& g,
+                             const uint64_t* d_plane_len, int n_planes, const JbGeom& g_in,
                              uint8_t* d_planes_out, size_t plane_stride, size_t row_pitch,
                              int16_t* d_coeffs_out, const int16_t* d_coeffs_in, uint64_t* d_status,
                              void* d_ws, size_t ws_bytes, cudaStream_t s) {
+    const JbGeom g = mode == 1 ? g_in : jb_geom_for_call(g_in, n_planes);       // (mode 1: the caller built g by hand)
     const size_t n_chunks = (size_t)n_planes * g.cpp;
     if (n_chunks > 0x7FFFFFFFull) return JB_ERR_UNSUPPORTED;
     const size_t table_bytes = jb_table_layout(g.d).total;

@@ -11,6 +11,16 @@
 #define JB_CHUNK_LARGE 8       // ... for dct_size >= 16, where a block is hundreds of coefficients and a chunk of 32
                                // would be megabytes of pixels per scheduling unit (a 4K frame: 54 units for 148 SMs)
 __host__ __device__ inline int jb_chunk_blocks(int d) { return d >= 16 ? JB_CHUNK_LARGE : JB_CHUNK; }
+// Large blocks, small calls: a 4K frame of 24 x 24 blocks is 216 chunks of 8 for some 1500 resident warps, each of which
+// then works through its 8 blocks one after the other.  Calls of up to JB_SMALL_CALL_BLOCKS blocks in total are dealt in
+// chunks of JB_CHUNK_LARGE_SMALL blocks instead (2: the decoder's pixel rows of a chunk still start on 16-byte
+// boundaries for even block columns).  Both directions, workspace sizes included, derive the chunk from this one rule.
+#define JB_CHUNK_LARGE_SMALL 2
+#define JB_SMALL_CALL_BLOCKS 16384ll
+__host__ __device__ inline int jb_call_chunk_blocks(int d, long long total_blocks) {
+    if (d >= 16 && total_blocks <= JB_SMALL_CALL_BLOCKS) return JB_CHUNK_LARGE_SMALL;
+    return jb_chunk_blocks(d);
+}
 
 #define JB_U32_NONE 0xFFFFFFFFu
 #define JB_U16_NONE 0xFFFFu

@@ -1,7 +1,7 @@
 // jb_forward_large.cu -- compress direction for large blocks: DCT, dct_size 16 / 24 / 32, source tile rows of at
 // most 128 bytes (BASELINE.json config 3: --block_size 5 --dct_size 24 --quantization divide --qdivisor 1000).
 //
-// Work unit: a chunk of JB_CHUNK_LARGE = 8 consecutive blocks of one plane, claimed from the ticket counter by a
+// Work unit: a chunk of g.chunk = 8 (2 in small calls: jb_call_chunk_blocks) consecutive blocks of one plane, claimed from the ticket counter by a
 // WARP of a persistent grid (one CTA of FL_WARPS warps per SM); the warp takes its blocks through every stage on
 // its own, so nothing in the kernel is CTA-wide after the table preload:
 //   * the (d bs) x (d bs) source tile of a block arrives in the warp's shared-memory slot by TMA (one elected lane,
@@ -223,15 +223,15 @@ jb_fwd_large_kernel(const __grid_constant__ CUtensorMap tmap, const FlKernelArgs
     bool first_in_flight = false;
     if (chunk < a.n_chunks && use_tma) {
         const int plane = (int)(chunk / (unsigned)g.cpp);
-        const int blk0 = (int)(chunk - (unsigned)plane * (unsigned)g.cpp) * JB_CHUNK_LARGE;
+        const int blk0 = (int)(chunk - (unsigned)plane * (unsigned)g.cpp) * g.chunk;
         const int by = blk0 / hb, bx = blk0 - by * hb;
         if (interior(by, bx)) { issue(plane, by, bx); first_in_flight = true; }
         dirty = false;
     }
     while (chunk < a.n_chunks) {
         const int plane = (int)(chunk / (unsigned)g.cpp);
-        const int blk0 = (int)(chunk - (unsigned)plane * (unsigned)g.cpp) * JB_CHUNK_LARGE;
-        const int nvalid = jb_min(JB_CHUNK_LARGE, g.nblocks - blk0);
+        const int blk0 = (int)(chunk - (unsigned)plane * (unsigned)g.cpp) * g.chunk;
+        const int nvalid = jb_min(g.chunk, g.nblocks - blk0);
         const uint8_t* src = a.planes + (size_t)plane * a.plane_stride;
         uint8_t* slot = a.tmp + (size_t)chunk * a.chunk_cap;           // (the large path always uses the big slots)
         unsigned chunk_bytes = 0;
@@ -373,7 +373,7 @@ jb_fwd_large_kernel(const __grid_constant__ CUtensorMap tmap, const FlKernelArgs
                     next_chunk = __shfl_sync(0xffffffffu, early_ticket, 0);
                     if (next_chunk < a.n_chunks) {
                         nplane = (int)(next_chunk / (unsigned)g.cpp);
-                        nblk = (int)(next_chunk - (unsigned)nplane * (unsigned)g.cpp) * JB_CHUNK_LARGE;
+                        nblk = (int)(next_chunk - (unsigned)nplane * (unsigned)g.cpp) * g.chunk;
                         have = true;
                     }
                 }

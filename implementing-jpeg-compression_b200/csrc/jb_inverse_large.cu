@@ -1,7 +1,7 @@
 // jb_inverse_large.cu -- decompress direction for large blocks: DCT, dct_size 16 / 24 / 32, tile rows of at most
 // 128 bytes (BASELINE.json config 3: --block_size 5 --dct_size 24 --quantization divide --qdivisor 1000).
 //
-// The mirror of jb_forward_large.cu.  A warp of a persistent grid claims a chunk of JB_CHUNK_LARGE = 8 consecutive
+// The mirror of jb_forward_large.cu.  A warp of a persistent grid claims a chunk of g.chunk = 8 (small calls: 2) consecutive
 // blocks of one plane (block offsets come from jb_framing.cu) and takes it through every stage on its own:
 //   * eight lanes decode the eight blocks (rle_byte_stream.py:74-88, run_length_encoding.py:31-41) into natural
 //     (un-zigzagged, zigzag_order.py:101-119) int16 rows in shared memory;
@@ -155,7 +155,8 @@ jb_inv_large_kernel(const JbInvArgs a) {
             sel[q][j] = sj;
         }
     }
-    const int nvec = (JB_CHUNK_LARGE * side) >> 4;               // 16-byte vectors per pixel row of a chunk
+    const int cb = g.chunk;                                      // blocks per chunk: 8, or 2 in small calls (jb_call_chunk_blocks)
+    const int nvec = (cb * side) >> 4;                           // 16-byte vectors per pixel row of a chunk
     const bool fast_store_ok = aligned && bs >= 3 && bs <= 8 && a.row_pitch < (1u << 24);     // (32-bit offsets inside a chunk row)
 
     const unsigned total_warps = gridDim.x * NWARPS;
@@ -171,13 +172,13 @@ jb_inv_large_kernel(const JbInvArgs a) {
         const unsigned chunk = next_chunk;
         next_chunk = claim(chunk);
         const int plane = (int)(chunk / (unsigned)g.cpp);
-        const int blk0 = (int)(chunk % (unsigned)g.cpp) * JB_CHUNK_LARGE;
-        const int nvalid = jb_min(JB_CHUNK_LARGE, g.nblocks - blk0);
+        const int blk0 = (int)(chunk % (unsigned)g.cpp) * cb;
+        const int nvalid = jb_min(cb, g.nblocks - blk0);
 
         // ---- coefficients of the chunk in natural order ----
         {
             uint4* z = (uint4*)coef;
-            for (int i = lane; i < JB_CHUNK_LARGE * n / 8; i += 32) z[i] = make_uint4(0, 0, 0, 0);
+            for (int i = lane; i < cb * n / 8; i += 32) z[i] = make_uint4(0, 0, 0, 0);
         }
         __syncwarp();
         int my_umax = D - 1, my_vmax = D - 1;                   // of the block this lane decoded (lane < nvalid)
@@ -307,8 +308,8 @@ jb_inv_large_kernel(const JbInvArgs a) {
         uint8_t* dstp = plane0 + (size_t)plane * a.plane_stride;
         const int by0 = blk0 / hb, bx0 = blk0 - by0 * hb;
         const int x0 = bx0 * side, y0 = by0 * side;
-        const bool one_row = nvalid == JB_CHUNK_LARGE && bx0 + JB_CHUNK_LARGE <= hb &&
-                             x0 + JB_CHUNK_LARGE * side <= g.W && y0 + side <= g.H && (x0 & 15) == 0;
+        const bool one_row = nvalid == cb && bx0 + cb <= hb &&
+                             x0 + cb * side <= g.W && y0 + side <= g.H && (x0 & 15) == 0 && ((cb * side) & 15) == 0;
         if (fast_store_ok && one_row) {
             uint8_t* base = dstp + (size_t)y0 * a.row_pitch + x0;
             const unsigned pitch32 = (unsigned)a.row_pitch;

@@ -40,6 +40,34 @@ def forward_coefficients(planes, config, flags=0):
     return coeffs.cpu().numpy()
 
 
+def float64_stage(planes, config, which, flags=0):
+    """Float64 intermediates of the compress direction, as the reference's stages hand them on
+    (pipeline/base.py:42-72).  which: 'samples' -- after Padding, SubSampling, DCTPadding: (n, vb*d, hb*d) box means;
+    'transform' -- after BasisChange.execute: (n, vb, hb, d, d), real part; 'prerounding' -- after the quantiser's
+    scaling, the value np.round receives: same shape.  Computed in the reference's operation order (the arithmetic
+    that decides rounding ties inside the fused kernels, csrc/jb_refine.cuh)."""
+    lib = _lib.load()
+    dev = _require_cuda()
+    code = {"samples": _lib.JB_F64_SAMPLES, "transform": _lib.JB_F64_TRANSFORM, "prerounding": _lib.JB_F64_PREROUNDING}[which]
+    planes = torch.as_tensor(np.ascontiguousarray(planes, dtype=np.uint8)).to(dev)
+    if planes.dim() == 2:
+        planes = planes.unsqueeze(0)
+    n, h, w = planes.shape
+    p = config.c_params(flags)
+    g = geometry(config)
+    d = config.dct_size
+    if code == _lib.JB_F64_SAMPLES:
+        out = torch.zeros((n, g["vb"] * d, g["hb"] * d), dtype=torch.float64, device=dev)
+    else:
+        out = torch.zeros((n, g["vb"], g["hb"], d, d), dtype=torch.float64, device=dev)
+    ws_bytes = lib.jb_compress_workspace_bytes(ctypes.byref(p), n)
+    ws = _workspace.get("fwd", ws_bytes, dev)
+    rc = lib.jb_stage_float64(_ptr(planes), h * planes.stride(1) if n == 1 else planes.stride(0), planes.stride(1), n,
+                              ctypes.byref(p), code, _ptr(out), _ptr(ws), ws.numel(), _stream_ptr())
+    _raise_for_code(rc)
+    return out.cpu().numpy()
+
+
 def pack_coefficients(coeffs, dct_size):
     """coeffs: integer array (n_planes, blocks, d*d) (or (blocks, d*d)) in zigzag order."""
     lib = _lib.load()

@@ -196,6 +196,23 @@ int jb_stage_inverse_coeffs(const int16_t* d_coeffs, int n_planes, const jb_para
                             uint8_t* d_planes_out, size_t plane_stride, size_t row_pitch,
                             uint64_t* d_status, void* d_ws, size_t ws_bytes, void* stream);
 
+/* Float64 intermediates of the compress direction, as the reference's stages hand them on (pipeline/base.py:42-72;
+ * each stage's execute() result is the next stage's input):
+ *   JB_F64_SAMPLES      after Padding, SubSampling, DCTPadding (padding.py:8-12, subsampling.py:9-11,
+ *                       dct_padding.py:8-9): n_planes x (vb*d) x (hb*d) box means;
+ *   JB_F64_TRANSFORM    after BasisChange.execute (basis_change.py:11-26): n_planes x blocks_per_plane x d*d in
+ *                       natural (u, v) order, blocks in raster order; the real part for the DFT;
+ *   JB_F64_PREROUNDING  after the quantiser's scaling, the value np.round receives (quantizers.py:5-6, 16-17, 27-28,
+ *                       47-49): same shape.
+ * Computed operation for operation in the reference's order -- the arithmetic that decides rounding ties inside the
+ * fused kernels -- so the arrays compare bit for bit (DCT; DFT with dct_size 8).  A parity hook, not a fast path.
+ * Workspace: jb_compress_workspace_bytes(p, n_planes) is enough (only the tables are used). */
+#define JB_F64_SAMPLES     0
+#define JB_F64_TRANSFORM   1
+#define JB_F64_PREROUNDING 2
+int jb_stage_float64(const uint8_t* d_planes, size_t plane_stride, size_t row_pitch, int n_planes,
+                     const jb_params* p, int which, double* d_out, void* d_ws, size_t ws_bytes, void* stream);
+
 /* ---- colour conversion on either side of the path -------------------------
  * Replaces PIL's im.convert('YCbCr') before Jpeg.compress reads the bands (compress.py:9,
  * pipeline/__init__.py:103-106) and im.convert('RGB') after Jpeg.decompress stacks them (decompress.py:10,

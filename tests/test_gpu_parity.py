@@ -652,3 +652,89 @@ def test_no_write_outside_the_callers_buffers(jb, h, w, bs, d, tr, qn, qp, pitch
     if pitch_extra:
         gaps = torch.as_strided(dec_flat, (n, h, pitch_extra), (h * pitch, pitch, 1), storage_offset=dec_flat.storage_offset() + w)
         assert bool((gaps == 0xA5).all()), "decompress wrote between the rows"
+
+
+# ---- float64 stage hooks (jb_stage_float64): the reference's stage-by-stage intermediates ---------------------------
+# pipeline/base.py:42-72 -- every stage hands its execute() result to the next one.  The hook computes these arrays
+# with the arithmetic that decides rounding ties inside the fused kernels (csrc/jb_refine.cuh), so a bit-for-bit match
+# with the oracle pins that arithmetic on EVERY coefficient, not only on the few that land near a tie.
+F64_CASES = [
+    # h, w, bs, d, transform, quantiser, parameter, bitwise
+    (64, 96, 4, 8, "DCT", "qtable", None, True),
+    (61, 75, 4, 8, "DCT", "qtable", None, True),           # ragged: both edge replications
+    (97, 161, 3, 8, "DCT", "divide", 7, True),             # block_size not a power of two: the mean is a division
+    (40, 56, 1, 8, "DCT", "none", None, True),
+    (50, 70, 2, 4, "DCT", "discard", 3, True),
+    (120, 240, 5, 24, "DCT", "divide", 1000, True),        # config 3's geometry
+    (66, 130, 2, 16, "DCT", "divide", 10, True),
+    (64, 64, 1, 32, "DCT", "divide", 64, True),            # (undivided, the DC term of a 32 x 32 block overflows the size field)
+    (64, 96, 4, 8, "DFT", "qtable", None, True),           # pocketfft's radix-8 pass, operation for operation
+    (61, 75, 2, 8, "DFT", "divide", 3, True),
+    (48, 48, 2, 4, "DFT", "none", None, False),            # other DFT sizes: direct sums (not pocketfft's order)
+]
+
+
+@pytest.mark.parametrize("h,w,bs,d,tr,qn,qp,bitwise", F64_CASES)
+def test_float64_stage_intermediates_equal_the_oracles(jb, h, w, bs, d, tr, qn, qp, bitwise):
+    cfg, ocfg = _cfgs(jb, (h, w, bs, d, tr, qn, qp))
+    planes = [synth_plane(h, w, seed=100 + k) for k in range(2)]
+    planes[1][:, :] = np.random.default_rng(5).integers(0, 256, size=(h, w))          # noise: every coefficient busy
+    stack = np.stack(planes).astype(np.uint8)
+    samples = jb.stages.float64_stage(stack, cfg, "samples")
+    coeff = jb.stages.float64_stage(stack, cfg, "transform")
+    pre = jb.stages.float64_stage(stack, cfg, "prerounding")
+    for i, a in enumerate(planes):
+        x = rp.subsample(a.astype(np.int64), bs, d)                                    # stages 0-3
+        assert samples[i].shape == x.shape
+        assert np.array_equal(samples[i].view(np.int64), x.view(np.int64)), "box means differ"
+        y = rp.forward_transform(x, d, tr)                                             # BasisChange.execute
+        want_y = rp._blocks_view(np.real(y), d)
+        want_v = rp._blocks_view(rp.quantize_prerounding(y, d, qn, qp), d)             # the value np.round receives
+        if bitwise:
+            # (-0.0 == 0.0: compare values, then the bit patterns of everything that is not a zero)
+            for got, want, what in ((coeff[i], want_y, "transform"), (pre[i], want_v, "prerounding")):
+                assert np.array_equal(got, want), what
+                nz = want != 0
+                assert np.array_equal(got[nz].view(np.int64), np.ascontiguousarray(want[nz]).view(np.int64)), what
+        else:
+            scale = np.abs(want_y).max() + 1.0
+            assert np.abs(coeff[i] - want_y).max() <= 1e-12 * scale
+            assert np.abs(pre[i] - want_v).max() <= 1e-12 * scale
+        # and the integers of the product path are these values rounded, wherever they are not within an ulp of a tie
+        q = jb.stages.forward_coefficients(stack[i], cfg)[0]
+        zz = rp.to_zigzag(rp._from_blocks(np.round(pre[i])), d).reshape(q.shape)
+        if qn == "discard":
+            zz = rp.quantised_zigzag(a.astype(np.int64), ocfg).reshape(q.shape)
+        assert np.array_equal(q.astype(np.int64), zz.astype(np.int64))
+
+
+def test_float64_stage_rejects_bad_arguments(jb):
+    cfg, _ = _cfgs(jb, (32, 32, 2, 8, "DCT", "none", None))
+    with pytest.raises(KeyError):
+        jb.stages.float64_stage(np.zeros((32, 32), np.uint8), cfg, "nonsense")
+
+
+@pytest.mark.parametrize("h,w,bs,d,qn,qp,n_planes", [
+    (2160, 3840, 5, 24, "divide", 1000, 30),      # config 3, ten frames: 17 280 blocks -> chunks of 8 (one plane: chunks of 2)
+    (1000, 2000, 3, 16, "divide", 25, 4),         # 16 x 16 blocks, ragged edges: 3 528 blocks -> chunks of 2 both ways
+    (1536, 2048, 2, 32, "divide", 64, 12),        # 32 x 32 blocks: 9 216 blocks -> chunks of 2
+    (2048, 4096, 2, 16, "divide", 40, 3),         # 64 x 128 blocks x 3 planes = 24 576 blocks -> chunks of 8
+])
+def test_large_block_calls_of_either_chunk_size_agree(jb, h, w, bs, d, qn, qp, n_planes):
+    """The large-block kernels deal chunks of 8 blocks in big calls and chunks of 2 in small ones
+    (jb_call_chunk_blocks): a batch must give, plane for plane, the bytes and pixels of one-plane calls, and one plane
+    the oracle's."""
+    cfg, ocfg = _cfgs(jb, (h, w, bs, d, "DCT", qn, qp))
+    base = [synth_plane(h, w, 300 + k) for k in range(2)]
+    planes = [np.roll(base[k % 2], 17 * k, axis=1).astype(np.uint8) for k in range(n_planes)]
+    batch = jb.compress_bands(planes, cfg)
+    singles = [jb.compress_band(planes[k], cfg) for k in (0, 1, n_planes - 1)]
+    assert [batch[0], batch[1], batch[n_planes - 1]] == singles
+    rec = jb.decompress_bands(batch, cfg)
+    for k in (0, n_planes - 1):
+        assert np.array_equal(rec[k], jb.decompress_band(batch[k], cfg))
+    coeffs = jb.stages.forward_coefficients(planes[0], cfg)[0]
+    p64 = planes[0].astype(np.int64)
+    check_quantised(coeffs, rp.quantised_zigzag(p64, ocfg), rp.prerounding_zigzag(p64, ocfg), what="chunks")
+    assert batch[0] == rp.pack_blocks(coeffs.reshape(-1, d * d))
+    check_pixels(rec[0], rp.decompress_band(batch[0], ocfg), p64, what="chunks")
