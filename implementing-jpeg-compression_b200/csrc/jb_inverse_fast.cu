@@ -140,26 +140,62 @@ jb_inv_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FiKernelArgs 
     }
     if (tables_const) jb_pdl_wait();                                   // from here on: data the kernels before this one wrote
 
-    // Chunks are claimed from a device-wide counter, one ahead (the claim of the next chunk travels while this one
-    // is processed): with a fixed deal the slowest SM finished 36 % later than the fastest (ncu, sm__cycles_active
-    // min / max), i.e. the kernel ran 13 % longer than its average SM.  Without a counter (stage entry points,
-    // whose workspace holds only the tables) chunks are dealt round-robin.
+    // Chunks are claimed from a device-wide counter: with a fixed deal the slowest SM finished 36 % later than the
+    // fastest (ncu, sm__cycles_active min / max), i.e. the kernel ran 13 % longer than its average SM.  Without a counter
+    // (stage entry points, whose workspace holds only the tables) chunks are dealt round-robin.
+    // A chunk begins with three dependent round trips -- its ticket, the offsets of its blocks, its bytes -- which a
+    // warp on its own would sit out (a quarter of the kernel's stall samples).  They are spread over the chunk before:
+    // the ticket of chunk n + 1 is drawn at the top of chunk n and picked up behind its entropy decode, where the loads
+    // of the new chunk's block offsets are issued; a few transform iterations later those have landed and the first
+    // FI_PRE_WORDS words per lane of its bytes are fetched into registers (the shared-memory stage still holds chunk n).
+    // No deeper: a warp that holds tickets further ahead widens the set of chunks in flight across the GPU, and the
+    // pixel rows of neighbouring chunks stop meeting in the same DRAM pages (measured with a pipeline two chunks deep:
+    // 1.066 -> 1.123 ms at 1024 frames).  The first chunk of every warp is dealt statically, CTA-major (a single frame
+    // spreads over all SMs).
     const unsigned total_warps = gridDim.x * NWARPS;
     unsigned store_seq = 0;
-    auto claim = [&](unsigned prev) -> unsigned {
-        if (a.ticket == nullptr) return prev + total_warps;
-        unsigned c = 0;
-        if (lane == 0) c = total_warps + atomicAdd(a.ticket, 1u);
-        return __shfl_sync(0xffffffffu, c, 0);
+    constexpr int FI_PRE_WORDS = 8;                                     // 1 KB per chunk: an average chunk is ~0.6 KB
+    struct FiChunk {
+        int plane, blk0, nvalid;
+        unsigned my_start, end_raw;                                     // block offsets as loaded (lane < nvalid; lane 0)
+        unsigned long long len, off;
     };
-    // (first chunk dealt statically, CTA-major: a single frame spreads over all SMs; the rest from the counter)
-    unsigned next_chunk = blockIdx.x + gridDim.x * (unsigned)warp;
-    while (next_chunk < a.n_chunks) {
-        const unsigned chunk = next_chunk;
-        next_chunk = claim(chunk);
-        const int plane = (int)(chunk / (unsigned)g.cpp);
-        const int blk0 = (int)(chunk % (unsigned)g.cpp) * JB_CHUNK;
-        const int nvalid = jb_min(JB_CHUNK, g.nblocks - blk0);
+    auto describe = [&](unsigned c, FiChunk& k) {                       // issues the loads of a chunk's offsets
+        k.plane = (int)(c / (unsigned)g.cpp);
+        k.blk0 = (int)(c % (unsigned)g.cpp) * JB_CHUNK;
+        k.nvalid = jb_min(JB_CHUNK, g.nblocks - k.blk0);
+        k.my_start = 0u; k.end_raw = 0u; k.len = 0ull; k.off = 0ull;
+        if (MODE != 2) {
+            k.len = a.plane_len[k.plane];
+            k.off = a.plane_off[k.plane];
+            const unsigned* bs = a.block_start + (size_t)k.plane * g.nblocks + k.blk0;
+            if (lane < k.nvalid) k.my_start = bs[lane];
+            if (lane == 0 && k.blk0 + k.nvalid < g.nblocks) k.end_raw = bs[k.nvalid];
+        }
+    };
+    struct FiBytes { bool ok; unsigned c_start, c_end, mis, nwords; const uint32_t* wsrc; };
+    auto locate = [&](const FiChunk& k, FiBytes& y) {                   // (consumes the loads of describe)
+        y.c_start = __shfl_sync(0xffffffffu, k.my_start, 0);
+        const unsigned e0 = __shfl_sync(0xffffffffu, k.end_raw, 0);
+        y.c_end = (k.blk0 + k.nvalid < g.nblocks) ? e0 : (unsigned)k.len;
+        // (a stream must lie inside the caller's buffer: device-supplied offsets are not trusted)
+        y.ok = y.c_start <= y.c_end && y.c_end <= k.len && k.off <= a.in_bytes && k.len <= a.in_bytes - k.off;
+        const unsigned long long addr0 = (unsigned long long)(uintptr_t)(a.in + k.off + y.c_start);
+        y.mis = (unsigned)(addr0 & 3ull);
+        y.wsrc = (const uint32_t*)(uintptr_t)(addr0 - y.mis);
+        y.nwords = y.ok ? (((y.c_end - y.c_start) + y.mis + 3u) >> 2) : 0u;
+    };
+    unsigned chunk = blockIdx.x + gridDim.x * (unsigned)warp;
+    FiChunk cur_k, next_k;
+    uint32_t pre[FI_PRE_WORDS];
+    bool pre_valid = false;                                             // pre[] holds the first words of `chunk`
+    if (chunk < a.n_chunks) describe(chunk, cur_k);
+    while (chunk < a.n_chunks) {
+        unsigned pend = 0;                                              // lane 0: the next chunk
+        if (a.ticket != nullptr && lane == 0) pend = total_warps + atomicAdd(a.ticket, 1u);
+        unsigned next_chunk = 0xFFFFFFFFu;
+        bool have_next = false, next_pre = false, next_located = false;
+        const int plane = cur_k.plane, blk0 = cur_k.blk0, nvalid = cur_k.nvalid;
         const int nit = (nvalid + 3) >> 2;
 
         // ---- coefficients of the chunk in natural order ----
@@ -173,19 +209,11 @@ jb_inv_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FiKernelArgs 
             for (int idx = lane; idx < nvalid * 64; idx += 32)
                 ((int16_t*)(w_coef + (idx >> 6) * FF_COEF_W))[s_izz[idx & 63]] = src[idx];
         } else {
-            const unsigned long long len = a.plane_len[plane];
-            const uint8_t* stream = a.in + a.plane_off[plane];
-            const unsigned* bs = a.block_start + (size_t)plane * g.nblocks + blk0;
-            const unsigned my_start = lane < nvalid ? bs[lane] : 0u;
-            const unsigned c_start = __shfl_sync(0xffffffffu, my_start, 0);
-            unsigned c_end = (blk0 + nvalid < g.nblocks) ? bs[nvalid] : (unsigned)len;
-            c_end = __shfl_sync(0xffffffffu, c_end, 0);
-            const unsigned long long addr0 = (unsigned long long)(uintptr_t)(stream + c_start);
-            const unsigned mis = (unsigned)(addr0 & 3ull);
-            // (a stream must lie inside the caller's buffer: device-supplied offsets are not trusted)
-            const bool ok = c_start <= c_end && c_end <= len && a.plane_off[plane] <= a.in_bytes && len <= a.in_bytes - a.plane_off[plane];
-            const uint32_t* wsrc = (const uint32_t*)(uintptr_t)(addr0 - mis);
-            const unsigned nwords = ok ? (((c_end - c_start) + mis + 3u) >> 2) : 0u;
+            FiBytes y;
+            locate(cur_k, y);
+            const unsigned my_start = cur_k.my_start, c_start = y.c_start, c_end = y.c_end, mis = y.mis, nwords = y.nwords;
+            const bool ok = y.ok;
+            const uint32_t* wsrc = y.wsrc;
             const bool staged = nwords <= STAGE_WORDS;
             // the chunk's bytes are staged in the ring slot that the next tile will use: the store issued
             // from it two tiles ago has to be done reading it
@@ -194,8 +222,16 @@ jb_inv_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FiKernelArgs 
                 if (lane == 0) ff_bulk_wait_read<FI_RING - 1>();
                 __syncwarp();
             }
-            if (ok && staged)
-                for (unsigned i = lane; i < nwords; i += 32) sbytes[i] = __ldg(wsrc + i);
+            if (ok && staged) {
+                if (pre_valid) {
+                    #pragma unroll
+                    for (int q = 0; q < FI_PRE_WORDS; ++q)
+                        if ((unsigned)(lane + 32 * q) < nwords) sbytes[lane + 32 * q] = pre[q];
+                    for (unsigned i = lane + 32 * FI_PRE_WORDS; i < nwords; i += 32) sbytes[i] = __ldg(wsrc + i);
+                } else {
+                    for (unsigned i = lane; i < nwords; i += 32) sbytes[i] = __ldg(wsrc + i);
+                }
+            }
             __syncwarp();
             int bad = ok ? 0 : 1;
             if (ok && lane < nvalid) {
@@ -207,12 +243,29 @@ jb_inv_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FiKernelArgs 
             }
             if (__any_sync(0xffffffffu, bad) && lane == 0) jb_set_error(a.status, JB_ERR_BAD_STREAM);
         }
+        // the ticket has landed by now: the loads of the next chunk's block offsets go out
+        next_chunk = a.ticket != nullptr ? __shfl_sync(0xffffffffu, pend, 0) : chunk + total_warps;
+        have_next = next_chunk < a.n_chunks;
+        if (have_next) describe(next_chunk, next_k);
+        auto prefetch_next = [&]() {                                    // (once per chunk, when the offsets are there)
+            next_located = true;
+            if (MODE == 2 || !have_next) return;
+            FiBytes ny;
+            locate(next_k, ny);
+            if (ny.ok && ny.nwords <= STAGE_WORDS) {
+                #pragma unroll
+                for (int q = 0; q < FI_PRE_WORDS; ++q)
+                    pre[q] = (unsigned)(lane + 32 * q) < ny.nwords ? __ldg(ny.wsrc + lane + 32 * q) : 0u;
+                next_pre = true;
+            }
+        };
         __syncwarp();
 
         // ---- 4 blocks per iteration ----
         FiCursor cur;
         cur.it = 0; cur.by = blk0 / g.hb; cur.bx = blk0 - cur.by * g.hb;
         for (int it = 0; it < nit; ++it) {
+            if (it == 3) prefetch_next();
             const int slot = (int)(store_seq % FI_RING);
             uint8_t* tile = ws.tile[slot];
             const int kind = ROWS ? 0 : fi_tile_kind(g, nvalid, cur, ka.aligned != 0);
@@ -349,6 +402,11 @@ jb_inv_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FiKernelArgs 
             }
             __syncwarp();                                     // the sample buffer is rewritten by the next chunk
         }
+        // ---- the pipeline moves on ----
+        if (!next_located) prefetch_next();                             // (a chunk of fewer than four iterations)
+        chunk = next_chunk;
+        cur_k = next_k;
+        pre_valid = next_pre;
     }
     if (!ROWS) {
         if (lane == 0) ff_bulk_wait_read<0>();

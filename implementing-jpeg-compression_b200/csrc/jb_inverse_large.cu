@@ -69,7 +69,15 @@ __device__ __forceinline__ int il_decode_block(const uint8_t* stream, uint32_t s
     const uint32_t nwords = (len - start + mis + 3u) >> 2;
     const uint32_t bitlimit = (len - start + mis) * 8u;
     uint32_t widx = 0, used = mis * 8u;
-    auto ld = [&](uint32_t i) -> uint32_t { return i < nwords ? jb_bswap32(__ldg(words + i)) : 0u; };
+    // the first IL_PRE words in one round trip (a heavily quantised block is 15-30 bytes: config 3), the rest on demand
+    constexpr uint32_t IL_PRE = 8;
+    uint32_t pw[IL_PRE];
+    #pragma unroll
+    for (uint32_t q = 0; q < IL_PRE; ++q) pw[q] = q < nwords ? __ldg(words + q) : 0u;
+    auto ld = [&](uint32_t i) -> uint32_t {
+        if (i < IL_PRE) return jb_bswap32(pw[i]);
+        return i < nwords ? jb_bswap32(__ldg(words + i)) : 0u;
+    };
     uint64_t buf = ld(widx++);
     int nb = 32 - (int)used;
     int count = 0;
@@ -160,17 +168,13 @@ jb_inv_large_kernel(const JbInvArgs a) {
     const bool fast_store_ok = aligned && bs >= 3 && bs <= 8 && a.row_pitch < (1u << 24);     // (32-bit offsets inside a chunk row)
 
     const unsigned total_warps = gridDim.x * NWARPS;
-    auto claim = [&](unsigned prev) -> unsigned {
-        if (a.ticket == nullptr) return prev + total_warps;
-        unsigned c = 0;
-        if (lane == 0) c = total_warps + atomicAdd(a.ticket, 1u);
-        return __shfl_sync(0xffffffffu, c, 0);
-    };
-    // (first chunk dealt statically, CTA-major: a single frame spreads over all SMs; the rest from the counter)
+    // (first chunk dealt statically, CTA-major: a single frame spreads over all SMs; the rest from the counter, whose
+    // answer is picked up only at the end of the chunk: the round trip of the atomic hides behind the work)
     unsigned next_chunk = blockIdx.x + gridDim.x * (unsigned)warp;
     while (next_chunk < a.n_chunks) {
         const unsigned chunk = next_chunk;
-        next_chunk = claim(chunk);
+        unsigned pend = 0;
+        if (a.ticket != nullptr && lane == 0) pend = total_warps + atomicAdd(a.ticket, 1u);
         const int plane = (int)(chunk / (unsigned)g.cpp);
         const int blk0 = (int)(chunk % (unsigned)g.cpp) * cb;
         const int nvalid = jb_min(cb, g.nblocks - blk0);
@@ -353,6 +357,7 @@ jb_inv_large_kernel(const JbInvArgs a) {
             }
         }
         __syncwarp();                                            // the sample buffer is rewritten by the next chunk
+        next_chunk = a.ticket != nullptr ? __shfl_sync(0xffffffffu, pend, 0) : chunk + total_warps;
     }
     jb_dec_epilogue(a);
 }

@@ -101,7 +101,8 @@ typedef struct jb_geometry {
     int32_t vb, hb;            /* blocks down / across                             */
     int32_t blocks_per_plane;  /* vb * hb                                          */
     int32_t max_block_bytes;   /* ceil((23 d^2 + 8) / 8): worst case of one block  */
-    int32_t chunks_per_plane;  /* scheduling units: ceil(blocks_per_plane / 32), / 8 for dct_size >= 16 */
+    int32_t chunks_per_plane;  /* scheduling units: ceil(blocks_per_plane / 32), / 8 for dct_size >= 16 (informational:
+                                * calls of at most 16384 large blocks are dealt in units of 2) */
     int32_t reserved;
 } jb_geometry;
 
