@@ -738,3 +738,24 @@ def test_large_block_calls_of_either_chunk_size_agree(jb, h, w, bs, d, qn, qp, n
     check_quantised(coeffs, rp.quantised_zigzag(p64, ocfg), rp.prerounding_zigzag(p64, ocfg), what="chunks")
     assert batch[0] == rp.pack_blocks(coeffs.reshape(-1, d * d))
     check_pixels(rec[0], rp.decompress_band(batch[0], ocfg), p64, what="chunks")
+
+
+def test_small_and_large_call_tails_agree_at_the_threshold(jb):
+    """Calls of up to 2048 chunks end with one scan-and-gather kernel, larger ones with the scan and the gather
+    kernels: 256 planes of 512 x 512 are exactly 2048 chunks, 257 planes one more plane's worth."""
+    h = w = 512
+    cfg, ocfg = _cfgs(jb, (h, w, 4, 8, "DCT", "qtable", None))
+    base = [synth_plane(h, w, 500 + k).astype(np.uint8) for k in range(4)]
+    planes = [np.roll(base[k % 4], 13 * k, axis=0) for k in range(257)]
+    small = jb.compress_bands(planes[:256], cfg)          # 2048 chunks
+    large = jb.compress_bands(planes, cfg)                # 2056 chunks
+    assert large[:256] == small
+    for k in (0, 255, 256):
+        assert large[k] == jb.compress_band(planes[k], cfg)
+    coeffs = jb.stages.forward_coefficients(planes[256], cfg)[0]
+    p64 = planes[256].astype(np.int64)
+    check_quantised(coeffs, rp.quantised_zigzag(p64, ocfg), rp.prerounding_zigzag(p64, ocfg), what="threshold")
+    assert large[256] == rp.pack_blocks(coeffs.reshape(-1, 64))
+    rec = jb.decompress_bands(large, cfg)
+    check_pixels(rec[256], rp.decompress_band(large[256], ocfg), p64, what="threshold")
+    assert np.array_equal(rec[:256], jb.decompress_bands(small, cfg))
