@@ -273,6 +273,8 @@ def run_ours(args, rank, world, local_rank):
     i0, i1 = jb.sharding.image_slice(N_IMAGES, rank, world)
     n_img = i1 - i0
     n_planes = 3 * n_img
+    if args.streams == 0:
+        args.streams = 4 if n_img <= 256 else 3
     cfg = jb.Configuration(width=W, height=H, block_size=BS, dct_size=D, transform=TRANSFORM,
                            quantization=jb.QuantizationMethod(QNAME))
     bc = jb.BatchCodec(cfg, n_planes, device=device, flags=(jb._lib.JB_FLAG_PDL if args.pdl else 0))
@@ -697,8 +699,10 @@ def main():
                     help="launch the kernels without programmatic dependent launch (JB_FLAG_PDL is the default)")
     ap.add_argument("--call-graphs", dest="step_graph", action="store_false",
                     help="time one CUDA graph per library call instead of one per step (compress + decompress)")
-    ap.add_argument("--streams", type=int, default=3, choices=[1, 2, 3, 4],
-                    help="n > 1: consecutive steps take turns on n codec objects, each on its own CUDA stream (default 3); 1: one stream")
+    ap.add_argument("--streams", type=int, default=0, choices=[0, 1, 2, 3, 4],
+                    help="n > 1: consecutive steps take turns on n codec objects, each on its own CUDA stream; 1: one stream; "
+                         "0 (default): 3, or 4 when a rank holds at most 256 images (measured: 2.38 against 2.41 ms per step "
+                         "at 1024 images with 3 / 4 streams, 0.331 against 0.327 ms at 128)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
     args = ap.parse_args()
