@@ -49,13 +49,6 @@ struct FfCtaSmem {
     double B64[64];
 };
 
-// fp64 re-evaluation of coefficient (u, v) from the 8x8 box sums of one block (jb_refine.cuh); out of line and
-// with few operands: the fused kernel pays nothing for it in registers.
-template <bool DFT>
-__device__ __noinline__ double ff_refine8(const float* X, int u, int v, const FfCtaSmem& cs, int qmode, double recip) {
-    return jb_refine_f64(X, u, v, 8, 4, DFT ? JB_TRANSFORM_DFT : JB_TRANSFORM_DCT, qmode, cs.A64, cs.B64, recip);
-}
-
 // ---- tile staging -----------------------------------------------------------------------------
 // kind 0: the 32 x 128 tile lies inside the image, rows 16-byte aligned  -> TMA (LDG.128 when TMA is off)
 // kind 1: same columns, but rows run past the bottom edge              -> LDG.128 with replicated rows
@@ -423,50 +416,41 @@ jb_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfKernelArgs 
                 sc[h0] = h0 ? make_float4(x[4], x[5], x[6], x[7]) : make_float4(x[0], x[1], x[2], x[3]);
                 sc[h0 ^ 1] = h0 ? make_float4(x[0], x[1], x[2], x[3]) : make_float4(x[4], x[5], x[6], x[7]);
                 __syncwarp();
-                // The DFT's other positions: one coefficient at a time by the whole warp (jb_pf_fft2_8x8_warp), the lanes
-                // taking turns -- a lane on its own would keep the other 31 waiting ten times as long.
-                if (DFT) {
-                    unsigned pend = 0;
-                    #pragma unroll
-                    for (int u = 0; u < 8; ++u)
-                        if ((nearmask >> u & 1u) && (((u | v) & 1) != 0)) pend |= 1u << u;
-                    nearmask &= ~pend;
-                    for (;;) {
-                        const unsigned have = __ballot_sync(0xffffffffu, pend != 0);
-                        if (!have) break;
-                        const int L = __ffs((int)have) - 1;
-                        const int u = __ffs((int)__shfl_sync(0xffffffffu, pend, L)) - 1;
-                        const int vL = __shfl_sync(0xffffffffu, v, L);
-                        const double F = jb_pf_fft2_8x8_warp(ws.scr + (L & 3) * FF_BLK_W, u, vL);
-                        if (lane == L) {
-                            const double recip = a.t.qrecip[u * 8 + v];
-                            const double f64 = g.qmode == JB_Q_QTABLE ? __dmul_rn(F, recip) : g.qmode == JB_Q_DIVIDE ? __ddiv_rn(F, recip) : F;
-                            const int q = (int)rint(f64);
-                            #pragma unroll
-                            for (int uu = 0; uu < 8; ++uu) if (uu == u) qi[uu] = q;
-                            pend &= pend - 1u;
-                        }
+                // Where every twiddle is 0 or +-1 -- the DC term of the DCT; rows and columns 0, 2, 4, 6 of the DFT -- the
+                // reference's float64 transform is an exact sum of the box means, and so is y[u] (integers below 2^24):
+                // only the quantiser step has to be redone in float64.  These are the positions where exact ties are
+                // common (K/256 for the DC term).  The other positions: one coefficient at a time
+                // by the whole warp (jb_pf_fft2_8x8_warp / jb_dct2_8x8_warp), the lanes taking turns -- a lane on its own
+                // would keep the other 31 waiting five to ten times as long (5 % of the DCT kernel's instructions).
+                unsigned pend = 0;
+                #pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if ((nearmask >> u & 1u) && (DFT ? (((u | v) & 1) != 0) : ((u | v) != 0))) pend |= 1u << u;
+                nearmask &= ~pend;
+                for (;;) {
+                    const unsigned have = __ballot_sync(0xffffffffu, pend != 0);
+                    if (!have) break;
+                    const int L = __ffs((int)have) - 1;
+                    const int u = __ffs((int)__shfl_sync(0xffffffffu, pend, L)) - 1;
+                    const int vL = __shfl_sync(0xffffffffu, v, L);
+                    const float* XL = ws.scr + (L & 3) * FF_BLK_W;
+                    const double F = DFT ? jb_pf_fft2_8x8_warp(XL, u, vL) : jb_dct2_8x8_warp(XL, u, vL, cs.A64);
+                    if (lane == L) {
+                        const double recip = a.t.qrecip[u * 8 + v];
+                        const double f64 = g.qmode == JB_Q_QTABLE ? __dmul_rn(F, recip) : g.qmode == JB_Q_DIVIDE ? __ddiv_rn(F, recip) : F;
+                        const int q = (int)rint(f64);
+                        #pragma unroll
+                        for (int uu = 0; uu < 8; ++uu) if (uu == u) qi[uu] = q;
+                        pend &= pend - 1u;
                     }
                 }
                 if (nearmask) {
-                    const float* X = ws.scr + lb * FF_BLK_W;
                     #pragma unroll
                     for (int u = 0; u < 8; ++u)
                         if (nearmask >> u & 1u) {
-                            // Where every twiddle is 0 or +-1 -- the DC term of the DCT; rows and columns 0, 2, 4, 6 of the
-                            // DFT -- the reference's float64 transform is an exact sum of the box means, and so is y[u]
-                            // (integers below 2^24): only the quantiser step has to be redone in float64.  These are the
-                            // positions where exact ties are common (K/256 for the DC term).
-                            const bool exact = DFT ? (((u | v) & 1) == 0) : ((u | v) == 0);
                             const double recip = a.t.qrecip[u * 8 + v];
-                            double f64;
-                            if (exact) {
-                                const double F = __dmul_rn((double)y[u], 0.0625);
-                                f64 = g.qmode == JB_Q_QTABLE ? __dmul_rn(F, recip) : g.qmode == JB_Q_DIVIDE ? __ddiv_rn(F, recip) : F;
-                            } else {
-                                // (DCT only: the DFT's inexact positions were taken by the warp above)
-                                f64 = DFT ? 0.0 : ff_refine8<false>(X, u, v, cs, g.qmode, recip);
-                            }
+                            const double F = __dmul_rn((double)y[u], 0.0625);
+                            const double f64 = g.qmode == JB_Q_QTABLE ? __dmul_rn(F, recip) : g.qmode == JB_Q_DIVIDE ? __ddiv_rn(F, recip) : F;
                             qi[u] = (int)rint(f64);
                         }
                 }

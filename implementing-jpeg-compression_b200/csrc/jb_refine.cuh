@@ -81,6 +81,22 @@ static __device__ __noinline__ double jb_pf_fft2_8x8_warp(const float* X, int u,
     return y;
 }
 
+// The DCT of one 8 x 8 block (block_size 4) at (u, v) by a whole warp, in the order of jb_refine_f64's DCT branch: lane i
+// (and its copies) sums row i against C[v] term by term in ascending j, multiplies by C[u][i], and the eight terms are
+// added in ascending i.  Every lane must call; every lane gets the value.  ~60 instructions against ~300 for one lane
+// on its own with 31 waiting.  A64: the fp64 matrix (shared or global memory).
+static __device__ __noinline__ double jb_dct2_8x8_warp(const float* X, int u, int v, const double* A64) {
+    const int i = threadIdx.x & 7;
+    double m = __dmul_rn(__dmul_rn((double)X[i * 8], 0.0625), A64[v * 8]);
+    #pragma unroll
+    for (int j = 1; j < 8; ++j) m = __dadd_rn(m, __dmul_rn(__dmul_rn((double)X[i * 8 + j], 0.0625), A64[v * 8 + j]));
+    const double term = __dmul_rn(m, A64[u * 8 + i]);
+    double y = __shfl_sync(0xffffffffu, term, 0);
+    #pragma unroll
+    for (int r = 1; r < 8; ++r) y = __dadd_rn(y, __shfl_sync(0xffffffffu, term, r));
+    return y;
+}
+
 // X: the d x d box sums of the block (exact integers, as int or float; anything indexable by i * d + j); returns the value the reference hands to
 // np.round for coefficient (u, v).  A64 / B64: the fp64 transform matrices of jb_tables.cu; recip: qrecip[u*d+v].
 // (Inlined into a small __noinline__ wrapper per kernel file, so that the hot kernels see a call with few operands.)
